@@ -1,0 +1,376 @@
+// elem_math.cuh -- per-element arithmetic of the VMS Navier-Stokes weak form on linear tets, written for
+// registers: closed-form geometry, gather, interpolation, residual (F) and the hoisted Jacobian (J) blocks.
+//
+// What it restates (reference paths relative to /root/reference/src):
+//   assemble.cu:321-357,1245-1291  J, J^-1 (batched LU there, cofactors here), detJ = |det J|
+//   assemble.cu:1308-1328          shape gradients      sh[a][d] = dN_a/dx_d
+//   assemble.cu:1586-1593          metric               G = Jinv * Jinv^T
+//   assemble.cu:135-154,1601-1693  nodal gather + interpolation to the 4 quadrature points
+//   assemble.cu:444-484,761-924    GetStabTau + AssembleWeakFormKernel<TENSOR=1>   (element residual)
+//   assemble.cu:495-759            AssembleWeakFormLHSKernel                      (element Jacobian, u-p 4x4)
+//   assemble.cu:279-319,1038-1214  face normal (Nanson) + FaceAssemblyKernel
+//
+// The reference evaluates the Jacobian with a 4-point quadrature loop per (a,b) pair (~190 flop per (a,b,q)).
+// For linear tets grad N is constant and N_a(q) = SB + (SA-SB)*[a==q], so every q-sum collapses to a few
+// per-element vectors (P, R, t) -- see JPrep/jac_block below: ~50 flop per (a,b) block instead of ~760.
+// The re-association changes results at the 1e-16 level (parity bound: 1e-12).
+//
+// All functions are __host__ __device__ so that tests can probe the very same arithmetic on the CPU
+// (tests/cpu_probe); the product only ever calls them from kernels.
+#pragma once
+#include <math.h>
+
+#ifndef __CUDACC__
+#define __host__
+#define __device__
+#define __forceinline__ inline
+#endif
+#define DFB_HD __host__ __device__ __forceinline__
+
+namespace dfb {
+namespace em {
+
+typedef double f64;
+
+constexpr f64 RHOC = 0.5, DT = 5e-2;
+constexpr f64 ALPHAM = (3.0 - RHOC) / (1.0 + RHOC);
+constexpr f64 ALPHAF = 1.0 / (1.0 + RHOC);
+constexpr f64 GAMMA = 0.5 + ALPHAM - ALPHAF;
+constexpr f64 RHO = 1.0e3, CP = 1.0, KAPPA = 0.66, MU = 10.0 / 3.0;
+constexpr f64 GW = 0.0416666666666667;
+constexpr f64 SA = 0.5854101966249685, SB = 0.1381966011250105, SD = SA - SB;
+constexpr f64 SN = SA + 3.0 * SB;  // sum_q N_b(q)
+constexpr f64 FACT1 = ALPHAM, FACT2 = DT * ALPHAF * GAMMA;
+constexpr f64 FB0 = 0.0, FB1 = 0.0, FB2 = -9.81 * 0.0;  // body force, assemble.cu:42
+constexpr f64 GWB = 0.1666666666666667;                // face rule, assemble.cu:86
+constexpr f64 T6 = 0.1666666666666667, T3 = 0.6666666666666667;
+
+DFB_HD f64 shl(int a, int q) { return a == q ? SA : SB; }
+DFB_HD f64 rsqrt_(f64 x) {
+#ifdef __CUDA_ARCH__
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
+struct Geom {
+  f64 sh[4][3];  // dN_a/dx_d
+  f64 inv[3][3]; // Jinv(i,j) = d xi_i / d x_j
+  f64 detJ;      // |det J|
+};
+
+// x[a][d] : coordinates of the 4 vertices
+DFB_HD void geometry(const f64 x[4][3], Geom& g) {
+  f64 c0[3], c1[3], c2[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    c0[d] = x[1][d] - x[0][d];
+    c1[d] = x[2][d] - x[0][d];
+    c2[d] = x[3][d] - x[0][d];
+  }
+  // rows of the inverse are the cross products of the columns of J divided by det
+  f64 r0[3] = {c1[1] * c2[2] - c1[2] * c2[1], c1[2] * c2[0] - c1[0] * c2[2], c1[0] * c2[1] - c1[1] * c2[0]};
+  f64 r1[3] = {c2[1] * c0[2] - c2[2] * c0[1], c2[2] * c0[0] - c2[0] * c0[2], c2[0] * c0[1] - c2[1] * c0[0]};
+  f64 r2[3] = {c0[1] * c1[2] - c0[2] * c1[1], c0[2] * c1[0] - c0[0] * c1[2], c0[0] * c1[1] - c0[1] * c1[0]};
+  f64 det = c0[0] * r0[0] + c0[1] * r0[1] + c0[2] * r0[2];
+  f64 idet = 1.0 / det;
+  g.detJ = fabs(det);
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    g.inv[0][d] = r0[d] * idet;
+    g.inv[1][d] = r1[d] * idet;
+    g.inv[2][d] = r2[d] * idet;
+    g.sh[1][d] = g.inv[0][d];
+    g.sh[2][d] = g.inv[1][d];
+    g.sh[3][d] = g.inv[2][d];
+    g.sh[0][d] = -g.inv[0][d] - g.inv[1][d] - g.inv[2][d];
+  }
+}
+
+// G(i,j) = sum_d Jinv(i,d) Jinv(j,d)   (assemble.cu:1586-1593)
+DFB_HD void metric(const Geom& g, f64 G[3][3]) {
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) G[i][j] = g.inv[i][0] * g.inv[j][0] + g.inv[i][1] * g.inv[j][1] + g.inv[i][2] * g.inv[j][2];
+}
+
+// ------------------------------------------------------------------------------------------
+// residual.  val[comp][a]: nodal values; comp 0..2 = u (wgalpha), 3 = p (dwgalpha slot 3, defect D6),
+// 4 = phi, 5 = T (wgalpha);  dval[comp][a]: nodal rates from dwgalpha.  eF[a][ii].
+// ------------------------------------------------------------------------------------------
+DFB_HD void residual(const Geom& g, const f64 val[6][4], const f64 dval[6][4], f64 eF[4][6]) {
+  f64 G[3][3];
+  metric(g, G);
+  f64 grad[6][3];
+#pragma unroll
+  for (int c = 0; c < 6; c++)
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+      grad[c][d] = g.sh[0][d] * val[c][0] + g.sh[1][d] * val[c][1] + g.sh[2][d] * val[c][2] + g.sh[3][d] * val[c][3];
+  f64 gg = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) gg += G[i][j] * G[i][j];
+  const f64 tr = G[0][0] + G[1][1] + G[2][2];
+  const f64 nu = MU / RHO, al = KAPPA / (RHO * CP);
+  const f64 divu = grad[0][0] + grad[1][1] + grad[2][2];
+  const f64 t0 = 4.0 / (DT * DT);
+  const f64 fb[3] = {FB0, FB1, FB2};
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int i = 0; i < 6; i++) eF[a][i] = 0.0;
+  const f64 wdet = GW * g.detJ;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    f64 vq[6], dq[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      vq[c] = shl(0, q) * val[c][0] + shl(1, q) * val[c][1] + shl(2, q) * val[c][2] + shl(3, q) * val[c][3];
+      dq[c] = shl(0, q) * dval[c][0] + shl(1, q) * dval[c][1] + shl(2, q) * dval[c][2] + shl(3, q) * dval[c][3];
+    }
+    const f64 u0 = vq[0], u1 = vq[1], u2 = vq[2];
+    const f64 uadv[3] = {u0, u1, u2};
+    f64 rLi[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      rLi[i] = RHO * (dq[i] - fb[i]) + RHO * u0 * grad[i][0] + RHO * u1 * grad[i][1] + RHO * u2 * grad[i][2] + grad[3][i];
+    // GetStabTau (assemble.cu:444-484)
+    f64 t1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) t1 += G[i][j] * uadv[i] * uadv[j];
+    const f64 tauM = rsqrt_(t0 + t1 + 3.0 * nu * nu * gg) / RHO;
+    const f64 tauC = sqrt(t1 + 3.0 * nu * nu * gg) / tr;
+    const f64 tauP = rsqrt_(t0 + t1);
+    const f64 tauT = rsqrt_(t0 + t1 + 3.0 * al * al * gg) / (RHO * CP);
+    f64 shconv[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) shconv[a] = u0 * g.sh[a][0] + u1 * g.sh[a][1] + u2 * g.sh[a][2];
+    f64 tmp0[3], tmp1[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      tmp0[i] = RHO * (dq[i] - fb[i]) + RHO * (u0 - tauM * rLi[0]) * grad[i][0] + RHO * (u1 - tauM * rLi[1]) * grad[i][1] +
+                RHO * (u2 - tauM * rLi[2]) * grad[i][2];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+        tmp1[i][j] = MU * (grad[i][j] + grad[j][i]) + RHO * tauM * rLi[i] * uadv[j] - RHO * tauM * tauM * rLi[i] * rLi[j];
+    const f64 pd = -vq[3] + RHO * tauC * divu;
+    tmp1[0][0] += pd;
+    tmp1[1][1] += pd;
+    tmp1[2][2] += pd;
+    const f64 bp = dq[4] + u0 * grad[4][0] + u1 * grad[4][1] + u2 * grad[4][2];
+    const f64 btc = RHO * CP * (dq[5] + u0 * grad[5][0] + u1 * grad[5][1] + u2 * grad[5][2]);
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const f64 Na = shl(a, q);
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        f64 bm = Na * tmp0[i] + g.sh[a][0] * tmp1[i][0] + g.sh[a][1] * tmp1[i][1] + g.sh[a][2] * tmp1[i][2];
+        eF[a][i] += bm * wdet;
+      }
+      f64 bc = Na * divu + tauM * rLi[0] * g.sh[a][0] + tauM * rLi[1] * g.sh[a][1] + tauM * rLi[2] * g.sh[a][2];
+      eF[a][3] += bc * wdet;
+      eF[a][4] += bp * (Na + tauP * shconv[a]) * wdet;
+      f64 bt = btc * (Na + RHO * CP * tauT * shconv[a]) +
+               KAPPA * (grad[5][0] * g.sh[a][0] + grad[5][1] * g.sh[a][1] + grad[5][2] * g.sh[a][2]);
+      eF[a][5] += bt * wdet;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Jacobian, hoisted form.
+// ------------------------------------------------------------------------------------------
+struct JPrep {
+  f64 w;         // detJ * gw
+  f64 c[4][4];   // c[q][a] = u(q) . grad N_a          (shconv of assemble.cu:574-583)
+  f64 t[4][4];   // t[q][a] = tauM(q) * c[q][a]
+  f64 tM[4];     // tauM(q)
+  f64 P[4];      // P[a] = sum_q t[q][a]
+  f64 R[4];      // R[b] = sum_q c[q][b]
+  f64 sTM, sTC;  // sum_q tauM(q), sum_q tauC(q)
+};
+
+// u[a][d]: nodal advection velocity (wgalpha u-part)
+DFB_HD void jac_prep(const Geom& g, const f64 u[4][3], JPrep& p) {
+  f64 G[3][3];
+  metric(g, G);
+  f64 gg = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) gg += G[i][j] * G[i][j];
+  const f64 itr = 1.0 / (G[0][0] + G[1][1] + G[2][2]);
+  const f64 nu = MU / RHO;
+  p.w = g.detJ * GW;
+  p.sTM = 0.0;
+  p.sTC = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; a++) { p.P[a] = 0.0; p.R[a] = 0.0; }
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    f64 uq[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) uq[d] = shl(0, q) * u[0][d] + shl(1, q) * u[1][d] + shl(2, q) * u[2][d] + shl(3, q) * u[3][d];
+#pragma unroll
+    for (int a = 0; a < 4; a++) p.c[q][a] = g.sh[a][0] * uq[0] + g.sh[a][1] * uq[1] + g.sh[a][2] * uq[2];
+    // tau of the LHS kernel: sum_{a=1..3} (u.gradN_a)^2 instead of u.G.u (defect D5), assemble.cu:592-602
+    const f64 tmp = p.c[q][1] * p.c[q][1] + p.c[q][2] * p.c[q][2] + p.c[q][3] * p.c[q][3];
+    const f64 tauM = rsqrt_(4.0 / (DT * DT) + tmp + 3.0 * nu * nu * gg) / RHO;
+    const f64 tauC = sqrt(tmp + 3.0 * nu * nu * gg) * itr;
+    p.tM[q] = tauM;
+    p.sTM += tauM;
+    p.sTC += tauC;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      p.t[q][a] = tauM * p.c[q][a];
+      p.P[a] += p.t[q][a];
+      p.R[a] += p.c[q][a];
+    }
+  }
+}
+
+// 4x4 (u,p) block of node pair (a,b): blk[ii*4+jj]
+DFB_HD void jac_block(const Geom& g, const JPrep& p, int a, int b, f64 blk[16]) {
+  const f64* ga = g.sh[a];
+  const f64* gb = g.sh[b];
+  const f64 eK = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
+  const f64 mab = (a == b) ? (SA * SA + 3.0 * SB * SB) : (2.0 * SA * SB + 2.0 * SB * SB);
+  const f64 stc = p.t[0][a] * p.c[0][b] + p.t[1][a] * p.c[1][b] + p.t[2][a] * p.c[2][b] + p.t[3][a] * p.c[3][b];
+  const f64 T = p.w * (FACT1 * RHO * mab + FACT1 * RHO * RHO * (SB * p.P[a] + SD * p.t[b][a]) +
+                       FACT2 * RHO * (SB * p.R[b] + SD * p.c[a][b]) + FACT2 * RHO * RHO * stc + 4.0 * FACT2 * MU * eK);
+  const f64 k1 = 4.0 * p.w * FACT2 * MU;          // viscous transpose term
+  const f64 k2 = p.w * FACT2 * RHO * p.sTC;       // grad-div (tauC) term
+#pragma unroll
+  for (int ii = 0; ii < 3; ii++)
+#pragma unroll
+    for (int jj = 0; jj < 3; jj++) blk[ii * 4 + jj] = k1 * ga[jj] * gb[ii] + k2 * ga[ii] * gb[jj] + (ii == jj ? T : 0.0);
+  const f64 k3 = p.w * SN, k4 = RHO * p.w * p.P[a];
+  const f64 k5 = p.w * RHO * (FACT1 * (SB * p.sTM + SD * p.tM[b]) + FACT2 * p.P[b]);
+  const f64 k6 = FACT2 * p.w * SN;
+#pragma unroll
+  for (int ii = 0; ii < 3; ii++) {
+    blk[ii * 4 + 3] = -k3 * ga[ii] + k4 * gb[ii];   // dRM/dP
+    blk[3 * 4 + ii] = k5 * ga[ii] + k6 * gb[ii];    // dRC/dU
+  }
+  blk[15] = p.w * p.sTM * eK;                       // dRC/dP
+}
+
+// ------------------------------------------------------------------------------------------
+// boundary face (weak BC).  iorn = local index of the vertex opposite the face.
+// val[comp][a]: comp 0..2 = u (wgalpha), 3 = p (dwgalpha slot 3).
+// ------------------------------------------------------------------------------------------
+DFB_HD f64 shlub(int iorn, int q, int a) {
+  // c_shlub[iorn*12 + q*4 + a], assemble.cu:87-102: 0 on the opposite vertex, 2/3 on the "peak" face vertex of
+  // quadrature point q, 1/6 on the other two.  Peak vertex table [iorn][q] = {3,2,1},{3,2,0},{0,1,3},{1,2,0},
+  // packed 2 bits per entry.
+  if (a == iorn) return 0.0;
+  const unsigned PK = 0x2742dbu;
+  int pk = (int)((PK >> (2 * (iorn * 3 + q))) & 3u);
+  return a == pk ? T3 : T6;
+}
+
+struct FacePrep {
+  f64 nv[3];
+  f64 tau_b;
+};
+
+DFB_HD void face_prep(const Geom& g, int iorn, FacePrep& f) {
+  // c_nv2 (assemble.cu:114-118) and Nanson: nv = detJ * Jinv^T n_ref
+  const f64 nref[3] = {iorn == 0 ? 1.0 : (iorn == 1 ? -1.0 : 0.0), iorn == 0 ? 1.0 : (iorn == 2 ? -1.0 : 0.0),
+                       iorn == 0 ? 1.0 : (iorn == 3 ? -1.0 : 0.0)};
+#pragma unroll
+  for (int n = 0; n < 3; n++) f.nv[n] = (g.inv[0][n] * nref[0] + g.inv[1][n] * nref[1] + g.inv[2][n] * nref[2]) * g.detJ;
+  f64 h = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    f64 v = g.inv[i][0] * f.nv[0] + g.inv[i][1] * f.nv[1] + g.inv[i][2] * f.nv[2];
+    h += v * v;
+  }
+  f.tau_b = 4.0 * MU * sqrt(h);
+}
+
+DFB_HD void face_residual(const Geom& g, const FacePrep& f, int iorn, const f64 val[4][4], f64 eF[4][6]) {
+  f64 grad[4][3];
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+      grad[c][d] = g.sh[0][d] * val[c][0] + g.sh[1][d] * val[c][1] + g.sh[2][d] * val[c][2] + g.sh[3][d] * val[c][3];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int i = 0; i < 6; i++) eF[a][i] = 0.0;
+  const f64* nv = f.nv;
+  for (int q = 0; q < 3; q++) {
+    f64 N[4], vq[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) N[a] = shlub(iorn, q, a);
+#pragma unroll
+    for (int c = 0; c < 4; c++) vq[c] = N[0] * val[c][0] + N[1] * val[c][1] + N[2] * val[c][2] + N[3] * val[c][3];
+    const f64 unor = vq[0] * nv[0] + vq[1] * nv[1] + vq[2] * nv[2];
+    const f64 uneg = (unor - fabs(unor)) * 0.5;
+    f64 tmp0[3], tmp1[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      tmp0[i] = nv[i] * vq[3] - MU * (nv[0] * grad[i][0] + nv[1] * grad[i][1] + nv[2] * grad[i][2]) -
+                MU * (nv[0] * grad[0][i] + nv[1] * grad[1][i] + nv[2] * grad[2][i]) - RHO * uneg * vq[i] + f.tau_b * vq[i];
+#pragma unroll
+      for (int j = 0; j < 3; j++) tmp1[i][j] = -MU * (nv[i] * vq[j] + nv[j] * vq[i]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        f64 bm = N[a] * tmp0[i] + g.sh[a][0] * tmp1[i][0] + g.sh[a][1] * tmp1[i][1] + g.sh[a][2] * tmp1[i][2];
+        eF[a][i] += bm * GWB;
+      }
+      eF[a][3] -= N[a] * unor * GWB;
+    }
+  }
+}
+
+// 4x4 block of pair (a,b) of the face Jacobian (assemble.cu:1127-1192); u[a][d] nodal velocity
+DFB_HD void face_block(const Geom& g, const FacePrep& f, int iorn, const f64 u[4][3], int a, int b, f64 blk[16]) {
+  const f64* nv = f.nv;
+  const f64 sna = g.sh[a][0] * nv[0] + g.sh[a][1] * nv[1] + g.sh[a][2] * nv[2];
+  const f64 snb = g.sh[b][0] * nv[0] + g.sh[b][1] * nv[1] + g.sh[b][2] * nv[2];
+#pragma unroll
+  for (int i = 0; i < 16; i++) blk[i] = 0.0;
+  for (int q = 0; q < 3; q++) {
+    f64 N[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) N[k] = shlub(iorn, q, k);
+    f64 uq[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) uq[d] = N[0] * u[0][d] + N[1] * u[1][d] + N[2] * u[2][d] + N[3] * u[3][d];
+    const f64 unor = uq[0] * nv[0] + uq[1] * nv[1] + uq[2] * nv[2];
+    const f64 uneg = (unor - fabs(unor)) * 0.5;
+    const f64 Na = N[a], Nb = N[b];
+    f64 t0 = -MU * (snb * Na + sna * Nb) - RHO * Na * Nb * uneg + f.tau_b * Na * Nb;
+    const f64 d = FACT2 * t0 * GWB;
+#pragma unroll
+    for (int ii = 0; ii < 3; ii++)
+#pragma unroll
+      for (int jj = 0; jj < 3; jj++) {
+        f64 t = -MU * Na * g.sh[b][ii] * nv[jj] - MU * Nb * g.sh[a][jj] * nv[ii];
+        blk[ii * 4 + jj] += FACT2 * t * GWB + (ii == jj ? d : 0.0);
+      }
+    const f64 nn = Na * Nb;
+#pragma unroll
+    for (int ii = 0; ii < 3; ii++) {
+      blk[3 * 4 + ii] -= FACT2 * nn * nv[ii] * GWB;
+      blk[ii * 4 + 3] += nn * nv[ii] * GWB;
+    }
+  }
+}
+
+}  // namespace em
+}  // namespace dfb

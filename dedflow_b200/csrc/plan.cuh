@@ -1,0 +1,28 @@
+// plan.cuh -- the integer "assembly plan" of one mesh, built once (setup.cu) and reused by every assembly.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+struct dfb_plan {
+  int N = 0, E = 0;
+  const int* ien = nullptr;      // [4E] borrowed
+  const int* row_ptr = nullptr;  // [N+1] nodal pattern, borrowed
+  const int* col_ind = nullptr;  // [nnz] borrowed
+  int* v2c_ptr = nullptr;        // [N+1] offsets into v2c
+  int* v2c = nullptr;            // [4E] corner ids (e*4+a) of every node, ascending
+  u8* slot = nullptr;            // [16E] slot[(e*4+a)*4+b] = position of ien[e,b] in nodal row ien[e,a]
+  int max_valence = 0;           // max corners per node
+  int max_row_len = 0;           // max nodal row length
+  // color batches (only for DFB_MODE_COLORED)
+  int num_batch = 0;
+  std::vector<int> batch_offset;
+  const int* batch_ind = nullptr;  // borrowed
+  // lazily allocated element-residual scratch for the deterministic F gather (24 doubles per element)
+  mutable f64* elemF = nullptr;
+  mutable size_t elemF_bytes = 0;
+};
+
+namespace dfb {
+int build_v2c(int N, int E, const int* d_ien, int** d_ptr_out, int** d_v2c_out, cudaStream_t st);
+}

@@ -1,0 +1,155 @@
+/*
+ * dedflow_b200.h -- C ABI of the B200-native FEM linear-system hot path (libdedflow_b200.so).
+ *
+ * Two layers, both extern "C", plain pointers and sizes only (no torch / C++ types):
+ *
+ *  (1) the CORE ABI (dfb_*): stateless kernels on raw DEVICE pointers plus two opaque handles
+ *      (dfb_plan: integer assembly plan of one mesh; dfb_gmres: persistent Krylov workspace).
+ *      Every function returns 0 on success or a negative dfb_status; dfb_last_error() gives
+ *      the message.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream,
+ *      the stream the reference runs on).
+ *
+ *  (2) the DROP-IN ABI: the reference's own entry points with the reference's struct layouts
+ *      (declared in dedflow_compat.h) implemented on top of (1), so that reference src/main.c,
+ *      Mesh.c, MeshData.c link against this library unchanged.
+ *
+ * Conventions shared with the reference: index = int32, value = double;
+ * xg[3N] interleaved; ien[4E]; every state / Krylov vector has 6N entries laid out
+ * [u: N x 3 interleaved | p: N | phi: N | T: N]  (reference src/main.c:297-319).
+ * The field-split matrix is four scalar-CSR value arrays over the nodal pattern (row_ptr,col_ind):
+ *   A00 (3x3): val[start*9 + ii*3*len + k*3 + jj]     A01 (3x1): val[start*3 + ii*len + k]
+ *   A10 (1x3): val[start*3 + k*3 + jj]                A11 (1x1): val[start + k]
+ * with start=row_ptr[i], len=row_ptr[i+1]-start, k the position of the column inside the nodal row
+ * (reference src/csr_impl.cu:24-59, src/matrix_impl.cu:370-453).
+ */
+#ifndef DEDFLOW_B200_H
+#define DEDFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum dfb_status {
+  DFB_OK = 0,
+  DFB_ERR_CUDA = -1,      /* a CUDA runtime call failed */
+  DFB_ERR_ARG = -2,       /* bad argument */
+  DFB_ERR_OVERFLOW = -3,  /* nodal row longer than 64 (reference csr.c:10,64 asserts) or i32 index overflow */
+  DFB_ERR_COLOR = -4,     /* more than max_color rounds needed */
+  DFB_ERR_NODEVICE = -5   /* no CUDA device: there is no CPU fallback */
+} dfb_status;
+
+const char* dfb_last_error(void);
+int dfb_version(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+long long dfb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Sparsity pattern.  Replaces CSRAttrCreate (reference src/csr.c:143-190, host, single thread)
+ * and ExpandCSRByBlockSize (src/csr_impl.cu:126-156).
+ * ------------------------------------------------------------------------------------------ */
+/* row_ptr[N+1] (device, out) of the scalar nodal pattern: row i = sorted unique {i} U neighbours. *nnz (host, out). */
+int dfb_pattern_rows(int num_node, int num_tet, const int* d_ien, int* d_row_ptr, int* nnz, void* stream);
+/* col_ind[nnz] (device, out), ascending inside each row. */
+int dfb_pattern_cols(int num_node, int num_tet, const int* d_ien, const int* d_row_ptr, int* d_col_ind, void* stream);
+/* blocked scalar-CSR pattern (br x bc): new_row_ptr[N*br+1], new_col_ind[nnz*br*bc].  Unlike the reference
+ * (defect D1) the final row_ptr entry IS written. */
+int dfb_pattern_expand(int num_node, const int* d_row_ptr, const int* d_col_ind, int br, int bc, int* d_new_row_ptr,
+                       int* d_new_col_ind, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Element coloring.  Replaces ColorMeshTet / GetMaxColor (src/color.c:14-67, src/color_impl.cu)
+ * and the batch construction of Mesh3DGenerateColorBatch (src/Mesh.c:165-206, src/indexing.cu:92-103).
+ * ------------------------------------------------------------------------------------------ */
+/* weight[e] = xorwow_u32(seed)[e] % 1073741823 in cuRAND's default ordering (src/color_impl.cu:185-192,225-237) */
+int dfb_color_weights(int num_tet, unsigned long long seed, int* d_weight, void* stream);
+/* Jones-Plassmann-Luby: color[e] = round in which e is the strict weight maximum among its still uncoloured
+ * vertex-sharing neighbours.  Equal weights are broken by element id (the reference is non-deterministic there,
+ * defect D2).  *num_color (host, out) = max color + 1. */
+int dfb_color_jpl(int num_node, int num_tet, const int* d_ien, const int* d_weight, int max_color, int* d_color,
+                  int* num_color, void* stream);
+/* batch_offset[num_color+1] (HOST, out), batch_ind[E] (device, out): ascending element ids per color. */
+int dfb_color_batches(int num_tet, const int* d_color, int num_color, int* h_batch_offset, int* d_batch_ind,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Assembly.  Replaces AssembleSystemTet / AssembleSystemTetFace (src/assemble.cu:1467-1964),
+ * MatrixAddElemValueBlockedBatched (src/matrix.c:574-592, src/matrix_impl.cu:370-453),
+ * ElemRHSLocal2Global (src/assemble.cu:188-208) and the Dirichlet kernels.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dfb_plan dfb_plan;
+
+typedef enum dfb_assemble_mode {
+  DFB_MODE_AUTO = 0,     /* fastest measured variant (gather) */
+  DFB_MODE_GATHER = 1,   /* atomic-free: one warp per nodal row gathers its corner contributions, every CSR value
+                            and F entry is written exactly once, fixed summation order (deterministic) */
+  DFB_MODE_ATOMIC = 2,   /* one launch over all elements, fp64 red.global.add scatter */
+  DFB_MODE_COLORED = 3   /* one launch per color batch, plain read-modify-write in the reference's order */
+} dfb_assemble_mode;
+
+/* Integer plan of one mesh: vertex->corner lists, corner->CSR-slot map, (optional) color batches.
+ * d_ien, d_row_ptr, d_col_ind are borrowed and must outlive the plan.  h_batch_offset/d_batch_ind may be NULL
+ * (then DFB_MODE_COLORED is unavailable). */
+int dfb_plan_create(dfb_plan** plan, int num_node, int num_tet, const int* d_ien, const int* d_row_ptr,
+                    const int* d_col_ind, int num_batch, const int* h_batch_offset, const int* d_batch_ind,
+                    void* stream);
+void dfb_plan_destroy(dfb_plan* plan);
+/* bytes of device memory held by the plan */
+size_t dfb_plan_bytes(const dfb_plan* plan);
+
+/* Interior (tet) assembly: F[6N] += element residuals and/or the four sub-block value arrays += element
+ * Jacobians.  F or the A-pointers may be NULL.  In GATHER mode with `overwrite` != 0 the outputs are written
+ * (=) instead of accumulated (+=), which makes the preceding memset (reference main.c:44-49) unnecessary. */
+int dfb_assemble_tet(const dfb_plan* plan, const double* d_xg, const double* d_wgalpha, const double* d_dwgalpha,
+                     double* d_F, double* d_A00, double* d_A01, double* d_A10, double* d_A11, int mode, int overwrite,
+                     void* stream);
+/* Weak-BC boundary faces of one boundary group (the reference runs group 4 only, defect D13). */
+int dfb_assemble_face(const dfb_plan* plan, int num_face, const int* d_f2e, const int* d_forn, const double* d_xg,
+                      const double* d_wgalpha, const double* d_dwgalpha, double* d_F, double* d_A00, double* d_A01,
+                      double* d_A10, double* d_A11, void* stream);
+/* Strong Dirichlet: b[node*shape + ic] = 0 for every ic with bctype[ic]==1 (src/dirichlet.c:31-42). */
+int dfb_dirichlet_vec(int num_bnode, const int* d_bnode, int shape, const int* h_bctype, double* d_b, void* stream);
+/* rows node*3+ic of A00 -> unit rows, of A01 -> zero rows (src/dirichlet.c:47-61, src/matrix.c:449-469). */
+int dfb_dirichlet_mat(int num_bnode, const int* d_bnode, int shape, const int* h_bctype, int num_node,
+                      const int* d_row_ptr, const int* d_col_ind, double* d_A00, double* d_A01, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Solve.  Replaces MatrixFSAMVPBY/MatVec (src/matrix.c:471-524, four cuSPARSE SpMVs), PCSetup/PCApply
+ * (src/pc.c:44-147) and GMRESSolvePrivate (src/krylov.c:56-334).
+ * ------------------------------------------------------------------------------------------ */
+/* y[0:4N) = beta*y[0:4N) + alpha * A x ; y[4N:6N) untouched (defect D4).  One fused kernel over the 4 blocks. */
+int dfb_spmv_fs(int num_node, const int* d_row_ptr, const int* d_col_ind, const double* d_A00, const double* d_A01,
+                const double* d_A10, const double* d_A11, double alpha, const double* d_x, double beta, double* d_y,
+                void* stream);
+/* dinv00[9N]: (B^-1)^T of the nodal 3x3 diagonal blocks of A00 in the layout the reference's gemv consumes
+ * (defect D3); dinv11[N] = 1/diag(A11). */
+int dfb_pc_setup(int num_node, const int* d_row_ptr, const int* d_col_ind, const double* d_A00, const double* d_A11,
+                 double* d_dinv00, double* d_dinv11, void* stream);
+/* y = P^-1 x on 6N vectors: block-Jacobi on u, Jacobi on p, identity on phi and T. */
+int dfb_pc_apply(int num_node, const double* d_dinv00, const double* d_dinv11, const double* d_x, double* d_y,
+                 void* stream);
+
+typedef struct dfb_gmres dfb_gmres;
+/* Persistent workspace for right-preconditioned, un-restarted GMRES(max_iter) on 6N vectors. */
+int dfb_gmres_create(dfb_gmres** ws, int num_node, int max_iter);
+void dfb_gmres_destroy(dfb_gmres* ws);
+size_t dfb_gmres_bytes(const dfb_gmres* ws);
+/* Optional data-parallel hooks (multi-GPU): owned rows [0,num_owned) of each section are reduced over ranks
+ * with `allreduce(buf, count, user)` (device buffer of doubles, summed in place, enqueued on `stream`) and ghost
+ * entries of the SpMV input are refreshed with `halo(d_x, user)` before every mat-vec.  NULL = single GPU. */
+typedef int (*dfb_allreduce_fn)(double* d_buf, int count, void* stream, void* user);
+typedef int (*dfb_halo_fn)(double* d_x, void* stream, void* user);
+int dfb_gmres_set_parallel(dfb_gmres* ws, int num_owned, dfb_allreduce_fn allreduce, dfb_halo_fn halo, void* user);
+/* Solve A x = b (x in/out, b in; both 6N device vectors).  Convergence is tested only when (iter+1)%20==0 against
+ * |r| < atol || |r| < (|r0| + 1e-16)*rtol (src/krylov.c:281-290, defect D10).  res_hist (HOST, may be NULL) receives
+ * max_iter+1 entries: |beta[k]| for k = 0..iters.  *iters (host, out). */
+int dfb_gmres_solve(dfb_gmres* ws, int num_node, const int* d_row_ptr, const int* d_col_ind, const double* d_A00,
+                    const double* d_A01, const double* d_A10, const double* d_A11, double* d_x, const double* d_b,
+                    double atol, double rtol, int* iters, double* res_hist, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEDFLOW_B200_H */
