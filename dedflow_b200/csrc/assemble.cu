@@ -1,0 +1,484 @@
+// assemble.cu -- element assembly of the field-split system (F and the four CSR sub-blocks) on B200.
+//
+// Replaces (reference paths relative to /root/reference/src):
+//   assemble.cu:1467-1762  AssembleSystemTet: per color batch ~25 launches (geometry, batched LU, 8 gathers,
+//                          3 batched GEMMs, weak form, memset + 576-double elem_J round trip, 5 scatters)
+//   assemble.cu:1764-1964  AssembleSystemTetFace (num_color x 7 masked scatter launches)
+//   matrix_impl.cu:370-453 SetBlockValueToSubmatKernel (linear search + scattered 8-byte RMW)
+//   dirichlet_impl.cu:15-37, matrix_impl.cu:6-23  Dirichlet rows
+//
+// B200 design:
+//   * J, GATHER (default): one warp per nodal row.  Lanes = the row's corners (element, local node); each lane
+//     stages connectivity + nodal data in registers, evaluates the hoisted element math (elem_math.cuh) and
+//     produces the 4 blocks (b = 0..3) of its element row.  Per b the 32 blocks are staged in shared memory,
+//     lanes switch roles to (slot, half-block) owners, and sum the staged blocks that target their slot
+//     (peer masks from __match_any_sync).  Every CSR value is written exactly once, coalesced per row, in a
+//     fixed order: no atomics, no colors, no memset, no elem_J round trip, deterministic.
+//   * J, ATOMIC: one thread per corner, red.global.add.f64 scatter through the precomputed slot map.
+//   * J, COLORED: same kernel without atomics, one launch per color batch (the reference's structure).
+//   * F: one thread per element evaluates the residual once; GATHER writes the 24 values to an L2-friendly
+//     scratch and a node-gather kernel sums them in fixed order; ATOMIC / COLORED scatter directly.
+#include "common.cuh"
+#include "elem_math.cuh"
+#include "plan.cuh"
+
+namespace dfb {
+using namespace em;
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------------------
+// loads
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_nodes(const int* __restrict__ ien, int e, int nodes[4]) {
+  int4 nd = __ldg(reinterpret_cast<const int4*>(ien) + e);
+  nodes[0] = nd.x; nodes[1] = nd.y; nodes[2] = nd.z; nodes[3] = nd.w;
+}
+
+__device__ __forceinline__ void load_xyz(const f64* __restrict__ v, const int nodes[4], f64 out[4][3]) {
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const f64* p = v + (size_t)nodes[a] * 3;
+    out[a][0] = __ldg(p); out[a][1] = __ldg(p + 1); out[a][2] = __ldg(p + 2);
+  }
+}
+
+// CSR positions of the 4x4 block of (row node with nodal row [start, start+len), slot k)
+template <int OP>  // 0: plain +=, 1: atomic +=, 2: =
+__device__ __forceinline__ void put(f64* p, f64 v) {
+  if (OP == 0) *p += v;
+  else if (OP == 1) atomicAdd(p, v);
+  else *p = v;
+}
+
+template <int OP>
+__device__ __forceinline__ void scatter_block(f64* __restrict__ A00, f64* __restrict__ A01, f64* __restrict__ A10,
+                                              f64* __restrict__ A11, size_t start, int len, int k, const f64 blk[16]) {
+  f64* p00 = A00 + start * 9 + (size_t)k * 3;
+#pragma unroll
+  for (int ii = 0; ii < 3; ii++) {
+#pragma unroll
+    for (int jj = 0; jj < 3; jj++) put<OP>(p00 + (size_t)ii * len * 3 + jj, blk[ii * 4 + jj]);
+    put<OP>(A01 + start * 3 + (size_t)ii * len + k, blk[ii * 4 + 3]);
+    put<OP>(A10 + start * 3 + (size_t)k * 3 + ii, blk[12 + ii]);
+  }
+  put<OP>(A11 + start + k, blk[15]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// F: one thread per element
+// ------------------------------------------------------------------------------------------------------------
+template <int MODE>  // 0: write scratch[e*24..], 1: atomic scatter, 2: plain scatter of a color batch
+__global__ void __launch_bounds__(128) k_elemF(int n, const int* __restrict__ elem_ids, int N, const int* __restrict__ ien,
+                                               const f64* __restrict__ xg, const f64* __restrict__ wg,
+                                               const f64* __restrict__ dwg, f64* __restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int e = elem_ids ? elem_ids[t] : t;
+  int nodes[4];
+  load_nodes(ien, e, nodes);
+  f64 x[4][3], val[6][4], dval[6][4];
+  load_xyz(xg, nodes, x);
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const int nd = nodes[a];
+    const f64* pu = wg + (size_t)nd * 3;
+    const f64* pd = dwg + (size_t)nd * 3;
+    val[0][a] = __ldg(pu); val[1][a] = __ldg(pu + 1); val[2][a] = __ldg(pu + 2);
+    dval[0][a] = __ldg(pd); dval[1][a] = __ldg(pd + 1); dval[2][a] = __ldg(pd + 2);
+    const f64 p = __ldg(dwg + (size_t)3 * N + nd);  // pressure lives in the increment vector (defect D6)
+    val[3][a] = p; dval[3][a] = p;
+    val[4][a] = __ldg(wg + (size_t)4 * N + nd); dval[4][a] = __ldg(dwg + (size_t)4 * N + nd);
+    val[5][a] = __ldg(wg + (size_t)5 * N + nd); dval[5][a] = __ldg(dwg + (size_t)5 * N + nd);
+  }
+  Geom g;
+  geometry(x, g);
+  f64 eF[4][6];
+  residual(g, val, dval, eF);
+  if (MODE == 0) {
+    f64* dst = out + (size_t)e * 24;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int i = 0; i < 6; i += 2) *reinterpret_cast<double2*>(dst + a * 6 + i) = make_double2(eF[a][i], eF[a][i + 1]);
+  } else {
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const size_t nd = (size_t)nodes[a];
+      put<MODE == 1 ? 1 : 0>(out + nd * 3 + 0, eF[a][0]);
+      put<MODE == 1 ? 1 : 0>(out + nd * 3 + 1, eF[a][1]);
+      put<MODE == 1 ? 1 : 0>(out + nd * 3 + 2, eF[a][2]);
+      put<MODE == 1 ? 1 : 0>(out + (size_t)3 * N + nd, eF[a][3]);
+      put<MODE == 1 ? 1 : 0>(out + (size_t)4 * N + nd, eF[a][4]);
+      put<MODE == 1 ? 1 : 0>(out + (size_t)5 * N + nd, eF[a][5]);
+    }
+  }
+}
+
+// node gather: F[node] (+)= sum over the node's corners, ascending corner id
+__global__ void k_gatherF(int N, const int* __restrict__ v2c_ptr, const int* __restrict__ v2c,
+                          const f64* __restrict__ scratch, f64* __restrict__ F, int overwrite) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  f64 s[6] = {0, 0, 0, 0, 0, 0};
+  for (int p = v2c_ptr[i]; p < v2c_ptr[i + 1]; p++) {
+    const f64* src = scratch + (size_t)v2c[p] * 6;
+    double2 a = *reinterpret_cast<const double2*>(src), b = *reinterpret_cast<const double2*>(src + 2),
+            c = *reinterpret_cast<const double2*>(src + 4);
+    s[0] += a.x; s[1] += a.y; s[2] += b.x; s[3] += b.y; s[4] += c.x; s[5] += c.y;
+  }
+  f64* fu = F + (size_t)i * 3;
+  if (overwrite) {
+    fu[0] = s[0]; fu[1] = s[1]; fu[2] = s[2];
+    F[(size_t)3 * N + i] = s[3]; F[(size_t)4 * N + i] = s[4]; F[(size_t)5 * N + i] = s[5];
+  } else {
+    fu[0] += s[0]; fu[1] += s[1]; fu[2] += s[2];
+    F[(size_t)3 * N + i] += s[3]; F[(size_t)4 * N + i] += s[4]; F[(size_t)5 * N + i] += s[5];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// J: per-corner work shared by all variants
+// ------------------------------------------------------------------------------------------------------------
+struct CornerCtx {
+  Geom g;
+  JPrep p;
+  ARow r;
+  int row;  // global node of the corner
+};
+
+__device__ __forceinline__ void corner_setup(int corner, const int* __restrict__ ien, const f64* __restrict__ xg,
+                                             const f64* __restrict__ wg, CornerCtx& c) {
+  const int e = corner >> 2, a = corner & 3;
+  int nodes[4];
+  load_nodes(ien, e, nodes);
+  f64 x[4][3], u[4][3];
+  load_xyz(xg, nodes, x);
+  load_xyz(wg, nodes, u);
+  geometry(x, c.g);
+  jac_prep(c.g, u, c.p);
+  extract_row(c.g, c.p, a, c.r);
+  c.row = a == 0 ? nodes[0] : (a == 1 ? nodes[1] : (a == 2 ? nodes[2] : nodes[3]));
+}
+
+// ATOMIC / COLORED: one thread per corner, scatter through the slot map
+template <int OP>
+__global__ void __launch_bounds__(128) k_cornerJ(int n_elem, const int* __restrict__ elem_ids, const int* __restrict__ ien,
+                                                 const f64* __restrict__ xg, const f64* __restrict__ wg,
+                                                 const int* __restrict__ row_ptr, const u32* __restrict__ slot32,
+                                                 f64* __restrict__ A00, f64* __restrict__ A01, f64* __restrict__ A10,
+                                                 f64* __restrict__ A11) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 4 * n_elem) return;
+  int e = elem_ids ? elem_ids[t >> 2] : (t >> 2);
+  int corner = e * 4 + (t & 3);
+  CornerCtx c;
+  corner_setup(corner, ien, xg, wg, c);
+  const int start = row_ptr[c.row], len = row_ptr[c.row + 1] - start;
+  const u32 slots = slot32[corner];
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    f64 blk[16];
+    jac_block_row(c.g, c.p, c.r, b, blk);
+    scatter_block<OP>(A00, A01, A10, A11, (size_t)start, len, (int)((slots >> (8 * b)) & 0xffu), blk);
+  }
+}
+
+// GATHER: one warp per nodal row
+template <int NSG>  // slot groups of 16 (row length <= 16*NSG)
+__global__ void __launch_bounds__(128) k_rowJ(int N, const int* __restrict__ ien, const f64* __restrict__ xg,
+                                              const f64* __restrict__ wg, const int* __restrict__ row_ptr,
+                                              const int* __restrict__ v2c_ptr, const int* __restrict__ v2c,
+                                              const u32* __restrict__ slot32, f64* __restrict__ A00,
+                                              f64* __restrict__ A01, f64* __restrict__ A10, f64* __restrict__ A11,
+                                              int overwrite) {
+  __shared__ f64 stage_s[4][16 * 32];
+  __shared__ u32 smask_s[4][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= N) return;
+  f64* stage = stage_s[warp];
+  u32* smask = smask_s[warp];
+  smask[lane] = 0u;
+  smask[lane + 32] = 0u;
+  const int cs = v2c_ptr[row], ce = v2c_ptr[row + 1];
+  const int start = row_ptr[row], len = row_ptr[row + 1] - start;
+  f64 acc[NSG][8];
+#pragma unroll
+  for (int sg = 0; sg < NSG; sg++)
+#pragma unroll
+    for (int v = 0; v < 8; v++) acc[sg][v] = 0.0;
+  const int myslot = lane >> 1, half = lane & 1;
+  __syncwarp();
+  for (int base = cs; base < ce; base += 32) {
+    const bool active = base + lane < ce;
+    CornerCtx c;
+    u32 slots = 0xffffffffu;
+    if (active) {
+      const int corner = v2c[base + lane];
+      corner_setup(corner, ien, xg, wg, c);
+      slots = slot32[corner];
+    }
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      f64 blk[16];
+      if (active) jac_block_row(c.g, c.p, c.r, b, blk);
+      const u32 tgt = active ? ((slots >> (8 * b)) & 0xffu) : 255u;
+      const u32 peers = __match_any_sync(FULL, tgt);
+      const bool leader = active && ((__ffs(peers) - 1) == lane);
+      if (leader) smask[tgt] = peers;
+      if (active) {
+#pragma unroll
+        for (int v = 0; v < 16; v++) stage[v * 32 + lane] = blk[v];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int sg = 0; sg < NSG; sg++) {
+        const int s = sg * 16 + myslot;
+        if (s < len) {
+          u32 m = smask[s];
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+#pragma unroll
+            for (int v = 0; v < 8; v++) acc[sg][v] += stage[(half * 8 + v) * 32 + src];
+          }
+        }
+      }
+      __syncwarp();
+      if (leader) smask[tgt] = 0u;
+      __syncwarp();
+    }
+  }
+  // write-out: lane (slot, half) owns rows ii = 2*half, 2*half+1 of the 4x4 block
+#pragma unroll
+  for (int sg = 0; sg < NSG; sg++) {
+    const int s = sg * 16 + myslot;
+    if (s >= len) continue;
+    const size_t st = (size_t)start;
+    f64* p00 = A00 + st * 9 + (size_t)s * 3;
+    f64* p01 = A01 + st * 3 + s;
+    f64* p10 = A10 + st * 3 + (size_t)s * 3;
+    f64* p11 = A11 + st + s;
+    if (half == 0) {
+      if (overwrite) {
+#pragma unroll
+        for (int ii = 0; ii < 2; ii++) {
+#pragma unroll
+          for (int jj = 0; jj < 3; jj++) p00[(size_t)ii * len * 3 + jj] = acc[sg][ii * 4 + jj];
+          p01[(size_t)ii * len] = acc[sg][ii * 4 + 3];
+        }
+      } else {
+#pragma unroll
+        for (int ii = 0; ii < 2; ii++) {
+#pragma unroll
+          for (int jj = 0; jj < 3; jj++) p00[(size_t)ii * len * 3 + jj] += acc[sg][ii * 4 + jj];
+          p01[(size_t)ii * len] += acc[sg][ii * 4 + 3];
+        }
+      }
+    } else {
+      if (overwrite) {
+#pragma unroll
+        for (int jj = 0; jj < 3; jj++) { p00[(size_t)2 * len * 3 + jj] = acc[sg][jj]; p10[jj] = acc[sg][4 + jj]; }
+        p01[(size_t)2 * len] = acc[sg][3];
+        p11[0] = acc[sg][7];
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 3; jj++) { p00[(size_t)2 * len * 3 + jj] += acc[sg][jj]; p10[jj] += acc[sg][4 + jj]; }
+        p01[(size_t)2 * len] += acc[sg][3];
+        p11[0] += acc[sg][7];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// boundary faces (tiny: O(N^(2/3)) faces): one thread per face, atomic scatter
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_face(int nf, const int* __restrict__ f2e, const int* __restrict__ forn, int N,
+                                              const int* __restrict__ ien, const f64* __restrict__ xg,
+                                              const f64* __restrict__ wg, const f64* __restrict__ dwg,
+                                              const int* __restrict__ row_ptr, const u32* __restrict__ slot32,
+                                              f64* __restrict__ F, f64* __restrict__ A00, f64* __restrict__ A01,
+                                              f64* __restrict__ A10, f64* __restrict__ A11) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  const int e = f2e[f], iorn = forn[f];
+  int nodes[4];
+  load_nodes(ien, e, nodes);
+  f64 x[4][3], u[4][3];
+  load_xyz(xg, nodes, x);
+  load_xyz(wg, nodes, u);
+  Geom g;
+  geometry(x, g);
+  FacePrep fp;
+  face_prep(g, iorn, fp);
+  if (F) {
+    f64 val[4][4], eF[4][6];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      val[0][a] = u[a][0]; val[1][a] = u[a][1]; val[2][a] = u[a][2];
+      val[3][a] = __ldg(dwg + (size_t)3 * N + nodes[a]);
+    }
+    face_residual(g, fp, iorn, val, eF);
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const size_t nd = (size_t)nodes[a];
+      atomicAdd(F + nd * 3 + 0, eF[a][0]);
+      atomicAdd(F + nd * 3 + 1, eF[a][1]);
+      atomicAdd(F + nd * 3 + 2, eF[a][2]);
+      atomicAdd(F + (size_t)3 * N + nd, eF[a][3]);
+    }
+  }
+  if (A00) {
+#pragma unroll 1
+    for (int a = 0; a < 4; a++) {
+      const int row = nodes[a];
+      const int start = row_ptr[row], len = row_ptr[row + 1] - start;
+      const u32 slots = slot32[e * 4 + a];
+#pragma unroll 1
+      for (int b = 0; b < 4; b++) {
+        f64 blk[16];
+        face_block(g, fp, iorn, u, a, b, blk);
+        scatter_block<1>(A00, A01, A10, A11, (size_t)start, len, (int)((slots >> (8 * b)) & 0xffu), blk);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Dirichlet
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_dirichlet_vec(int nb, const int* __restrict__ bnode, int shape, int mask, f64* __restrict__ b) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const size_t base = (size_t)bnode[i] * shape;
+  for (int ic = 0; ic < shape; ic++)
+    if (mask & (1 << ic)) b[base + ic] = 0.0;
+}
+
+// one thread per (boundary node, slot k): rows node*3+ic of A00 become unit rows, of A01 zero rows
+__global__ void k_dirichlet_mat(int nb, const int* __restrict__ bnode, int mask, int N, const int* __restrict__ row_ptr,
+                                const int* __restrict__ col_ind, f64* __restrict__ A00, f64* __restrict__ A01) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = t >> 6, k = t & 63;
+  if (i >= nb) return;
+  const int node = bnode[i];
+  if (node < 0 || node >= N) return;
+  const int start = row_ptr[node], len = row_ptr[node + 1] - start;
+  if (k >= len) return;
+  const bool diag = col_ind[start + k] == node;
+#pragma unroll
+  for (int ic = 0; ic < 3; ic++) {
+    if (!(mask & (1 << ic))) continue;
+    f64* p = A00 + (size_t)start * 9 + (size_t)ic * 3 * len + (size_t)k * 3;
+    p[0] = (diag && ic == 0) ? 1.0 : 0.0;
+    p[1] = (diag && ic == 1) ? 1.0 : 0.0;
+    p[2] = (diag && ic == 2) ? 1.0 : 0.0;
+    A01[(size_t)start * 3 + (size_t)ic * len + k] = 0.0;
+  }
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" {
+
+int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, const double* d_dwg, double* d_F,
+                     double* d_A00, double* d_A01, double* d_A10, double* d_A11, int mode, int overwrite, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  if (!P || !d_xg || !d_wg || !d_dwg) { set_error("dfb_assemble_tet: bad argument"); return DFB_ERR_ARG; }
+  const bool doJ = d_A00 != nullptr;
+  if (doJ && (!d_A01 || !d_A10 || !d_A11)) { set_error("dfb_assemble_tet: all four sub-block arrays are required"); return DFB_ERR_ARG; }
+  if (mode == DFB_MODE_AUTO) mode = DFB_MODE_GATHER;
+  if (mode == DFB_MODE_COLORED && (P->num_batch <= 0 || !P->batch_ind)) { set_error("dfb_assemble_tet: plan has no color batches"); return DFB_ERR_ARG; }
+  if (overwrite && mode != DFB_MODE_GATHER) { set_error("dfb_assemble_tet: overwrite needs DFB_MODE_GATHER"); return DFB_ERR_ARG; }
+  const int N = P->N, E = P->E;
+  const u32* slot32 = reinterpret_cast<const u32*>(P->slot);
+  if (d_F) {
+    if (mode == DFB_MODE_GATHER) {
+      if (!P->elemF) {
+        P->elemF_bytes = sizeof(f64) * 24 * (size_t)E;
+        DFB_CUDA(cudaMalloc(&P->elemF, P->elemF_bytes));
+      }
+      k_elemF<0><<<ceil_div(E, 128), 128, 0, st>>>(E, nullptr, N, P->ien, d_xg, d_wg, d_dwg, P->elemF);
+      DFB_LAUNCH_CHECK();
+      k_gatherF<<<ceil_div(N, 128), 128, 0, st>>>(N, P->v2c_ptr, P->v2c, P->elemF, d_F, overwrite);
+      DFB_LAUNCH_CHECK();
+    } else if (mode == DFB_MODE_ATOMIC) {
+      k_elemF<1><<<ceil_div(E, 128), 128, 0, st>>>(E, nullptr, N, P->ien, d_xg, d_wg, d_dwg, d_F);
+      DFB_LAUNCH_CHECK();
+    } else {
+      for (int b = 0; b < P->num_batch; b++) {
+        int n = P->batch_offset[b + 1] - P->batch_offset[b];
+        if (n == 0) break;  // reference assemble.cu:1565-1567
+        k_elemF<2><<<ceil_div(n, 128), 128, 0, st>>>(n, P->batch_ind + P->batch_offset[b], N, P->ien, d_xg, d_wg, d_dwg, d_F);
+        DFB_LAUNCH_CHECK();
+      }
+    }
+  }
+  if (doJ) {
+    if (mode == DFB_MODE_GATHER) {
+      const int grid = ceil_div(N, 4);
+      if (P->max_row_len <= 16)
+        k_rowJ<1><<<grid, 128, 0, st>>>(N, P->ien, d_xg, d_wg, P->row_ptr, P->v2c_ptr, P->v2c, slot32, d_A00, d_A01, d_A10, d_A11, overwrite);
+      else if (P->max_row_len <= 32)
+        k_rowJ<2><<<grid, 128, 0, st>>>(N, P->ien, d_xg, d_wg, P->row_ptr, P->v2c_ptr, P->v2c, slot32, d_A00, d_A01, d_A10, d_A11, overwrite);
+      else
+        k_rowJ<4><<<grid, 128, 0, st>>>(N, P->ien, d_xg, d_wg, P->row_ptr, P->v2c_ptr, P->v2c, slot32, d_A00, d_A01, d_A10, d_A11, overwrite);
+      DFB_LAUNCH_CHECK();
+    } else if (mode == DFB_MODE_ATOMIC) {
+      k_cornerJ<1><<<ceil_div(4 * (i64)E, 128), 128, 0, st>>>(E, nullptr, P->ien, d_xg, d_wg, P->row_ptr, slot32, d_A00, d_A01, d_A10, d_A11);
+      DFB_LAUNCH_CHECK();
+    } else {
+      for (int b = 0; b < P->num_batch; b++) {
+        int n = P->batch_offset[b + 1] - P->batch_offset[b];
+        if (n == 0) break;
+        k_cornerJ<0><<<ceil_div(4 * (i64)n, 128), 128, 0, st>>>(n, P->batch_ind + P->batch_offset[b], P->ien, d_xg, d_wg, P->row_ptr, slot32, d_A00, d_A01, d_A10, d_A11);
+        DFB_LAUNCH_CHECK();
+      }
+    }
+  }
+  return DFB_OK;
+}
+
+int dfb_assemble_face(const dfb_plan* P, int nf, const int* d_f2e, const int* d_forn, const double* d_xg,
+                      const double* d_wg, const double* d_dwg, double* d_F, double* d_A00, double* d_A01, double* d_A10,
+                      double* d_A11, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  if (!P || nf < 0 || !d_xg || !d_wg || !d_dwg) { set_error("dfb_assemble_face: bad argument"); return DFB_ERR_ARG; }
+  if (nf == 0 || (!d_F && !d_A00)) return DFB_OK;
+  if (d_A00 && (!d_A01 || !d_A10 || !d_A11)) { set_error("dfb_assemble_face: all four sub-block arrays are required"); return DFB_ERR_ARG; }
+  k_face<<<ceil_div(nf, 128), 128, 0, st>>>(nf, d_f2e, d_forn, P->N, P->ien, d_xg, d_wg, d_dwg, P->row_ptr,
+                                          reinterpret_cast<const u32*>(P->slot), d_F, d_A00, d_A01, d_A10, d_A11);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int dfb_dirichlet_vec(int nb, const int* d_bnode, int shape, const int* h_bctype, double* d_b, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  if (nb < 0 || shape <= 0 || shape > 30 || !h_bctype || !d_b) { set_error("dfb_dirichlet_vec: bad argument"); return DFB_ERR_ARG; }
+  int mask = 0;
+  for (int ic = 0; ic < shape; ic++)
+    if (h_bctype[ic] == 1) mask |= 1 << ic;  // BC_STRONG, reference dirichlet.h:8-13
+  if (!mask || nb == 0) return DFB_OK;
+  k_dirichlet_vec<<<ceil_div(nb, 128), 128, 0, st>>>(nb, d_bnode, shape, mask, d_b);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+int dfb_dirichlet_mat(int nb, const int* d_bnode, int shape, const int* h_bctype, int N, const int* d_row_ptr,
+                      const int* d_col_ind, double* d_A00, double* d_A01, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  if (nb < 0 || shape != 3 || !h_bctype || !d_row_ptr || !d_col_ind || !d_A00 || !d_A01) { set_error("dfb_dirichlet_mat: bad argument (shape must be 3)"); return DFB_ERR_ARG; }
+  int mask = 0;
+  for (int ic = 0; ic < 3; ic++)
+    if (h_bctype[ic] == 1) mask |= 1 << ic;
+  if (!mask || nb == 0) return DFB_OK;
+  k_dirichlet_mat<<<ceil_div((i64)nb * 64, 128), 128, 0, st>>>(nb, d_bnode, mask, N, d_row_ptr, d_col_ind, d_A00, d_A01);
+  DFB_LAUNCH_CHECK();
+  return DFB_OK;
+}
+
+}  // extern "C"

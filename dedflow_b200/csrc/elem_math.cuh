@@ -237,22 +237,51 @@ DFB_HD void jac_prep(const Geom& g, const f64 u[4][3], JPrep& p) {
   }
 }
 
-// 4x4 (u,p) block of node pair (a,b): blk[ii*4+jj]
-DFB_HD void jac_block(const Geom& g, const JPrep& p, int a, int b, f64 blk[16]) {
-  const f64* ga = g.sh[a];
+// branch-free 4-way select: keeps per-thread arrays in registers when the index is a run-time value
+DFB_HD f64 sel4(int i, f64 v0, f64 v1, f64 v2, f64 v3) {
+  f64 lo = (i & 1) ? v1 : v0, hi = (i & 1) ? v3 : v2;
+  return (i & 2) ? hi : lo;
+}
+
+// everything of JPrep/Geom that is indexed by the ROW node a of a block (a is a run-time value per thread)
+struct ARow {
+  int a;
+  f64 ga[3];    // grad N_a
+  f64 cqa[4];   // c[q][a]
+  f64 tqa[4];   // t[q][a]
+  f64 cab[4];   // c[a][b]   (a used as quadrature index)
+  f64 Pa;       // P[a]
+};
+
+DFB_HD void extract_row(const Geom& g, const JPrep& p, int a, ARow& r) {
+  r.a = a;
+#pragma unroll
+  for (int d = 0; d < 3; d++) r.ga[d] = sel4(a, g.sh[0][d], g.sh[1][d], g.sh[2][d], g.sh[3][d]);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    r.cqa[q] = sel4(a, p.c[q][0], p.c[q][1], p.c[q][2], p.c[q][3]);
+    r.tqa[q] = sel4(a, p.t[q][0], p.t[q][1], p.t[q][2], p.t[q][3]);
+    r.cab[q] = sel4(a, p.c[0][q], p.c[1][q], p.c[2][q], p.c[3][q]);
+  }
+  r.Pa = sel4(a, p.P[0], p.P[1], p.P[2], p.P[3]);
+}
+
+// 4x4 (u,p) block of node pair (a,b): blk[ii*4+jj].  b must be a compile-time constant after unrolling.
+DFB_HD void jac_block_row(const Geom& g, const JPrep& p, const ARow& r, int b, f64 blk[16]) {
+  const f64* ga = r.ga;
   const f64* gb = g.sh[b];
   const f64 eK = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
-  const f64 mab = (a == b) ? (SA * SA + 3.0 * SB * SB) : (2.0 * SA * SB + 2.0 * SB * SB);
-  const f64 stc = p.t[0][a] * p.c[0][b] + p.t[1][a] * p.c[1][b] + p.t[2][a] * p.c[2][b] + p.t[3][a] * p.c[3][b];
-  const f64 T = p.w * (FACT1 * RHO * mab + FACT1 * RHO * RHO * (SB * p.P[a] + SD * p.t[b][a]) +
-                       FACT2 * RHO * (SB * p.R[b] + SD * p.c[a][b]) + FACT2 * RHO * RHO * stc + 4.0 * FACT2 * MU * eK);
+  const f64 mab = (r.a == b) ? (SA * SA + 3.0 * SB * SB) : (2.0 * SA * SB + 2.0 * SB * SB);
+  const f64 stc = r.tqa[0] * p.c[0][b] + r.tqa[1] * p.c[1][b] + r.tqa[2] * p.c[2][b] + r.tqa[3] * p.c[3][b];
+  const f64 T = p.w * (FACT1 * RHO * mab + FACT1 * RHO * RHO * (SB * r.Pa + SD * r.tqa[b]) +
+                       FACT2 * RHO * (SB * p.R[b] + SD * r.cab[b]) + FACT2 * RHO * RHO * stc + 4.0 * FACT2 * MU * eK);
   const f64 k1 = 4.0 * p.w * FACT2 * MU;          // viscous transpose term
   const f64 k2 = p.w * FACT2 * RHO * p.sTC;       // grad-div (tauC) term
 #pragma unroll
   for (int ii = 0; ii < 3; ii++)
 #pragma unroll
     for (int jj = 0; jj < 3; jj++) blk[ii * 4 + jj] = k1 * ga[jj] * gb[ii] + k2 * ga[ii] * gb[jj] + (ii == jj ? T : 0.0);
-  const f64 k3 = p.w * SN, k4 = RHO * p.w * p.P[a];
+  const f64 k3 = p.w * SN, k4 = RHO * p.w * r.Pa;
   const f64 k5 = p.w * RHO * (FACT1 * (SB * p.sTM + SD * p.tM[b]) + FACT2 * p.P[b]);
   const f64 k6 = FACT2 * p.w * SN;
 #pragma unroll
@@ -261,6 +290,17 @@ DFB_HD void jac_block(const Geom& g, const JPrep& p, int a, int b, f64 blk[16]) 
     blk[3 * 4 + ii] = k5 * ga[ii] + k6 * gb[ii];    // dRC/dU
   }
   blk[15] = p.w * p.sTM * eK;                       // dRC/dP
+}
+
+DFB_HD void jac_block(const Geom& g, const JPrep& p, int a, int b, f64 blk[16]) {
+  ARow r;
+  extract_row(g, p, a, r);
+  switch (b) {
+    case 0: jac_block_row(g, p, r, 0, blk); break;
+    case 1: jac_block_row(g, p, r, 1, blk); break;
+    case 2: jac_block_row(g, p, r, 2, blk); break;
+    default: jac_block_row(g, p, r, 3, blk); break;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

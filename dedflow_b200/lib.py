@@ -1,0 +1,81 @@
+"""ctypes binding of libdedflow_b200.so (the C ABI declared in include/dedflow_b200.h).
+
+There is NO fallback: if the shared object is missing, or a call fails, this module raises.  Device memory is
+owned by the caller (torch tensors in the tests / bench); only raw pointers cross the boundary.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libdedflow_b200.so"
+
+vp = C.c_void_p
+ci = C.c_int
+
+
+class DfbError(RuntimeError):
+    pass
+
+
+_SIGS = {
+    # name: (restype, argtypes)
+    "dfb_last_error": (C.c_char_p, []),
+    "dfb_version": (ci, []),
+    "dfb_launch_count": (C.c_longlong, []),
+    "dfb_pattern_rows": (ci, [ci, ci, vp, vp, C.POINTER(ci), vp]),
+    "dfb_pattern_cols": (ci, [ci, ci, vp, vp, vp, vp]),
+    "dfb_pattern_expand": (ci, [ci, vp, vp, ci, ci, vp, vp, vp]),
+    "dfb_color_weights": (ci, [ci, C.c_ulonglong, vp, vp]),
+    "dfb_color_jpl": (ci, [ci, ci, vp, vp, ci, vp, C.POINTER(ci), vp]),
+    "dfb_color_batches": (ci, [ci, vp, ci, vp, vp, vp]),
+    "dfb_plan_create": (ci, [C.POINTER(vp), ci, ci, vp, vp, vp, ci, vp, vp, vp]),
+    "dfb_plan_destroy": (None, [vp]),
+    "dfb_plan_bytes": (C.c_size_t, [vp]),
+    "dfb_assemble_tet": (ci, [vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, vp]),
+    "dfb_assemble_face": (ci, [vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "dfb_dirichlet_vec": (ci, [ci, vp, ci, vp, vp, vp]),
+    "dfb_dirichlet_mat": (ci, [ci, vp, ci, vp, ci, vp, vp, vp, vp, vp]),
+    "dfb_spmv_fs": (ci, [ci, vp, vp, vp, vp, vp, vp, C.c_double, vp, C.c_double, vp, vp]),
+    "dfb_pc_setup": (ci, [ci, vp, vp, vp, vp, vp, vp, vp]),
+    "dfb_pc_apply": (ci, [ci, vp, vp, vp, vp, vp]),
+    "dfb_gmres_create": (ci, [C.POINTER(vp), ci, ci]),
+    "dfb_gmres_destroy": (None, [vp]),
+    "dfb_gmres_bytes": (C.c_size_t, [vp]),
+    "dfb_gmres_set_parallel": (ci, [vp, ci, vp, vp, vp]),
+    "dfb_gmres_solve": (ci, [vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.POINTER(ci), vp, vp]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Every entry point include/dedflow_b200.h declares (used by the CPU-side ABI test)."""
+    return sorted(_SIGS)
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise DfbError(f"{LIB_PATH} is missing: build it with `python -m dedflow_b200._build` "
+                       "(there is no CPU fallback)")
+    lib = C.CDLL(str(LIB_PATH), mode=C.RTLD_LOCAL)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)          # raises AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = load().dfb_last_error().decode(errors="replace")
+        raise DfbError(f"{what} failed with status {status}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load().dfb_launch_count())

@@ -31,6 +31,7 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#pragma GCC visibility push(default)
 
 typedef enum dfb_status {
   DFB_OK = 0,
@@ -149,6 +150,7 @@ int dfb_gmres_solve(dfb_gmres* ws, int num_node, const int* d_row_ptr, const int
                     const double* d_A01, const double* d_A10, const double* d_A11, double* d_x, const double* d_b,
                     double atol, double rtol, int* iters, double* res_hist, void* stream);
 
+#pragma GCC visibility pop
 #ifdef __cplusplus
 }
 #endif

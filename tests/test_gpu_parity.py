@@ -1,0 +1,305 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Integer outputs bit-exact; assembled values max|d|/max|A| <= 1e-12 per sub-block; GMRES residual
+history and solution within 1e-10 relative (BASELINE.json north_star / SURVEY.md §8c)."""
+import numpy as np
+import pytest
+
+from conftest import shuffled_mesh
+from dedflow_b200 import boxmesh
+from oracle import pyoracle
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL_ASM = 1e-12
+TOL_SOLVE = 1e-10
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def api():
+    from dedflow_b200 import api as _api
+    return _api
+
+
+def make_pair(api, oracle, mesh, state="B"):
+    fs = api.FlowSystem(mesh)
+    N = mesh.num_node
+    wg, dwg = boxmesh.state_random(N) if state == "B" else boxmesh.state_default(mesh)
+    return fs, wg, dwg
+
+
+def oracle_system(O, mesh, wg, dwg, faces=True, dirichlet=True):
+    N = mesh.num_node
+    rp, ci = O.nodal_pattern(N, mesh.ien)
+    Z = ci.size
+    w = O.weights(pyoracle.curand_host_u32(mesh.num_tet))
+    color, nc, ties = O.color_jpl(N, mesh.ien, w)
+    off, ind = O.color_batches(color)
+    F = np.zeros(6 * N)
+    blocks = [np.zeros(9 * Z), np.zeros(3 * Z), np.zeros(3 * Z), np.zeros(Z)]
+    O.assemble_tet(N, mesh.ien, mesh.xg, off, ind, wg, dwg, F=F)
+    O.assemble_tet(N, mesh.ien, mesh.xg, off, ind, wg, dwg, pattern=(rp, ci), blocks=blocks)
+    if faces:
+        f2e, forn = mesh.bound_faces(4)
+        O.assemble_face(f2e, forn, N, mesh.ien, mesh.xg, color, nc, wg, dwg, F=F)
+        O.assemble_face(f2e, forn, N, mesh.ien, mesh.xg, color, nc, wg, dwg, pattern=(rp, ci), blocks=blocks)
+    F[4 * N:] = 0
+    if dirichlet:
+        for b, t in {0: (1, 1, 1), 2: (0, 1, 0), 3: (0, 0, 1), 4: (0, 0, 0)}.items():
+            O.dirichlet_vec(mesh.bound_nodes(b), np.array(t, np.int32), F)
+            O.dirichlet_mat(mesh.bound_nodes(b), np.array(t, np.int32), N, (rp, ci), blocks[0], blocks[1])
+    return dict(pattern=(rp, ci), color=color, nc=nc, ties=ties, off=off, ind=ind, F=F, blocks=blocks, weight=w)
+
+
+@pytest.mark.parametrize("m,shuffle", [(1, False), (2, True), (6, True), (20, False)])
+def test_pattern_color_batches_bit_exact(api, oracle, m, shuffle):
+    mesh = shuffled_mesh(m) if shuffle else boxmesh.make_box(m)
+    fs = api.FlowSystem(mesh)
+    rp, ci = oracle.nodal_pattern(mesh.num_node, mesh.ien)
+    assert np.array_equal(fs.row_ptr.cpu().numpy(), rp)
+    assert np.array_equal(fs.col_ind.cpu().numpy(), ci)
+    for br, bc in ((3, 3), (3, 1), (1, 3), (1, 1)):
+        nrp, nci = fs.csr_attr_create_block(br, bc)
+        orp, oci = oracle.expand_block(rp, ci, br, bc, fix_last=True)
+        assert np.array_equal(nrp.cpu().numpy(), orp) and np.array_equal(nci.cpu().numpy(), oci)
+    w = oracle.weights(pyoracle.curand_host_u32(mesh.num_tet))
+    assert np.array_equal(fs.weight.cpu().numpy(), w)               # device XORWOW stream == cuRAND host stream
+    color, rounds, ties = oracle.color_jpl(mesh.num_node, mesh.ien, w)
+    assert ties == 0                                                # bit-exact coloring is defined on tie-free input (D2)
+    assert fs.num_color == rounds
+    assert np.array_equal(fs.color.cpu().numpy(), color)
+    off, ind = oracle.color_batches(color)
+    assert np.array_equal(fs.batch_offset, off) and np.array_equal(fs.batch_ind.cpu().numpy(), ind)
+    fs.close()
+
+
+def test_coloring_breaks_ties_deterministically(api, oracle):
+    mesh = boxmesh.make_box(4)
+    fs = api.FlowSystem(mesh, with_colors=False)
+    w = np.full(mesh.num_tet, 5, np.int32)                          # every weight equal: the reference would race (D2)
+    fs.generate_color_batch(weights=w)
+    color = fs.color.cpu().numpy()
+    for c in range(fs.num_color):
+        nodes = mesh.ien[color == c].ravel()
+        assert len(np.unique(nodes)) == len(nodes)
+    fs.close()
+
+
+@pytest.mark.parametrize("mode", ["gather", "atomic", "colored"])
+@pytest.mark.parametrize("m,shuffle,state", [(1, False, "B"), (3, True, "B"), (8, True, "B"), (20, False, "A"), (20, False, "B")])
+def test_assembly_matches_oracle(api, oracle, m, shuffle, state, mode):
+    mesh = shuffled_mesh(m) if shuffle else boxmesh.make_box(m)
+    fs, wg, dwg = make_pair(api, oracle, mesh, state)
+    ref = oracle_system(oracle, mesh, wg, dwg)
+    N = mesh.num_node
+    d_wg, d_dwg = torch.from_numpy(wg).cuda(), torch.from_numpy(dwg).cuda()
+    F = torch.full((6 * N,), 7.0, dtype=torch.float64, device="cuda")      # garbage: assembly must not depend on it
+    fs.assemble_system(d_wg, d_dwg, F=F, mode=mode)
+    for a in fs.blocks():
+        a.fill_(3.0)
+    fs.assemble_system(d_wg, d_dwg, J=True, mode=mode)
+    Fh = F.cpu().numpy()
+    assert rel(Fh[:3 * N], ref["F"][:3 * N]) <= TOL_ASM
+    assert np.abs(Fh[3 * N:4 * N] - ref["F"][3 * N:4 * N]).max() <= TOL_ASM * np.abs(ref["F"]).max()
+    assert np.all(Fh[4 * N:] == 0)
+    for got, want, name in zip(fs.blocks(), ref["blocks"], ("A00", "A01", "A10", "A11")):
+        assert rel(got.cpu().numpy(), want) <= TOL_ASM, name
+    fs.close()
+
+
+def test_assembly_interior_only_and_accumulate(api, oracle):
+    """F / J without faces and Dirichlet (the bare AssembleSystemTet), and phi/T residual slots before zeroing."""
+    mesh = shuffled_mesh(5)
+    fs, wg, dwg = make_pair(api, oracle, mesh)
+    N = mesh.num_node
+    O = oracle
+    ref = oracle_system(O, mesh, wg, dwg, faces=False, dirichlet=False)
+    Fo = np.zeros(6 * N)
+    O.assemble_tet(N, mesh.ien, mesh.xg, ref["off"], ref["ind"], wg, dwg, F=Fo)
+    d_wg, d_dwg = torch.from_numpy(wg).cuda(), torch.from_numpy(dwg).cuda()
+    from dedflow_b200 import lib as _lib
+    import ctypes as C
+    for mode in (1, 2, 3):
+        F = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+        st = fs._stream()
+        _lib.check(fs.L.dfb_assemble_tet(fs.plan, C.c_void_p(fs.xg.data_ptr()), C.c_void_p(d_wg.data_ptr()),
+                                         C.c_void_p(d_dwg.data_ptr()), C.c_void_p(F.data_ptr()), None, None, None, None,
+                                         mode, 0, st))
+        Fh = F.cpu().numpy()
+        for lo, hi in ((0, 3 * N), (3 * N, 4 * N), (4 * N, 5 * N), (5 * N, 6 * N)):
+            assert rel(Fh[lo:hi], Fo[lo:hi]) <= TOL_ASM, (mode, lo)
+    fs.close()
+
+
+def test_matvec_pc_match_oracle(api, oracle):
+    mesh = shuffled_mesh(8)
+    fs, wg, dwg = make_pair(api, oracle, mesh)
+    ref = oracle_system(oracle, mesh, wg, dwg)
+    N = mesh.num_node
+    for a, b in zip(fs.blocks(), ref["blocks"]):
+        a.copy_(torch.from_numpy(b))
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(6 * N)
+    y0 = rng.standard_normal(6 * N)
+    for alpha, beta in ((1.0, 0.0), (-1.0, 1.0), (0.5, -2.0)):
+        y = y0.copy()
+        oracle.fs_amvpby(ref["pattern"], ref["blocks"], alpha, x, beta, y)
+        dy = torch.from_numpy(y0.copy()).cuda()
+        fs.matrix_amvpby(alpha, torch.from_numpy(x).cuda(), beta, dy)
+        got = dy.cpu().numpy()
+        assert rel(got[:4 * N], y[:4 * N]) <= 1e-13
+        assert np.array_equal(got[4 * N:], y0[4 * N:])                        # defect D4
+    d00, d11 = oracle.pc_setup(ref["pattern"], ref["blocks"])
+    fs.pc_setup()
+    assert rel(fs.dinv00.cpu().numpy(), d00) <= 1e-12 and rel(fs.dinv11.cpu().numpy(), d11) <= 1e-13
+    yo = oracle.pc_apply(d00, d11, x)
+    dy = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    fs.pc_apply(torch.from_numpy(x).cuda(), dy)
+    assert rel(dy.cpu().numpy(), yo) <= 1e-12
+    fs.close()
+
+
+@pytest.mark.parametrize("m,state", [(6, "B"), (20, "A"), (20, "B")])
+def test_gmres_matches_oracle(api, oracle, m, state):
+    mesh = boxmesh.make_box(m)
+    fs, wg, dwg = make_pair(api, oracle, mesh, state)
+    ref = oracle_system(oracle, mesh, wg, dwg)
+    N = mesh.num_node
+    for a, b in zip(fs.blocks(), ref["blocks"]):
+        a.copy_(torch.from_numpy(b))
+    xo, ito, histo = oracle.gmres(ref["pattern"], ref["blocks"], ref["F"])
+    dx = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    F = torch.from_numpy(ref["F"]).cuda()
+    it, hist = fs.krylov_solve(dx, F)
+    assert it == ito and it % 20 == 0
+    # residual history at the iterations the reference reports (every 20th, D10), relative to |r0|
+    for k in range(0, it + 1, 20):
+        assert abs(hist[k] - histo[k]) <= TOL_SOLVE * histo[0], k
+    assert np.abs(hist - histo).max() <= TOL_SOLVE * histo[0]
+    got = dx.cpu().numpy()
+    assert rel(got[:4 * N], xo[:4 * N]) <= TOL_SOLVE
+    assert np.all(got[4 * N:] == 0)
+    # the answer actually solves the system
+    y = torch.zeros_like(dx)
+    fs.matrix_matvec(dx, y)
+    res = (F - y)[:4 * N].norm().item()
+    assert abs(res - hist[-1]) <= 1e-8 * hist[0]
+    fs.close()
+
+
+def test_gmres_dead_tail_rank_one(api, oracle):
+    """b[4N:6N) != 0: the reference carries the dead rows through CGS (defect D4); ours does so with one scalar per
+    basis vector.  x0 != 0 as well.  40 iterations: beyond that this (never-converging) system stagnates and single-pass
+    CGS amplifies ANY summation-order difference -- two literal 6N implementations differ by 3e-4 at iteration 120."""
+    mesh = boxmesh.make_box(5)
+    wg, dwg = boxmesh.state_random(mesh.num_node)
+    fs = api.FlowSystem(mesh, max_iter=40, atol=0.0, rtol=0.0)
+    ref = oracle_system(oracle, mesh, wg, dwg)
+    N = mesh.num_node
+    for a, b in zip(fs.blocks(), ref["blocks"]):
+        a.copy_(torch.from_numpy(b))
+    rng = np.random.default_rng(11)
+    b = ref["F"].copy()
+    b[4 * N:] = rng.standard_normal(2 * N) * np.abs(b).max() * 0.1
+    x0 = rng.standard_normal(6 * N) * 1e-3
+    xo, ito, histo = oracle.gmres(ref["pattern"], ref["blocks"], b, x0=x0, maxit=40, atol=0.0, rtol=0.0)
+    dx = torch.from_numpy(x0.copy()).cuda()
+    it, hist = fs.krylov_solve(dx, torch.from_numpy(b).cuda())
+    assert it == ito == 40
+    assert np.abs(hist - histo).max() <= TOL_SOLVE * histo[0]
+    assert rel(dx.cpu().numpy(), xo) <= TOL_SOLVE
+    assert np.abs(dx.cpu().numpy()[4 * N:] - xo[4 * N:]).max() <= TOL_SOLVE * np.abs(xo[4 * N:]).max()
+    fs.close()
+
+
+def test_full_size_properties_1m(api):
+    """BASELINE config 2 (1M-element mesh): size-independent properties -- linearity of the mat-vec, agreement of the
+    three assembly variants, GMRES residual equals the true residual."""
+    mesh = boxmesh.make_box(55)
+    fs = api.FlowSystem(mesh)
+    N = mesh.num_node
+    assert mesh.num_tet == 998250
+    wg, dwg = boxmesh.state_random(N)
+    d_wg, d_dwg = torch.from_numpy(wg).cuda(), torch.from_numpy(dwg).cuda()
+    # coloring validity (no two same-color elements share a node)
+    color = fs.color.cpu().numpy()
+    key = color[:, None].astype(np.int64) * N + mesh.ien
+    assert np.unique(key).size == key.size
+    results = {}
+    for mode in ("gather", "atomic", "colored"):
+        F = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+        fs.assemble_system(d_wg, d_dwg, F=F, mode=mode)
+        fs.assemble_system(d_wg, d_dwg, J=True, mode=mode)
+        results[mode] = (F.clone(), [a.clone() for a in fs.blocks()])
+    for mode in ("atomic", "colored"):
+        assert (results[mode][0] - results["gather"][0]).abs().max().item() <= TOL_ASM * results["gather"][0].abs().max().item()
+        for a, b in zip(results[mode][1], results["gather"][1]):
+            assert (a - b).abs().max().item() <= TOL_ASM * b.abs().max().item()
+    F, blocks = results["gather"]
+    for a, b in zip(fs.blocks(), blocks):
+        a.copy_(b)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x1 = torch.randn(6 * N, dtype=torch.float64, device="cuda", generator=g)
+    x2 = torch.randn(6 * N, dtype=torch.float64, device="cuda", generator=g)
+    y1, y2, y12 = torch.zeros_like(x1), torch.zeros_like(x1), torch.zeros_like(x1)
+    fs.matrix_matvec(x1, y1)
+    fs.matrix_matvec(x2, y2)
+    fs.matrix_matvec(2.0 * x1 - 3.0 * x2, y12)
+    assert (y12 - (2.0 * y1 - 3.0 * y2)).abs().max().item() <= 1e-12 * y12.abs().max().item()
+    dx = torch.zeros_like(F)
+    it, hist = fs.krylov_solve(dx, F)
+    assert it % 20 == 0 and it > 0
+    y = torch.zeros_like(dx)
+    fs.matrix_matvec(dx, y)
+    assert abs((F - y)[:4 * N].norm().item() - hist[-1]) <= 1e-8 * hist[0]
+    assert np.all(np.diff(hist) <= 1e-12 * hist[0])
+    fs.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# golden vectors produced by the reference's OWN CUDA build on a B200 (oracle/ref/run_ref.py, tests/golden/README.md)
+# ---------------------------------------------------------------------------------------------------------------
+def test_cuda_path_matches_reference_golden(api):
+    from test_golden import load_golden, golden_mesh
+    g = load_golden()
+    mesh = golden_mesh(g)
+    N = mesh.num_node
+    fs = api.FlowSystem(mesh)
+    assert np.array_equal(fs.row_ptr.cpu().numpy(), g["row_ptr"]) and np.array_equal(fs.col_ind.cpu().numpy(), g["col_ind"])
+    for name, (br, bc) in {"3x3": (3, 3), "3x1": (3, 1), "1x3": (1, 3)}.items():
+        nrp, nci = fs.csr_attr_create_block(br, bc)
+        assert np.array_equal(nrp.cpu().numpy(), g[f"row_ptr_{name}"]) and np.array_equal(nci.cpu().numpy(), g[f"col_ind_{name}"])
+    assert np.array_equal(fs.color.cpu().numpy(), g["color"])
+    assert np.array_equal(fs.batch_offset, g["batch_offset"]) and np.array_equal(fs.batch_ind.cpu().numpy(), g["batch_ind"])
+    wg, dwg = boxmesh.state_random(N)
+    d_wg, d_dwg = torch.from_numpy(wg).cuda(), torch.from_numpy(dwg).cuda()
+    for mode in ("gather", "atomic", "colored"):
+        F = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+        fs.assemble_system(d_wg, d_dwg, F=F, mode=mode)
+        fs.assemble_system(d_wg, d_dwg, J=True, mode=mode)
+        assert rel(F.cpu().numpy(), g["F"]) <= TOL_ASM
+        for a, nme in zip(fs.blocks(), ("A00", "A01", "A10", "A11")):
+            assert rel(a.cpu().numpy(), g[nme]) <= TOL_ASM, (mode, nme)
+    for a, nme in zip(fs.blocks(), ("A00", "A01", "A10", "A11")):
+        a.copy_(torch.from_numpy(g[nme]))
+    y = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    fs.matrix_matvec(torch.from_numpy(g["x"]).cuda(), y)
+    assert rel(y.cpu().numpy()[:4 * N], g["y"][:4 * N]) <= 1e-13
+    F = torch.from_numpy(g["F"]).cuda()
+    dx = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    it, hist = fs.krylov_solve(dx, F)
+    assert it == int(g["printed"][-1, 0])
+    assert rel(dx.cpu().numpy()[:4 * N], g["dx"][:4 * N]) <= TOL_SOLVE
+    for k, v in g["printed"]:                                            # the reference's own printout, 5 digits
+        assert abs(hist[int(k)] - v) <= 6e-5 * v
+    fs.atol = fs.rtol = 0.0
+    dx = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    it, hist = fs.krylov_solve(dx, F)
+    for k, r in zip(g["res_iters"], g["res_true"]):                      # true residuals of the truncated reference solves
+        assert abs(hist[int(k)] - r) <= TOL_SOLVE * hist[0]
+    assert rel(dx.cpu().numpy()[:4 * N], g["dx120"][:4 * N]) <= TOL_SOLVE
+    fs.close()

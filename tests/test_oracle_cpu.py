@@ -1,0 +1,231 @@
+"""CPU-side tests (pytest -m "not gpu"): the oracle against structural properties and known answers, the element
+arithmetic of the kernels (probed on the host) against the oracle, and the C-ABI surface of the library."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, shuffled_mesh
+from dedflow_b200 import boxmesh
+from oracle import pyoracle
+
+
+def test_box_mesh_counts():
+    m = boxmesh.make_box(20)
+    assert m.num_tet == 48000 and m.num_node == 9261          # BASELINE config 1
+    x = m.xg[m.ien]
+    J = np.stack([x[:, 1] - x[:, 0], x[:, 2] - x[:, 0], x[:, 3] - x[:, 0]], axis=2)
+    det = np.linalg.det(J)
+    assert det.min() > 0 and abs(det.sum() / 6 - 1.0) < 1e-12  # positively oriented, fills the unit cube
+    for b in range(6):
+        assert len(m.bound_nodes(b)) == 21 * 21 and len(m.bound_faces(b)[0]) == 2 * 20 * 20
+
+
+def test_curand_known_answer():
+    # cuRAND host XORWOW, seed 1234 -- first draws and the weights derived from them
+    raw = pyoracle.curand_host_u32(8)
+    assert raw.tolist() == [624778773, 3522650202, 2363946744, 1266286439, 3928747533, 3732235839, 1382638835, 3362343509]
+    w = pyoracle.get().weights(raw)
+    assert w.tolist() == [624778773, 301424733, 216463098, 192544616, 707522064, 511010370, 308897012, 141118040]
+
+
+def test_pattern_properties(oracle):
+    m = boxmesh.make_box(5)
+    rp, ci = oracle.nodal_pattern(m.num_node, m.ien)
+    # independent construction with numpy sets
+    adj = [set([i]) for i in range(m.num_node)]
+    for e in m.ien:
+        for a in e:
+            adj[a].update(e.tolist())
+    for i in range(m.num_node):
+        assert ci[rp[i]:rp[i + 1]].tolist() == sorted(adj[i])
+    assert np.diff(rp).max() == 15
+    for br, bc in ((3, 3), (3, 1), (1, 3)):
+        nrp, nci = oracle.expand_block(rp, ci, br, bc)
+        assert nrp[-1] == ci.size * br * bc and np.all(np.diff(nrp) >= 0)
+        # scalar row i*br+j holds columns col*bc+l, k outer / l inner
+        i, j = 17, br - 1
+        row = nci[nrp[i * br + j]:nrp[i * br + j + 1]]
+        want = (ci[rp[i]:rp[i + 1]][:, None] * bc + np.arange(bc)[None, :]).ravel()
+        assert row.tolist() == want.tolist()
+        nrp0, _ = oracle.expand_block(rp, ci, br, bc, fix_last=False)
+        assert nrp0[-1] == 0 and np.array_equal(nrp0[:-1], nrp[:-1])      # defect D1
+
+
+def test_coloring_valid_and_is_dag_depth(oracle):
+    m = boxmesh.make_box(6)
+    w = oracle.weights(pyoracle.curand_host_u32(m.num_tet))
+    color, rounds, ties = oracle.color_jpl(m.num_node, m.ien, w)
+    assert ties == 0 and color.min() == 0 and color.max() + 1 == rounds
+    for c in range(rounds):
+        nodes = m.ien[color == c].ravel()
+        assert len(np.unique(nodes)) == len(nodes)
+    # JPL on tie-free weights == longest-path depth in the weight-oriented conflict graph
+    rp, cidx = oracle.v2e(m.num_node, m.ien)
+    order = np.argsort(-w.astype(np.int64))
+    depth = np.full(m.num_tet, -1)
+    for e in order:
+        nb = np.unique(np.concatenate([cidx[rp[n]:rp[n + 1]] for n in m.ien[e]]))
+        nb = nb[(nb != e) & (w[nb] > w[e])]
+        depth[e] = 0 if nb.size == 0 else depth[nb].max() + 1
+    assert np.array_equal(depth, color)
+    off, ind = oracle.color_batches(color)
+    assert off[-1] == m.num_tet
+    for c in range(rounds):
+        seg = ind[off[c]:off[c + 1]]
+        assert np.all(color[seg] == c) and np.all(np.diff(seg) > 0)
+
+
+def _assemble_oracle(O, m, wg, dwg):
+    N = m.num_node
+    rp, ci = O.nodal_pattern(N, m.ien)
+    Z = ci.size
+    w = O.weights(pyoracle.curand_host_u32(m.num_tet))
+    color, nc, _ = O.color_jpl(N, m.ien, w)
+    off, ind = O.color_batches(color)
+    F = np.zeros(6 * N)
+    blocks = [np.zeros(9 * Z), np.zeros(3 * Z), np.zeros(3 * Z), np.zeros(Z)]
+    O.assemble_tet(N, m.ien, m.xg, off, ind, wg, dwg, F=F)
+    O.assemble_tet(N, m.ien, m.xg, off, ind, wg, dwg, pattern=(rp, ci), blocks=blocks)
+    f2e, forn = m.bound_faces(4)
+    O.assemble_face(f2e, forn, N, m.ien, m.xg, color, nc, wg, dwg, F=F)
+    O.assemble_face(f2e, forn, N, m.ien, m.xg, color, nc, wg, dwg, pattern=(rp, ci), blocks=blocks)
+    F[4 * N:] = 0
+    for b, t in {0: (1, 1, 1), 2: (0, 1, 0), 3: (0, 0, 1), 4: (0, 0, 0)}.items():
+        O.dirichlet_vec(m.bound_nodes(b), np.array(t, np.int32), F)
+        O.dirichlet_mat(m.bound_nodes(b), np.array(t, np.int32), N, (rp, ci), blocks[0], blocks[1])
+    return (rp, ci), F, blocks
+
+
+def test_oracle_assembly_matches_dense_reassembly(oracle):
+    """The CSR scatter + Dirichlet of the oracle against a dense re-assembly of the per-element checkpoints."""
+    m = shuffled_mesh(3)
+    N = m.num_node
+    wg, dwg = boxmesh.state_random(N)
+    (rp, ci), F, blocks = _assemble_oracle(oracle, m, wg, dwg)
+    eF, eJ, _, _ = oracle.tet_elements(N, m.ien, m.xg, wg, dwg)
+    D = np.zeros((4 * N, 4 * N))
+    Fd = np.zeros(6 * N)
+
+    def dof(n, i):
+        return n * 3 + i if i < 3 else 3 * N + n
+
+    def add(nodes, ef, ej):
+        for a in range(4):
+            for i in range(3):
+                Fd[nodes[a] * 3 + i] += ef[a, i]
+            Fd[3 * N + nodes[a]] += ef[a, 3]
+            for b in range(4):
+                for i in range(4):
+                    for j in range(4):
+                        D[dof(nodes[a], i), dof(nodes[b], j)] += ej[a, b, i, j]
+    for e in range(m.num_tet):
+        add(m.ien[e], eF[e], eJ[e])
+    f2e, forn = m.bound_faces(4)
+    fF, fJ = oracle.face_elements(f2e, forn, N, m.ien, m.xg, wg, dwg)
+    for k, e in enumerate(f2e):
+        add(m.ien[e], fF[k], fJ[k])
+    for b, t in {0: (1, 1, 1), 2: (0, 1, 0), 3: (0, 0, 1)}.items():
+        for n in m.bound_nodes(b):
+            for ic in range(3):
+                if t[ic]:
+                    Fd[n * 3 + ic] = 0
+                    D[n * 3 + ic, :] = 0
+                    D[n * 3 + ic, n * 3 + ic] = 1
+    assert np.abs(F - Fd).max() <= 1e-13 * np.abs(Fd).max()
+    x = np.random.default_rng(0).standard_normal(6 * N)
+    y = np.zeros(6 * N)
+    oracle.fs_amvpby((rp, ci), blocks, 1.0, x, 0.0, y)
+    yd = D @ x[:4 * N]
+    assert np.abs(y[:4 * N] - yd).max() <= 1e-12 * np.abs(yd).max()
+    assert np.all(y[4 * N:] == 0)                                   # defect D4: rows [4N,6N) untouched
+
+
+def test_oracle_gmres_consistent(oracle):
+    m = boxmesh.make_box(6)
+    N = m.num_node
+    wg, dwg = boxmesh.state_random(N)
+    pat, F, blocks = _assemble_oracle(oracle, m, wg, dwg)
+    x, it, hist = oracle.gmres(pat, blocks, F)
+    assert it % 20 == 0 and it <= 120                                # defect D10
+    y = np.zeros(6 * N)
+    oracle.fs_amvpby(pat, blocks, 1.0, x, 0.0, y)
+    true_res = np.linalg.norm(F[:4 * N] - y[:4 * N])
+    assert abs(true_res - hist[-1]) <= 1e-8 * hist[0]
+    assert np.all(np.diff(hist) <= 1e-12 * hist[0])                  # GMRES residuals are non-increasing
+    # block-Jacobi applies (B^-1)^T (defect D3)
+    d00, d11 = oracle.pc_setup(pat, blocks)
+    rp, ci = pat
+    i = 100
+    k = rp[i] + np.searchsorted(ci[rp[i]:rp[i + 1]], i)
+    ln = rp[i + 1] - rp[i]
+    B = np.array([[blocks[0][rp[i] * 9 + (k - rp[i]) * 3 + r * ln * 3 + c] for c in range(3)] for r in range(3)])
+    v = np.zeros(6 * N)
+    v[3 * i:3 * i + 3] = [1.0, 2.0, 3.0]
+    out = oracle.pc_apply(d00, d11, v)
+    assert np.allclose(out[3 * i:3 * i + 3], np.linalg.inv(B).T @ [1.0, 2.0, 3.0], rtol=1e-10)
+
+
+@pytest.fixture(scope="module")
+def probe():
+    src = ROOT / "tests" / "cpu_probe" / "probe.cpp"
+    so = ROOT / "tests" / "cpu_probe" / "libprobe.so"
+    hdr = ROOT / "dedflow_b200" / "csrc" / "elem_math.cuh"
+    if not so.exists() or so.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime):
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", str(so), str(src)], check=True)
+    return C.CDLL(str(so))
+
+
+def test_kernel_element_math_matches_oracle(oracle, probe):
+    """The hoisted Jacobian / residual / face arithmetic the CUDA kernels use (elem_math.cuh, evaluated on the host)
+    against the reference-ordered oracle: max|d| / max|A| <= 1e-12 per sub-block."""
+    m = shuffled_mesh(6)
+    N, E = m.num_node, m.num_tet
+    for wg, dwg in (boxmesh.state_random(N), boxmesh.state_default(m)):
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        eF = np.zeros((E, 4, 6))
+        eJ = np.zeros((E, 4, 4, 4, 4))
+        probe.probe_tet(E, N, vp(m.ien), vp(m.xg), vp(wg), vp(dwg), vp(eF), vp(eJ))
+        oF, oJ, _, _ = oracle.tet_elements(N, m.ien, m.xg, wg, dwg)
+        assert np.abs(eF - oF).max() <= 1e-12 * np.abs(oF).max()
+        for i0, i1, j0, j1 in ((0, 3, 0, 3), (0, 3, 3, 4), (3, 4, 0, 3), (3, 4, 3, 4)):
+            a, b = eJ[..., i0:i1, j0:j1], oJ[..., i0:i1, j0:j1]
+            assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max()
+        for b in range(6):
+            f2e, forn = m.bound_faces(b)
+            assert set(np.unique(forn)) == {0, 1, 2, 3}
+            fF = np.zeros((len(f2e), 4, 6))
+            fJ = np.zeros((len(f2e), 4, 4, 4, 4))
+            probe.probe_face(len(f2e), vp(f2e), vp(forn), N, vp(m.ien), vp(m.xg), vp(wg), vp(dwg), vp(fF), vp(fJ))
+            gF, gJ = oracle.face_elements(f2e, forn, N, m.ien, m.xg, wg, dwg)
+            assert np.abs(fF - gF).max() <= 1e-12 * max(np.abs(gF).max(), 1e-300)
+            assert np.abs(fJ - gJ[..., :4, :4]).max() <= 1e-12 * np.abs(gJ).max()
+
+
+def test_abi_library_exports_every_declared_symbol():
+    """libdedflow_b200.so loads on a GPU-less host and exports exactly what include/*.h declares."""
+    from dedflow_b200 import _build, lib
+    _build.build()
+    L = lib.load()
+    assert L.dfb_version() >= 100
+    declared = set()
+    for h in (ROOT / "include").glob("*.h"):
+        text = re.sub(r"/\*.*?\*/", "", h.read_text(), flags=re.S)
+        text = re.sub(r"typedef[^;{]*\(\s*\*[^;]*;", "", text)          # function-pointer typedefs
+        declared |= set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", text))
+    declared = {d for d in declared if not d.startswith("(")}
+    missing = [d for d in sorted(declared) if not hasattr(L, d)]
+    assert not missing, f"declared but not exported: {missing}"
+    assert set(lib.exported_symbols()) <= declared
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from dedflow_b200 import api, lib
+    with pytest.raises(lib.DfbError):
+        api.FlowSystem(boxmesh.make_box(2))
