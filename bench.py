@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the DEDFlow FEM linear-system hot path on B200.
+
+A STEP is one pass of the hot path the reference executes per Newton iteration (reference src/main.c:157-221):
+    AssembleSystem(F)  +  AssembleSystem(J)  (tets + weak-BC faces + Dirichlet)  +  KrylovSolve(ksp, J, dx, F)
+on the synthetic Kuhn box mesh of BASELINE.json configs[1] (m=55: 998,250 tets, 175,616 nodes, fp64), state B.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--m 55] [--impl ours|reference]
+
+Prints ONE JSON line (see the keys below).  `value` = elements / second through the whole step with inputs resident
+in HBM; `e2e` = the same with host buffers (pinned H2D of the nodal states, D2H of the solution inside the timed
+region); `breakdown` carries the three quantities BASELINE.json names separately (assembly elems/s, SpMV GB/s and
+% of measured HBM peak, Krylov solve s/step); `roofline` is the dominant kernel of the step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "assembled elems/s"
+UNIT = "elems/s"
+
+
+def measured_hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ev_ms(torch, fn, reps):
+    """median CUDA-event time of fn() in ms"""
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def algorithmic_bytes(N, E, Z):
+    """SURVEY.md §8(d) / DESIGN.md: compulsory bytes per launch."""
+    return {
+        "assemble_J": 16 * E + 48 * N + 128 * Z,
+        "assemble_F": 16 * E + 160 * N,
+        "spmv": 132 * Z + 4 * (N + 1) + 64 * N,          # our single-index format: 16 f64 + 1 i32 per nodal nonzero
+        "spmv_reference_format": 192 * Z + 96 * N,       # four scalar-CSR blocks as cuSPARSE reads them
+    }
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_baseline(mesh, wg, dwg, with_solve=True):
+    """The oracle port of the same step timed on the host cores (reported baseline, not the target)."""
+    from oracle import pyoracle
+    O = pyoracle.get()
+    N, E = mesh.num_node, mesh.num_tet
+    t_setup = time.time()
+    rp, ci = O.nodal_pattern(N, mesh.ien)
+    w = O.weights(pyoracle.curand_host_u32(E))
+    color, nc, _ = O.color_jpl(N, mesh.ien, w)
+    off, ind = O.color_batches(color)
+    t_setup = time.time() - t_setup
+    Z = ci.size
+    F = np.zeros(6 * N)
+    blocks = [np.zeros(9 * Z), np.zeros(3 * Z), np.zeros(3 * Z), np.zeros(Z)]
+    f2e, forn = mesh.bound_faces(4)
+    bcs = {0: (1, 1, 1), 2: (0, 1, 0), 3: (0, 0, 1), 4: (0, 0, 0)}
+    t0 = time.time()
+    O.assemble_tet(N, mesh.ien, mesh.xg, off, ind, wg, dwg, F=F)
+    O.assemble_face(f2e, forn, N, mesh.ien, mesh.xg, color, nc, wg, dwg, F=F)
+    F[4 * N:] = 0
+    for b, t in bcs.items():
+        O.dirichlet_vec(mesh.bound_nodes(b), np.array(t, np.int32), F)
+    tF = time.time() - t0
+    t0 = time.time()
+    O.assemble_tet(N, mesh.ien, mesh.xg, off, ind, wg, dwg, pattern=(rp, ci), blocks=blocks)
+    O.assemble_face(f2e, forn, N, mesh.ien, mesh.xg, color, nc, wg, dwg, pattern=(rp, ci), blocks=blocks)
+    for b, t in bcs.items():
+        O.dirichlet_mat(mesh.bound_nodes(b), np.array(t, np.int32), N, (rp, ci), blocks[0], blocks[1])
+    tJ = time.time() - t0
+    ts, it = 0.0, 0
+    if with_solve:
+        t0 = time.time()
+        x, it, hist = O.gmres((rp, ci), blocks, F)
+        ts = time.time() - t0
+    step = tF + tJ + ts
+    return {"value": E / step, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+            "sample": f"1 full step (assemble F {tF:.2f}s + J {tJ:.2f}s + GMRES {it} its {ts:.2f}s) of the m={mesh.m} mesh, "
+                      f"oracle/oracle.c with OpenMP",
+            "assemble_elems_per_s": E / (tF + tJ), "solve_s_per_step": ts, "setup_s": t_setup}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: the reference's OWN implementation of the step.  The reference has no CPU implementation of this
+    path -- its only implementation is CUDA -- so when oracle/_ref (built from /root/reference/src, unmodified) loads and
+    a GPU is present, that is what is timed (kind "reference"); otherwise the oracle port runs on the host cores."""
+    if rank != 0:
+        return
+    from dedflow_b200 import boxmesh
+    mesh = boxmesh.make_box(args.m)
+    N, E = mesh.num_node, mesh.num_tet
+    wg, dwg = boxmesh.state_random(N)
+    line = {"metric": METRIC, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"Kuhn box m={args.m}: {E} tets, {N} nodes; step = AssembleSystem(F)+AssembleSystem(J)+KrylovSolve"}}
+    use_cuda_ref = False
+    try:
+        import torch
+        from oracle.ref import reflib
+        use_cuda_ref = torch.cuda.is_available() and reflib.available() and not args.ref_port
+    except Exception:
+        use_cuda_ref = False
+    if use_cuda_ref:
+        R = reflib.RefProblem(mesh, patch_d1=True)
+        R.color_batches()
+        d_wg, d_dwg = torch.from_numpy(wg).cuda(), torch.from_numpy(dwg).cuda()
+        F = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+        dx = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+        its = [0]
+
+        def step():
+            R.assemble(d_wg, d_dwg, F_t=F)
+            R.assemble(d_wg, d_dwg, J=True)
+            dx.zero_()
+            h = R.solve(dx, F)
+            its[0] = h[-1][0] if h else 0
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        sampler = ClockSampler()
+        sampler.start()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / args.steps
+        clocks = sampler.stop()
+        tF = ev_ms(torch, lambda: R.assemble(d_wg, d_dwg, F_t=F), 3)
+        tJ = ev_ms(torch, lambda: R.assemble(d_wg, d_dwg, J=True), 3)
+        xs = torch.randn(6 * N, dtype=torch.float64, device="cuda")
+        ys = torch.zeros_like(xs)
+        tmv = ev_ms(torch, lambda: R.matvec(xs, ys), 20)
+        Z = int(R.spy1x1.contents.nnz)
+        ab = algorithmic_bytes(N, E, Z)
+        val = E / (ms * 1e-3)
+        line.update({"value": val, "ms_per_step": ms, "clocks": clocks,
+                     "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference",
+                                      "sample": f"{args.steps} full steps of the m={args.m} mesh by the reference's own CUDA build "
+                                                "(oracle/_ref/libdedflow_ref.so, sm_100, D1 patched) on this GPU, driven by one host thread"},
+                     "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "breakdown": {"assemble_F_ms": tF, "assemble_J_ms": tJ, "assemble_elems_per_s": E / ((tF + tJ) * 1e-3),
+                                   "spmv_ms": tmv, "spmv_gbs_reference_format": ab["spmv_reference_format"] / (tmv * 1e-3) / 1e9,
+                                   "solve_s_per_step": max(ms - tF - tJ, 0.0) * 1e-3, "gmres_iters": its[0]}})
+    else:
+        # bounded sample on the host cores
+        t0 = time.time()
+        cb = None
+        for _ in range(max(1, min(args.steps, 2))):
+            cb = cpu_baseline(mesh, wg, dwg)
+        ms = (time.time() - t0) / max(1, min(args.steps, 2)) * 1e3
+        line.update({"value": cb["value"], "ms_per_step": ms, "cpu_baseline": cb,
+                     "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world):
+    import torch
+    from dedflow_b200 import boxmesh, lib as dlib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the host baseline)")
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        from dedflow_b200 import dist as ddist
+        return ddist.bench_main(args, rank, world, local_rank)
+    from dedflow_b200 import api
+    mesh = boxmesh.make_box(args.m)
+    N, E = mesh.num_node, mesh.num_tet
+    t0 = time.time()
+    fs = api.FlowSystem(mesh, device=f"cuda:{local_rank}")
+    torch.cuda.synchronize()
+    setup_s = time.time() - t0
+    Z = fs.nnz
+    wg, dwg = boxmesh.state_random(N)
+    h_wg = torch.from_numpy(wg).pin_memory()
+    h_dwg = torch.from_numpy(dwg).pin_memory()
+    h_dx = torch.zeros(6 * N, dtype=torch.float64).pin_memory()
+    d_wg, d_dwg = h_wg.cuda(), h_dwg.cuda()
+    F = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    dx = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    state = {"iters": 0, "hist": None}
+
+    def step():
+        fs.assemble_system(d_wg, d_dwg, F=F, mode=args.mode)
+        fs.assemble_system(d_wg, d_dwg, J=True, mode=args.mode)
+        dx.zero_()
+        state["iters"], state["hist"] = fs.krylov_solve(dx, F)
+
+    def step_e2e():
+        d_wg.copy_(h_wg, non_blocking=True)
+        d_dwg.copy_(h_dwg, non_blocking=True)
+        step()
+        h_dx.copy_(dx, non_blocking=True)
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)      # nvidia-smi needs ~0.3 s to deliver its first sample: start it before the
+    sampler.start()                         # warm-up so that samples exist for the (short) timed region
+    t_w = time.time()
+    nw = 0
+    while nw < max(args.warmup, 3) or time.time() - t_w < 1.0:
+        step()
+        nw += 1
+    torch.cuda.synchronize()
+    l0 = dlib.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(args.steps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / args.steps
+    launches = dlib.launch_count() - l0
+    # end-to-end through the C ABI with host buffers
+    step_e2e()
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(args.steps):
+        step_e2e()
+    b.record()
+    torch.cuda.synchronize()
+    ms_e2e = max(a.elapsed_time(b), (time.perf_counter() - t0) * 1e3) / args.steps
+    clocks = sampler.stop()
+    clocks["window"] = "warm-up + timed steps + e2e steps"
+
+    # ---- breakdown: the three quantities BASELINE.json names, each event-timed on its own ----
+    hbm, hbm_src = measured_hbm_peak()
+    ab = algorithmic_bytes(N, E, Z)
+    tF = ev_ms(torch, lambda: fs.assemble_system(d_wg, d_dwg, F=F, mode=args.mode), 10)
+    tJ = ev_ms(torch, lambda: fs.assemble_system(d_wg, d_dwg, J=True, mode=args.mode), 10)
+    import ctypes as C
+    P = lambda t: C.c_void_p(t.data_ptr())
+    st = fs._stream()
+    tJk = ev_ms(torch, lambda: fs.L.dfb_assemble_tet(fs.plan, P(fs.xg), P(d_wg), P(d_dwg), None, P(fs.A00), P(fs.A01), P(fs.A10),
+                                                    P(fs.A11), 1, 1, st), 10)
+    tFk = ev_ms(torch, lambda: fs.L.dfb_assemble_tet(fs.plan, P(fs.xg), P(d_wg), P(d_dwg), P(F), None, None, None, None, 1, 1, st), 10)
+    fs.assemble_system(d_wg, d_dwg, F=F, mode=args.mode)
+    fs.assemble_system(d_wg, d_dwg, J=True, mode=args.mode)
+    xs = torch.randn(6 * N, dtype=torch.float64, device="cuda")
+    ys = torch.zeros_like(xs)
+
+    def spmv_loop():
+        for _ in range(20):
+            fs.matrix_matvec(xs, ys)
+    t_spmv = ev_ms(torch, spmv_loop, 5) / 20
+
+    def solve():
+        dx.zero_()
+        state["iters"], state["hist"] = fs.krylov_solve(dx, F)
+    t_solve = ev_ms(torch, solve, 3)
+    its = state["iters"]
+    # Krylov algorithmic bytes with our SpMV format, n_eff = 4N live rows
+    nl = 4 * N
+    krylov_bytes = its * ab["spmv"] + sum(16 * nl * (j + 1) + 48 * nl for j in range(its)) + 8 * nl * its + 32 * nl
+    roofs = {
+        "k_spmv_fs": {"ms": t_spmv, "bytes": ab["spmv"]},
+        "k_rowJ (assemble J, gather)": {"ms": tJk, "bytes": ab["assemble_J"]},
+        "k_elemF+k_gatherF (assemble F, gather)": {"ms": tFk, "bytes": ab["assemble_F"]},
+        "KrylovSolve (all kernels)": {"ms": t_solve, "bytes": krylov_bytes},
+    }
+    for k, v in roofs.items():
+        v["achieved"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+        v["frac"] = v["achieved"] / hbm
+    # dominant kernel of the step: the Krylov solve is >90% of it; inside it the SpMV, the multi-dot and the update each
+    # stream comparable bytes.  The named kernel is the SpMV (the one BASELINE.json's metric quotes).
+    spmv_share = its * t_spmv / ms
+    roofline = {"kernel": "k_spmv_fs", "bound": "hbm", "achieved": roofs["k_spmv_fs"]["achieved"], "peak": hbm, "unit": "GB/s",
+                "frac": roofs["k_spmv_fs"]["frac"], "traffic": None, "peak_source": hbm_src,
+                "bytes_per_launch": ab["spmv"], "ms_per_launch": t_spmv, "share_of_step": spmv_share,
+                "achieved_reference_format": ab["spmv_reference_format"] / (t_spmv * 1e-3) / 1e9}
+    line = {
+        "metric": METRIC, "value": E / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": nw,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[1]: Kuhn box m={args.m}, {E} tets, {N} nodes, nnz {Z}; step = AssembleSystem(F) + "
+                               f"AssembleSystem(J) (tets+weak-BC faces+Dirichlet) + KrylovSolve (GMRES(120), {its} iterations to the "
+                               "reference's stopping rule), state B", "assembly_mode": args.mode,
+                   "l2": "working set (matrix 16*nnz*8 B + Krylov basis) exceeds the 126 MB L2; no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": E / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 2 * 6 * N * 8,
+                "d2h_bytes_per_step": 6 * N * 8 + 8 * (its + 1)},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "roofline_all": roofs,
+        "breakdown": {"assemble_F_ms": tF, "assemble_J_ms": tJ, "assemble_elems_per_s": E / ((tF + tJ) * 1e-3),
+                      "assemble_J_kernel_elems_per_s": E / (tJk * 1e-3), "spmv_ms": t_spmv, "spmv_gbs": roofs["k_spmv_fs"]["achieved"],
+                      "spmv_pct_hbm": 100 * roofs["k_spmv_fs"]["frac"], "solve_s_per_step": t_solve * 1e-3, "gmres_iters": its,
+                      "setup_s": setup_s, "final_residual": float(state["hist"][-1]), "initial_residual": float(state["hist"][0])},
+    }
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(mesh, wg, dwg)
+    print(json.dumps(line), flush=True)
+    fs.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--m", type=int, default=55, help="cells per direction of the box mesh (55 -> 998,250 tets)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="gather", choices=["gather", "atomic", "colored", "auto"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-port", action="store_true", help="--impl reference: force the host-core oracle port")
+    ap.add_argument("--fixed-m", action="store_true", help="N > 1: keep --m (strong scaling) instead of growing the mesh with N")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

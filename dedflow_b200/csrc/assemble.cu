@@ -116,10 +116,10 @@ __global__ void __launch_bounds__(128) k_elemF(int n, const int* __restrict__ el
 }
 
 // node gather: F[node] (+)= sum over the node's corners, ascending corner id
-__global__ void k_gatherF(int N, const int* __restrict__ v2c_ptr, const int* __restrict__ v2c,
+__global__ void k_gatherF(int N, int n_rows, const int* __restrict__ v2c_ptr, const int* __restrict__ v2c,
                           const f64* __restrict__ scratch, f64* __restrict__ F, int overwrite) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
+  if (i >= n_rows) return;
   f64 s[6] = {0, 0, 0, 0, 0, 0};
   for (int p = v2c_ptr[i]; p < v2c_ptr[i + 1]; p++) {
     const f64* src = scratch + (size_t)v2c[p] * 6;
@@ -404,7 +404,7 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
       }
       k_elemF<0><<<ceil_div(E, 128), 128, 0, st>>>(E, nullptr, N, P->ien, d_xg, d_wg, d_dwg, P->elemF);
       DFB_LAUNCH_CHECK();
-      k_gatherF<<<ceil_div(N, 128), 128, 0, st>>>(N, P->v2c_ptr, P->v2c, P->elemF, d_F, overwrite);
+      k_gatherF<<<ceil_div(P->n_rows, 128), 128, 0, st>>>(N, P->n_rows, P->v2c_ptr, P->v2c, P->elemF, d_F, overwrite);
       DFB_LAUNCH_CHECK();
     } else if (mode == DFB_MODE_ATOMIC) {
       k_elemF<1><<<ceil_div(E, 128), 128, 0, st>>>(E, nullptr, N, P->ien, d_xg, d_wg, d_dwg, d_F);
@@ -420,13 +420,13 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
   }
   if (doJ) {
     if (mode == DFB_MODE_GATHER) {
-      const int grid = ceil_div(N, 4);
+      const int grid = ceil_div(P->n_rows, 4);
       if (P->max_row_len <= 16)
-        k_rowJ<1><<<grid, 128, 0, st>>>(N, P->ien, d_xg, d_wg, P->row_ptr, P->v2c_ptr, P->v2c, slot32, d_A00, d_A01, d_A10, d_A11, overwrite);
+        k_rowJ<1><<<grid, 128, 0, st>>>(P->n_rows, P->ien, d_xg, d_wg, P->row_ptr, P->v2c_ptr, P->v2c, slot32, d_A00, d_A01, d_A10, d_A11, overwrite);
       else if (P->max_row_len <= 32)
-        k_rowJ<2><<<grid, 128, 0, st>>>(N, P->ien, d_xg, d_wg, P->row_ptr, P->v2c_ptr, P->v2c, slot32, d_A00, d_A01, d_A10, d_A11, overwrite);
+        k_rowJ<2><<<grid, 128, 0, st>>>(P->n_rows, P->ien, d_xg, d_wg, P->row_ptr, P->v2c_ptr, P->v2c, slot32, d_A00, d_A01, d_A10, d_A11, overwrite);
       else
-        k_rowJ<4><<<grid, 128, 0, st>>>(N, P->ien, d_xg, d_wg, P->row_ptr, P->v2c_ptr, P->v2c, slot32, d_A00, d_A01, d_A10, d_A11, overwrite);
+        k_rowJ<4><<<grid, 128, 0, st>>>(P->n_rows, P->ien, d_xg, d_wg, P->row_ptr, P->v2c_ptr, P->v2c, slot32, d_A00, d_A01, d_A10, d_A11, overwrite);
       DFB_LAUNCH_CHECK();
     } else if (mode == DFB_MODE_ATOMIC) {
       k_cornerJ<1><<<ceil_div(4 * (i64)E, 128), 128, 0, st>>>(E, nullptr, P->ien, d_xg, d_wg, P->row_ptr, slot32, d_A00, d_A01, d_A10, d_A11);

@@ -6,6 +6,7 @@
 
 struct dfb_plan {
   int N = 0, E = 0;
+  int n_rows = 0;                // rows produced by the gather kernels (== N unless data-parallel)
   const int* ien = nullptr;      // [4E] borrowed
   const int* row_ptr = nullptr;  // [N+1] nodal pattern, borrowed
   const int* col_ind = nullptr;  // [nnz] borrowed

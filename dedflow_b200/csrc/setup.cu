@@ -258,7 +258,7 @@ int dfb_plan_create(dfb_plan** out, int N, int E, const int* d_ien, const int* d
   cudaStream_t st = as_stream(stream);
   if (!out || N <= 0 || E <= 0 || !d_ien || !d_row_ptr || !d_col_ind) { set_error("dfb_plan_create: bad argument"); return DFB_ERR_ARG; }
   dfb_plan* p = new dfb_plan();
-  p->N = N; p->E = E; p->ien = d_ien; p->row_ptr = d_row_ptr; p->col_ind = d_col_ind;
+  p->N = N; p->E = E; p->n_rows = N; p->ien = d_ien; p->row_ptr = d_row_ptr; p->col_ind = d_col_ind;
   int s = build_v2c(N, E, d_ien, &p->v2c_ptr, &p->v2c, st);
   if (s != DFB_OK) { delete p; return s; }
   DFB_CUDA(cudaMalloc(&p->slot, (size_t)E * 16));
@@ -284,6 +284,12 @@ int dfb_plan_create(dfb_plan** out, int N, int E, const int* d_ien, const int* d
     p->batch_ind = d_batch_ind;
   }
   *out = p;
+  return DFB_OK;
+}
+
+int dfb_plan_set_rows(dfb_plan* p, int n_rows) {
+  if (!p || n_rows <= 0 || n_rows > p->N) { set_error("dfb_plan_set_rows: bad argument"); return DFB_ERR_ARG; }
+  p->n_rows = n_rows;
   return DFB_OK;
 }
 

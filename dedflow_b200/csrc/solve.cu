@@ -33,12 +33,12 @@ constexpr unsigned FULLM = 0xffffffffu;
 // ------------------------------------------------------------------------------------------------------------
 // SpMV.  Row i of the output: u -> y[3*i + ii], p -> y[y_poff + i]; input x: u -> x[3*c + l], p -> x[x_poff + c].
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_spmv_fs(int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
+__global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
                                                  const f64* __restrict__ A00, const f64* __restrict__ A01,
                                                  const f64* __restrict__ A10, const f64* __restrict__ A11, f64 alpha,
                                                  const f64* __restrict__ x, size_t x_poff, f64 beta, f64* __restrict__ y,
                                                  size_t y_poff) {
-  const int row = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int row = row0 + (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n_rows) return;
   const int start = __ldg(row_ptr + row), len = __ldg(row_ptr + row + 1) - start;
@@ -81,10 +81,12 @@ __global__ void __launch_bounds__(256) k_spmv_fs(int n_rows, const int* __restri
   }
 }
 
-int launch_spmv(int n_rows, const int* row_ptr, const int* col_ind, const f64* A00, const f64* A01, const f64* A10,
+// rows [row0, row1)
+int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, const f64* A00, const f64* A01, const f64* A10,
                 const f64* A11, f64 alpha, const f64* x, size_t x_poff, f64 beta, f64* y, size_t y_poff, cudaStream_t st) {
-  k_spmv_fs<<<ceil_div((i64)n_rows * 32, 256), 256, 0, st>>>(n_rows, row_ptr, col_ind, A00, A01, A10, A11, alpha, x, x_poff,
-                                                            beta, y, y_poff);
+  if (row1 <= row0) return DFB_OK;
+  k_spmv_fs<<<ceil_div((i64)(row1 - row0) * 32, 256), 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x,
+                                                                   x_poff, beta, y, y_poff);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
@@ -383,9 +385,9 @@ struct dfb_gmres {
   f64 *z = nullptr, *t = nullptr, *part = nullptr, *dinv00 = nullptr, *dinv11 = nullptr, *tail_coef = nullptr;
   GmresScalars* S = nullptr;
   size_t bytes = 0;
-  dfb_allreduce_fn allreduce = nullptr;
-  dfb_halo_fn halo = nullptr;
-  void* user = nullptr;
+  int n_interior = 0;
+  dfb_parallel_ops par = {0, 0, nullptr, nullptr, nullptr, nullptr};
+  bool parallel = false;
 };
 
 extern "C" {
@@ -394,7 +396,7 @@ int dfb_spmv_fs(int N, const int* d_row_ptr, const int* d_col_ind, const double*
                 const double* d_A10, const double* d_A11, double alpha, const double* d_x, double beta, double* d_y,
                 void* stream) {
   if (N <= 0 || !d_row_ptr || !d_col_ind || !d_A00 || !d_A01 || !d_A10 || !d_A11 || !d_x || !d_y) { set_error("dfb_spmv_fs: bad argument"); return DFB_ERR_ARG; }
-  return launch_spmv(N, d_row_ptr, d_col_ind, d_A00, d_A01, d_A10, d_A11, alpha, d_x, (size_t)3 * N, beta, d_y, (size_t)3 * N,
+  return launch_spmv(0, N, d_row_ptr, d_col_ind, d_A00, d_A01, d_A10, d_A11, alpha, d_x, (size_t)3 * N, beta, d_y, (size_t)3 * N,
                      as_stream(stream));
 }
 
@@ -417,7 +419,7 @@ int dfb_pc_apply(int N, const double* d_dinv00, const double* d_dinv11, const do
 int dfb_gmres_create(dfb_gmres** out, int N, int maxit) {
   if (!out || N <= 0 || maxit <= 0 || maxit > 127) { set_error("dfb_gmres_create: bad argument (max_iter must be in [1,127])"); return DFB_ERR_ARG; }
   dfb_gmres* w = new dfb_gmres();
-  w->N = N; w->n_own = N; w->maxit = maxit; w->ldh = ((maxit + 1 + 31) / 32) * 32;
+  w->N = N; w->n_own = N; w->n_interior = N; w->maxit = maxit; w->ldh = ((maxit + 1 + 31) / 32) * 32;
   const size_t nl = (size_t)4 * N;
   struct { f64** p; size_t n; } allocs[] = {
       {&w->Q, nl * ((size_t)maxit + 1)}, {&w->H, (size_t)w->ldh * maxit}, {&w->gv, (size_t)2 * maxit},
@@ -449,9 +451,12 @@ void dfb_gmres_destroy(dfb_gmres* w) {
 
 size_t dfb_gmres_bytes(const dfb_gmres* w) { return w ? w->bytes : 0; }
 
-int dfb_gmres_set_parallel(dfb_gmres* w, int n_own, dfb_allreduce_fn allreduce, dfb_halo_fn halo, void* user) {
-  if (!w || n_own <= 0 || n_own > w->N) { set_error("dfb_gmres_set_parallel: bad argument"); return DFB_ERR_ARG; }
-  w->n_own = n_own; w->allreduce = allreduce; w->halo = halo; w->user = user;
+int dfb_gmres_set_parallel(dfb_gmres* w, const dfb_parallel_ops* ops) {
+  if (!w) { set_error("dfb_gmres_set_parallel: bad argument"); return DFB_ERR_ARG; }
+  if (!ops) { w->parallel = false; w->n_own = w->N; w->n_interior = w->N; return DFB_OK; }
+  if (ops->n_own <= 0 || ops->n_own > w->N || ops->n_interior < 0 || ops->n_interior > ops->n_own || !ops->allreduce ||
+      !ops->halo_begin || !ops->halo_end) { set_error("dfb_gmres_set_parallel: bad argument"); return DFB_ERR_ARG; }
+  w->par = *ops; w->parallel = true; w->n_own = ops->n_own; w->n_interior = ops->n_interior;
   return DFB_OK;
 }
 
@@ -470,6 +475,18 @@ int dfb_gmres_solve(dfb_gmres* W, int N, const int* rp, const int* ci, const dou
 #define QCOL(c) (Q + (size_t)(c)*ldq)
 #define HCOL(c) (W->H + (size_t)(c)*ldh)
   const int vgrid = ceil_div((i64)nl, 256);
+  // y(compact) = beta*y + alpha * A x(local layout): interior rows overlap the ghost exchange of x
+  auto matvec = [&](f64 alpha, f64* x, f64 beta, f64* y) -> int {
+    if (W->parallel) {
+      DFB_CHECK(W->par.halo_begin(x, st, W->par.user));
+      DFB_CHECK(launch_spmv(0, W->n_interior, rp, ci, A00, A01, A10, A11, alpha, x, poffN, beta, y, poffC, st));
+      DFB_CHECK(W->par.halo_end(x, st, W->par.user));
+      DFB_CHECK(launch_spmv(W->n_interior, n_own, rp, ci, A00, A01, A10, A11, alpha, x, poffN, beta, y, poffC, st));
+    } else {
+      DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, alpha, x, poffN, beta, y, poffC, st));
+    }
+    return DFB_OK;
+  };
   // preconditioner setup on every solve, like KrylovSolve -> PCSetup (krylov.c:453)
   k_pc_setup<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, rp, ci, A00, A11, W->dinv00, W->dinv11);
   DFB_LAUNCH_CHECK();
@@ -477,8 +494,7 @@ int dfb_gmres_solve(dfb_gmres* W, int N, const int* rp, const int* ci, const dou
   // r0 = b - A x  (krylov.c:114-118)
   k_pack_live<<<vgrid, 256, 0, st>>>(n_own, d_b, poffN, QCOL(0));
   DFB_LAUNCH_CHECK();
-  if (W->halo) DFB_CHECK(W->halo(d_x, st, W->user));
-  DFB_CHECK(launch_spmv(n_own, rp, ci, A00, A01, A10, A11, -1.0, d_x, poffN, 1.0, QCOL(0), poffC, st));
+  DFB_CHECK(matvec(-1.0, d_x, 1.0, QCOL(0)));
   k_sumsq<<<NCHUNK, 256, 0, st>>>(nl, QCOL(0), W->part);
   DFB_LAUNCH_CHECK();
   k_final_sum<<<1, 32, 0, st>>>(W->part, &W->S->nrm2_live);
@@ -490,7 +506,7 @@ int dfb_gmres_solve(dfb_gmres* W, int N, const int* rp, const int* ci, const dou
   DFB_LAUNCH_CHECK();
   k_final_sum<<<1, 32, 0, st>>>(W->part + NCHUNK, &W->S->tail2);
   DFB_LAUNCH_CHECK();
-  if (W->allreduce) DFB_CHECK(W->allreduce(&W->S->nrm2_live, 2, st, W->user));
+  if (W->parallel) DFB_CHECK(W->par.allreduce(&W->S->nrm2_live, 2, st, W->par.user));
   k_gmres_begin<<<1, 1, 0, st>>>(W->S, W->beta, W->tailc, W->res_hist);
   DFB_LAUNCH_CHECK();
   k_scale<<<vgrid, 256, 0, st>>>(nl, QCOL(0), &W->S->inv_norm);
@@ -504,22 +520,21 @@ int dfb_gmres_solve(dfb_gmres* W, int N, const int* rp, const int* ci, const dou
     // z = P^-1 q_iter (local layout), w = A z
     k_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, W->dinv00, W->dinv11, QCOL(iter), poffC, W->z, poffN, 0, 0, 0);
     DFB_LAUNCH_CHECK();
-    if (W->halo) DFB_CHECK(W->halo(W->z, st, W->user));
     f64* w = QCOL(iter + 1);
-    DFB_CHECK(launch_spmv(n_own, rp, ci, A00, A01, A10, A11, 1.0, W->z, poffN, 0.0, w, poffC, st));
+    DFB_CHECK(matvec(1.0, W->z, 0.0, w));
     // h = Q^T w  (krylov.c:166-174)
     const int ncol = iter + 1;
     k_multidot<<<dim3(NCHUNK, ceil_div(ncol, JT)), 256, 0, st>>>(nl, Q, ldq, ncol, w, W->part);
     DFB_LAUNCH_CHECK();
     k_reduce_parts<<<ceil_div(ncol, 8), 256, 0, st>>>(ncol, W->part, HCOL(iter));
     DFB_LAUNCH_CHECK();
-    if (W->allreduce) DFB_CHECK(W->allreduce(HCOL(iter), ncol, st, W->user));
+    if (W->parallel) DFB_CHECK(W->par.allreduce(HCOL(iter), ncol, st, W->par.user));
     // w -= Q h, fused with ||w||^2  (krylov.c:176-183, 229-231)
     k_update<<<NCHUNK, 256, 0, st>>>(nl, Q, ldq, ncol, HCOL(iter), w, W->part);
     DFB_LAUNCH_CHECK();
     k_final_sum<<<1, 32, 0, st>>>(W->part, &W->S->nrm2_live);
     DFB_LAUNCH_CHECK();
-    if (W->allreduce) DFB_CHECK(W->allreduce(&W->S->nrm2_live, 1, st, W->user));
+    if (W->parallel) DFB_CHECK(W->par.allreduce(&W->S->nrm2_live, 1, st, W->par.user));
     k_gmres_step<<<1, 1, 0, st>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist);
     DFB_LAUNCH_CHECK();
     k_scale<<<vgrid, 256, 0, st>>>(nl, w, &W->S->inv_norm);
@@ -545,6 +560,10 @@ int dfb_gmres_solve(dfb_gmres* W, int N, const int* rp, const int* ci, const dou
     DFB_LAUNCH_CHECK();
     k_axpy_dev<<<ceil_div((i64)tail_n, 256), 256, 0, st>>>(tail_n, W->tail_coef, d_b + (size_t)4 * N, d_x + (size_t)4 * N);
     DFB_LAUNCH_CHECK();
+    if (W->parallel) {  // leave the ghosts of the solution consistent
+      DFB_CHECK(W->par.halo_begin(d_x, st, W->par.user));
+      DFB_CHECK(W->par.halo_end(d_x, st, W->par.user));
+    }
   }
   DFB_CUDA(cudaMemcpyAsync(hist.data(), W->res_hist, sizeof(f64) * ((size_t)iter + 1), cudaMemcpyDeviceToHost, st));
   DFB_CUDA(cudaStreamSynchronize(st));

@@ -1,0 +1,390 @@
+"""Data-parallel driver of the hot path: one process per GPU (torch.distributed for bootstrap only).
+
+Decomposition (the ownership notion of reference src/partition.c:16-77, which is dead code there):
+  * every node is owned by exactly one rank (`npart`; default: contiguous z-slabs of the structured box, which is what
+    a nodal METIS split of a box approximates);
+  * a rank keeps every element that touches an owned node ("ghost elements" are recomputed, so assembly needs no
+    communication and stays deterministic) and assembles the rows of its owned nodes only;
+  * local node numbering is [interior-owned | boundary-owned | ghost (grouped by owner)];
+  * per mat-vec the (u,p) values of boundary-owned nodes go to the neighbours (NCCL send/recv on a side stream,
+    overlapped with the interior rows); inner products are summed with ncclAllReduce.
+
+Pure numpy partition logic lives at module level (tested on CPU with gloo, world_size 2); everything touching the GPU
+is in DistFlowSystem.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+from dataclasses import dataclass
+
+import numpy as np
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# partition (numpy, no GPU)
+# ----------------------------------------------------------------------------------------------------------------
+def slab_owner(mesh, world: int) -> np.ndarray:
+    """Owner of every node for a z-slab split of the structured box: planes k are divided as evenly as possible."""
+    n1 = mesh.m + 1
+    plane_owner = np.zeros(n1, np.int32)
+    for r, chunk in enumerate(np.array_split(np.arange(n1), world)):
+        plane_owner[chunk] = r
+    k = np.arange(mesh.num_node) // (n1 * n1)
+    return plane_owner[k]
+
+
+@dataclass
+class LocalMesh:
+    rank: int
+    world: int
+    num_node_global: int
+    num_tet_global: int
+    nodes_g: np.ndarray        # [N_loc] global id of every local node, local order
+    elems_g: np.ndarray        # [E_loc] global id of every local element (ascending)
+    n_interior: int
+    n_own: int
+    ien: np.ndarray            # [E_loc,4] local node ids
+    xg: np.ndarray             # [N_loc,3]
+    neighbors: np.ndarray      # [nn]
+    send_offset: np.ndarray    # [nn+1]
+    send_nodes: np.ndarray     # local ids (owned), ascending global id per neighbour
+    recv_offset: np.ndarray
+    recv_nodes: np.ndarray     # local ids (ghost), ascending global id per neighbour
+    bound_nodes: dict          # boundary group -> local ids of OWNED nodes in the group
+    f2e: np.ndarray            # weak-BC faces (group 4): local element ids
+    forn: np.ndarray
+
+    @property
+    def num_node(self):
+        return self.nodes_g.size
+
+    @property
+    def num_tet(self):
+        return self.elems_g.size
+
+    def localize(self, v_global: np.ndarray) -> np.ndarray:
+        """6N-layout global vector -> 6N_loc-layout local vector (owned + ghost entries)."""
+        Ng, g = self.num_node_global, self.nodes_g
+        out = np.empty(6 * g.size)
+        out[:3 * g.size] = v_global[:3 * Ng].reshape(Ng, 3)[g].ravel()
+        for s in (3, 4, 5):
+            out[s * g.size:(s + 1) * g.size] = v_global[s * Ng + g]
+        return out
+
+    def scatter_owned(self, v_local: np.ndarray, v_global: np.ndarray):
+        """write the owned entries of a local 6N_loc vector into a global 6N vector"""
+        Ng, g, n = self.num_node_global, self.nodes_g[:self.n_own], self.nodes_g.size
+        v_global[:3 * Ng].reshape(Ng, 3)[g] = v_local[:3 * n].reshape(n, 3)[:self.n_own]
+        for s in (3, 4, 5):
+            v_global[s * Ng + g] = v_local[s * n:s * n + self.n_own]
+
+
+def partition(mesh, npart: np.ndarray, rank: int, world: int, weak_group: int = 4, bc_groups=(0, 2, 3, 4)) -> LocalMesh:
+    owned_mask = npart == rank
+    owner_e = npart[mesh.ien]                                  # [E,4]
+    el_mask = (owner_e == rank).any(axis=1)
+    elems_g = np.nonzero(el_mask)[0]
+    ien_g = mesh.ien[elems_g]
+    own_e = owner_e[elems_g]
+    nodes_all = np.unique(ien_g)
+    owned_g = nodes_all[owned_mask[nodes_all]]
+    ghost_g = nodes_all[~owned_mask[nodes_all]]
+    # (my node a, foreign owner q) pairs: a is needed by q  <=>  a shares an element with a q-owned node
+    mine = own_e == rank
+    pairs = []
+    for a in range(4):
+        for b in range(4):
+            sel = mine[:, a] & ~mine[:, b]
+            if sel.any():
+                pairs.append(np.stack([own_e[sel, b].astype(np.int64), ien_g[sel, a].astype(np.int64)], axis=1))
+    if pairs:
+        pr = np.unique(np.concatenate(pairs), axis=0)          # sorted by (q, global id)
+    else:
+        pr = np.zeros((0, 2), np.int64)
+    bnd_g = np.unique(pr[:, 1]).astype(ien_g.dtype)
+    interior_g = np.setdiff1d(owned_g, bnd_g, assume_unique=True)
+    ghost_owner = npart[ghost_g]
+    gorder = np.lexsort((ghost_g, ghost_owner))
+    ghost_sorted = ghost_g[gorder]
+    nodes_g = np.concatenate([interior_g, bnd_g, ghost_sorted]).astype(np.int64)
+    g2l = np.full(mesh.num_node, -1, np.int64)
+    g2l[nodes_g] = np.arange(nodes_g.size)
+    neighbors = np.unique(np.concatenate([pr[:, 0], ghost_owner[gorder].astype(np.int64)])).astype(np.int32)
+    send_off, recv_off, send_nodes, recv_nodes = [0], [0], [], []
+    gown_sorted = ghost_owner[gorder]
+    for q in neighbors:
+        s = pr[pr[:, 0] == q, 1]
+        r = ghost_sorted[gown_sorted == q]
+        send_nodes.append(g2l[s])
+        recv_nodes.append(g2l[r])
+        send_off.append(send_off[-1] + s.size)
+        recv_off.append(recv_off[-1] + r.size)
+    cat = lambda l: (np.concatenate(l) if l else np.zeros(0, np.int64)).astype(np.int32)
+    bound_nodes = {}
+    for b in bc_groups:
+        if b < mesh.num_bound:
+            gn = mesh.bound_nodes(b)
+            gn = gn[owned_mask[gn]]
+            bound_nodes[b] = g2l[gn].astype(np.int32)
+    if weak_group < mesh.num_bound:
+        f2e_g, forn_g = mesh.bound_faces(weak_group)
+        keep = el_mask[f2e_g]
+        f2e = np.searchsorted(elems_g, f2e_g[keep]).astype(np.int32)
+        forn = forn_g[keep].astype(np.int32)
+    else:
+        f2e, forn = np.zeros(0, np.int32), np.zeros(0, np.int32)
+    return LocalMesh(rank=rank, world=world, num_node_global=mesh.num_node, num_tet_global=mesh.num_tet, nodes_g=nodes_g,
+                     elems_g=elems_g, n_interior=interior_g.size, n_own=owned_g.size,
+                     ien=np.ascontiguousarray(g2l[ien_g].astype(np.int32)), xg=np.ascontiguousarray(mesh.xg[nodes_g]),
+                     neighbors=neighbors, send_offset=np.array(send_off, np.int32), send_nodes=cat(send_nodes),
+                     recv_offset=np.array(recv_off, np.int32), recv_nodes=cat(recv_nodes), bound_nodes=bound_nodes,
+                     f2e=f2e, forn=forn)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU side
+# ----------------------------------------------------------------------------------------------------------------
+class ParallelOps(C.Structure):
+    _fields_ = [("n_own", C.c_int), ("n_interior", C.c_int), ("allreduce", C.c_void_p), ("halo_begin", C.c_void_p),
+                ("halo_end", C.c_void_p), ("user", C.c_void_p)]
+
+
+class DistFlowSystem:
+    """The hot path of one rank.  Needs torch.distributed initialised (any backend) for the NCCL id broadcast."""
+
+    def __init__(self, lm: LocalMesh, device, bcs=None, max_iter=120, atol=1e-12, rtol=1e-4):
+        import torch
+        import torch.distributed as dist
+        from . import api, lib as _lib
+        self.torch, self._lib = torch, _lib
+        self.L = _lib.load()
+        self.lm = lm
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        L = self.L
+        self.N, self.E = lm.num_node, lm.num_tet
+        self.n_own, self.n_int = lm.n_own, lm.n_interior
+        self.ien = torch.from_numpy(lm.ien.reshape(-1)).to(self.dev)
+        self.xg = torch.from_numpy(lm.xg.reshape(-1)).to(self.dev)
+        self.bcs = dict(api.DEFAULT_BCS if bcs is None else bcs)
+        self.bnode = {b: torch.from_numpy(lm.bound_nodes[b]).to(self.dev) for b in self.bcs if b in lm.bound_nodes}
+        self.f2e = torch.from_numpy(lm.f2e).to(self.dev)
+        self.forn = torch.from_numpy(lm.forn).to(self.dev)
+        self.max_iter, self.atol, self.rtol = max_iter, atol, rtol
+        p = lambda t: C.c_void_p(t.data_ptr())
+        st = self._stream()
+        # local pattern (rows of ghost nodes are incomplete and never used)
+        self.row_ptr = torch.empty(self.N + 1, dtype=torch.int32, device=self.dev)
+        nnz = C.c_int(0)
+        _lib.check(L.dfb_pattern_rows(self.N, self.E, p(self.ien), p(self.row_ptr), C.byref(nnz), st), "dfb_pattern_rows")
+        self.nnz = nnz.value
+        self.col_ind = torch.empty(self.nnz, dtype=torch.int32, device=self.dev)
+        _lib.check(L.dfb_pattern_cols(self.N, self.E, p(self.ien), p(self.row_ptr), p(self.col_ind), st), "dfb_pattern_cols")
+        Z = self.nnz
+        self.A = [torch.zeros(k * Z, dtype=torch.float64, device=self.dev) for k in (9, 3, 3, 1)]
+        plan = C.c_void_p()
+        _lib.check(L.dfb_plan_create(C.byref(plan), self.N, self.E, p(self.ien), p(self.row_ptr), p(self.col_ind), 0, None,
+                                     None, st), "dfb_plan_create")
+        self.plan = plan
+        _lib.check(L.dfb_plan_set_rows(plan, self.n_own), "dfb_plan_set_rows")
+        # communicator
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if lm.rank == 0:
+            raw = (C.c_ubyte * 128)()
+            _lib.check(L.dfb_comm_unique_id(raw), "dfb_comm_unique_id")
+            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            idbuf = idbuf.to(self.dev)
+        dist.broadcast(idbuf, src=0)
+        raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
+        comm = C.c_void_p()
+        _lib.check(L.dfb_comm_create(C.byref(comm), lm.rank, lm.world, raw), "dfb_comm_create")
+        self.comm = comm
+        ip = lambda a: np.ascontiguousarray(a, np.int32).ctypes.data_as(C.c_void_p)
+        self._halo_keep = [np.ascontiguousarray(a, np.int32) for a in (lm.neighbors, lm.send_offset, lm.send_nodes,
+                                                                     lm.recv_offset, lm.recv_nodes)]
+        _lib.check(L.dfb_comm_set_halo(comm, self.N, lm.neighbors.size, *[a.ctypes.data_as(C.c_void_p) for a in self._halo_keep]),
+                   "dfb_comm_set_halo")
+        ws = C.c_void_p()
+        _lib.check(L.dfb_gmres_create(C.byref(ws), self.N, max_iter), "dfb_gmres_create")
+        self.gmres = ws
+        fn = lambda name: C.cast(getattr(L, name), C.c_void_p).value
+        self.ops = ParallelOps(self.n_own, self.n_int, fn("dfb_comm_allreduce"), fn("dfb_comm_halo_begin"),
+                               fn("dfb_comm_halo_end"), comm.value)
+        _lib.check(L.dfb_gmres_set_parallel(ws, C.byref(self.ops)), "dfb_gmres_set_parallel")
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def assemble_system(self, wg, dwg, F=None, J=False):
+        L, N, st, _lib = self.L, self.N, self._stream(), self._lib
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        A = self.A if J else [None] * 4
+        _lib.check(L.dfb_assemble_tet(self.plan, p(self.xg), p(wg), p(dwg), p(F), *[p(a) for a in A], 1, 1, st), "dfb_assemble_tet")
+        if self.f2e.numel():
+            _lib.check(L.dfb_assemble_face(self.plan, self.f2e.numel(), p(self.f2e), p(self.forn), p(self.xg), p(wg), p(dwg), p(F),
+                                           *[p(a) for a in A], st), "dfb_assemble_face")
+        if F is not None:
+            F[4 * N:].zero_()
+        for b, types in self.bcs.items():
+            if b not in self.bnode or self.bnode[b].numel() == 0:
+                continue
+            t = (C.c_int * 3)(*types)
+            if F is not None:
+                _lib.check(L.dfb_dirichlet_vec(self.bnode[b].numel(), p(self.bnode[b]), 3, t, p(F), st), "dfb_dirichlet_vec")
+            if J:
+                _lib.check(L.dfb_dirichlet_mat(self.bnode[b].numel(), p(self.bnode[b]), 3, t, N, p(self.row_ptr), p(self.col_ind),
+                                               p(self.A[0]), p(self.A[1]), st), "dfb_dirichlet_mat")
+
+    def krylov_solve(self, dx, F):
+        iters = C.c_int(0)
+        hist = np.zeros(self.max_iter + 1)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._lib.check(self.L.dfb_gmres_solve(self.gmres, self.N, p(self.row_ptr), p(self.col_ind), *[p(a) for a in self.A], p(dx),
+                                               p(F), self.atol, self.rtol, C.byref(iters), hist.ctypes.data_as(C.c_void_p),
+                                               self._stream()), "dfb_gmres_solve")
+        return iters.value, hist[:iters.value + 1]
+
+    def matvec_owned(self, x, y):
+        """y[owned rows, compact 4*n_own] = A x (ghosts of x refreshed first) -- used by the parity script."""
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._lib.check(self.L.dfb_comm_halo(self.comm, p(x), self._stream()), "dfb_comm_halo")
+        self._lib.check(self.L.dfb_spmv_fs(self.N, p(self.row_ptr), p(self.col_ind), *[p(a) for a in self.A], 1.0, p(x), 0.0, p(y),
+                                           self._stream()), "dfb_spmv_fs")
+
+    def close(self):
+        if getattr(self, "gmres", None):
+            self.L.dfb_gmres_destroy(self.gmres)
+            self.gmres = None
+        if getattr(self, "plan", None):
+            self.L.dfb_plan_destroy(self.plan)
+            self.plan = None
+        if getattr(self, "comm", None):
+            self.L.dfb_comm_destroy(self.comm)
+            self.comm = None
+
+
+def weak_scaling_m(m1: int, world: int) -> int:
+    """cells per direction so that the element count per GPU stays that of an m1^3 box"""
+    return int(round(m1 * world ** (1.0 / 3.0)))
+
+
+def bench_main(args, rank, world, local_rank):
+    """bench.py --gpus N (N > 1): weak scaling, ~the configs[1] element count per GPU."""
+    import torch
+    import torch.distributed as dist
+    from . import boxmesh, lib as dlib
+    import bench as B
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    m = args.m if args.fixed_m else weak_scaling_m(args.m, world)
+    t0 = time.time()
+    mesh = boxmesh.make_box(m)
+    npart = slab_owner(mesh, world)
+    lm = partition(mesh, npart, rank, world)
+    Ng, Eg = mesh.num_node, mesh.num_tet
+    wg_g, dwg_g = boxmesh.state_random(Ng)
+    wg, dwg = lm.localize(wg_g), lm.localize(dwg_g)
+    del mesh, wg_g, dwg_g
+    fs = DistFlowSystem(lm, f"cuda:{local_rank}")
+    torch.cuda.synchronize()
+    setup_s = time.time() - t0
+    N = fs.N
+    h_wg, h_dwg = torch.from_numpy(wg).pin_memory(), torch.from_numpy(dwg).pin_memory()
+    h_dx = torch.zeros(6 * N, dtype=torch.float64).pin_memory()
+    d_wg, d_dwg = h_wg.cuda(), h_dwg.cuda()
+    F = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    dx = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    state = {}
+
+    def step():
+        fs.assemble_system(d_wg, d_dwg, F=F)
+        fs.assemble_system(d_wg, d_dwg, J=True)
+        dx.zero_()
+        state["iters"], state["hist"] = fs.krylov_solve(dx, F)
+
+    def step_e2e():
+        d_wg.copy_(h_wg, non_blocking=True)
+        d_dwg.copy_(h_dwg, non_blocking=True)
+        step()
+        h_dx.copy_(dx, non_blocking=True)
+        torch.cuda.synchronize()
+
+    sampler = B.ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    nw = 0
+    t_w = time.time()
+    while nw < max(args.warmup, 3) or (nw < 50 and time.time() - t_w < 1.0):
+        step()
+        nw += 1
+    # the warm-up count must agree on all ranks
+    nwt = torch.tensor([nw], device="cuda")
+    dist.all_reduce(nwt, op=dist.ReduceOp.MAX)
+    for _ in range(int(nwt.item()) - nw):
+        step()
+    nw = int(nwt.item())
+
+    def timed(fn, k):
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)          # max over ranks
+        return t.item() / k
+
+    l0 = dlib.launch_count()
+    ms = timed(step, args.steps)
+    launches = dlib.launch_count() - l0
+    ms_e2e = timed(step_e2e, args.steps)
+    tF = timed(lambda: fs.assemble_system(d_wg, d_dwg, F=F), 5)
+    tJ = timed(lambda: fs.assemble_system(d_wg, d_dwg, J=True), 5)
+
+    def solve():
+        dx.zero_()
+        state["iters"], state["hist"] = fs.krylov_solve(dx, F)
+    t_solve = timed(solve, 3)
+    xs = torch.randn(6 * N, dtype=torch.float64, device="cuda")
+    ys = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    t_spmv = timed(lambda: fs.matvec_owned(xs, ys), 20)
+    clocks = sampler.stop() if rank == 0 else None
+    Zt = torch.tensor([float(fs.row_ptr[fs.n_own].item())], device="cuda", dtype=torch.float64)   # owned nonzeros
+    dist.all_reduce(Zt)
+    if rank == 0:
+        hbm, hbm_src = B.measured_hbm_peak()
+        Zg = int(Zt.item())
+        ab = B.algorithmic_bytes(Ng, Eg, Zg)
+        spmv_gbs = ab["spmv"] / (t_spmv * 1e-3) / 1e9
+        its = state["iters"]
+        line = {
+            "metric": B.METRIC, "value": Eg / (ms * 1e-3), "unit": B.UNIT, "n_gpus": world, "steps": args.steps, "warmup": nw,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.fixed_m else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"Kuhn box m={m}: {Eg} tets, {Ng} nodes over {world} GPUs (z-slab node ownership, ghost elements "
+                                   f"recomputed, NCCL halo + allreduce); step = AssembleSystem(F)+AssembleSystem(J)+KrylovSolve "
+                                   f"({its} GMRES iterations), state B", "elements_per_gpu": Eg / world,
+                       "l2": "per-GPU working set exceeds the 126 MB L2; no explicit flush"},
+            "clocks": clocks,
+            "e2e": {"value": Eg / (ms_e2e * 1e-3), "unit": B.UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 2 * 6 * N * 8 * world,
+                    "d2h_bytes_per_step": 6 * N * 8 * world},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "k_spmv_fs (+halo)", "bound": "hbm", "achieved": spmv_gbs, "peak": hbm * world, "unit": "GB/s",
+                         "frac": spmv_gbs / (hbm * world), "traffic": None, "peak_source": hbm_src + f" x {world} GPUs",
+                         "bytes_per_launch": ab["spmv"], "ms_per_launch": t_spmv},
+            "breakdown": {"assemble_F_ms": tF, "assemble_J_ms": tJ, "assemble_elems_per_s": Eg / ((tF + tJ) * 1e-3), "spmv_ms": t_spmv,
+                          "spmv_gbs": spmv_gbs, "spmv_pct_hbm": 100 * spmv_gbs / (hbm * world), "solve_s_per_step": t_solve * 1e-3,
+                          "gmres_iters": its, "setup_s": setup_s, "final_residual": float(state["hist"][-1]),
+                          "initial_residual": float(state["hist"][0])},
+        }
+        print(json.dumps(line), flush=True)
+    fs.close()
+    dist.destroy_process_group()

@@ -43,7 +43,16 @@ _SIGS = {
     "dfb_gmres_create": (ci, [C.POINTER(vp), ci, ci]),
     "dfb_gmres_destroy": (None, [vp]),
     "dfb_gmres_bytes": (C.c_size_t, [vp]),
-    "dfb_gmres_set_parallel": (ci, [vp, ci, vp, vp, vp]),
+    "dfb_gmres_set_parallel": (ci, [vp, vp]),
+    "dfb_plan_set_rows": (ci, [vp, ci]),
+    "dfb_comm_unique_id": (ci, [vp]),
+    "dfb_comm_create": (ci, [C.POINTER(vp), ci, ci, vp]),
+    "dfb_comm_destroy": (None, [vp]),
+    "dfb_comm_set_halo": (ci, [vp, ci, ci, vp, vp, vp, vp, vp]),
+    "dfb_comm_allreduce": (ci, [vp, ci, vp, vp]),
+    "dfb_comm_halo_begin": (ci, [vp, vp, vp]),
+    "dfb_comm_halo_end": (ci, [vp, vp, vp]),
+    "dfb_comm_halo": (ci, [vp, vp, vp]),
     "dfb_gmres_solve": (ci, [vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.POINTER(ci), vp, vp]),
 }
 

@@ -97,6 +97,8 @@ int dfb_plan_create(dfb_plan** plan, int num_node, int num_tet, const int* d_ien
                     const int* d_col_ind, int num_batch, const int* h_batch_offset, const int* d_batch_ind,
                     void* stream);
 void dfb_plan_destroy(dfb_plan* plan);
+/* Data-parallel assembly: only rows / F entries of the first n_rows (owned) nodes are produced by DFB_MODE_GATHER. */
+int dfb_plan_set_rows(dfb_plan* plan, int n_rows);
 /* bytes of device memory held by the plan */
 size_t dfb_plan_bytes(const dfb_plan* plan);
 
@@ -137,18 +139,49 @@ typedef struct dfb_gmres dfb_gmres;
 int dfb_gmres_create(dfb_gmres** ws, int num_node, int max_iter);
 void dfb_gmres_destroy(dfb_gmres* ws);
 size_t dfb_gmres_bytes(const dfb_gmres* ws);
-/* Optional data-parallel hooks (multi-GPU): owned rows [0,num_owned) of each section are reduced over ranks
- * with `allreduce(buf, count, user)` (device buffer of doubles, summed in place, enqueued on `stream`) and ghost
- * entries of the SpMV input are refreshed with `halo(d_x, user)` before every mat-vec.  NULL = single GPU. */
-typedef int (*dfb_allreduce_fn)(double* d_buf, int count, void* stream, void* user);
-typedef int (*dfb_halo_fn)(double* d_x, void* stream, void* user);
-int dfb_gmres_set_parallel(dfb_gmres* ws, int num_owned, dfb_allreduce_fn allreduce, dfb_halo_fn halo, void* user);
+/* Optional data-parallel hooks (multi-GPU, one process per GPU).  Local node numbering of a rank is
+ * [interior-owned | boundary-owned | ghost]: rows [0,n_own) are owned and assembled completely on this rank, rows
+ * [0,n_interior) reference no ghost column.  Inner products run over the owned rows and are summed over ranks with
+ * `allreduce` (device buffer of doubles, in place, enqueued on `stream`); before every mat-vec the ghost entries of the
+ * input vector are refreshed: halo_begin() starts the exchange (it may run concurrently on another stream), the
+ * interior rows are multiplied meanwhile, halo_end() makes `stream` wait for the ghosts, then the boundary rows follow. */
+typedef struct dfb_parallel_ops {
+  int n_own;
+  int n_interior;
+  int (*allreduce)(double* d_buf, int count, void* stream, void* user);
+  int (*halo_begin)(double* d_x, void* stream, void* user);
+  int (*halo_end)(double* d_x, void* stream, void* user);
+  void* user;
+} dfb_parallel_ops;
+int dfb_gmres_set_parallel(dfb_gmres* ws, const dfb_parallel_ops* ops);
 /* Solve A x = b (x in/out, b in; both 6N device vectors).  Convergence is tested only when (iter+1)%20==0 against
  * |r| < atol || |r| < (|r0| + 1e-16)*rtol (src/krylov.c:281-290, defect D10).  res_hist (HOST, may be NULL) receives
  * max_iter+1 entries: |beta[k]| for k = 0..iters.  *iters (host, out). */
 int dfb_gmres_solve(dfb_gmres* ws, int num_node, const int* d_row_ptr, const int* d_col_ind, const double* d_A00,
                     const double* d_A01, const double* d_A10, const double* d_A11, double* d_x, const double* d_b,
                     double atol, double rtol, int* iters, double* res_hist, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel communicator (NCCL over NVLink 5 / NVSwitch, resolved with dlopen at run time so that the
+ * single-GPU library has no NCCL dependency).  One process per GPU; the 128-byte unique id is created on rank 0
+ * and distributed by the host (torch.distributed in the bench).  New work: the reference is single-GPU
+ * (SURVEY.md §0, §8e).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dfb_comm dfb_comm;
+int dfb_comm_unique_id(void* id128);
+int dfb_comm_create(dfb_comm** comm, int rank, int nranks, const void* id128);
+void dfb_comm_destroy(dfb_comm* comm);
+/* Halo plan in local node ids: for neighbour q, send the (u,p) of owned nodes send_nodes[send_offset[q]..) and
+ * receive into ghost nodes recv_nodes[recv_offset[q]..).  Both sides list the nodes in ascending GLOBAL id. */
+int dfb_comm_set_halo(dfb_comm* comm, int num_local_nodes, int n_neighbors, const int* h_neighbor_rank,
+                      const int* h_send_offset, const int* h_send_nodes, const int* h_recv_offset,
+                      const int* h_recv_nodes);
+/* the three dfb_parallel_ops callbacks; `user` is the dfb_comm* */
+int dfb_comm_allreduce(double* d_buf, int count, void* stream, void* user);
+int dfb_comm_halo_begin(double* d_x, void* stream, void* user);
+int dfb_comm_halo_end(double* d_x, void* stream, void* user);
+/* blocking convenience: refresh the ghosts of a 6N-layout vector */
+int dfb_comm_halo(dfb_comm* comm, double* d_x, void* stream);
 
 #pragma GCC visibility pop
 #ifdef __cplusplus
