@@ -22,6 +22,9 @@ struct dfb_plan {
   // lazily allocated element-residual scratch for the deterministic F gather (24 doubles per element)
   mutable f64* elemF = nullptr;
   mutable size_t elemF_bytes = 0;
+  // lazily allocated per-element Jacobian records of the two-phase J gather (44 doubles per element)
+  mutable f64* jrec = nullptr;
+  mutable size_t jrec_bytes = 0;
 };
 
 namespace dfb {

@@ -33,28 +33,52 @@ constexpr unsigned FULLM = 0xffffffffu;
 // ------------------------------------------------------------------------------------------------------------
 // SpMV.  Row i of the output: u -> y[3*i + ii], p -> y[y_poff + i]; input x: u -> x[3*c + l], p -> x[x_poff + c].
 // ------------------------------------------------------------------------------------------------------------
+// G lanes cooperate on one nodal row (32/G rows per warp in flight).  The row's value streams are contiguous, so a
+// group reads G consecutive doubles per load; U iterations are issued back to back before the first FMA so that every
+// lane keeps 4*U independent 8-byte loads (plus the column/x gathers) in flight.
+template <int G>
 __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
                                                  const f64* __restrict__ A00, const f64* __restrict__ A01,
                                                  const f64* __restrict__ A10, const f64* __restrict__ A11, f64 alpha,
                                                  const f64* __restrict__ x, size_t x_poff, f64 beta, f64* __restrict__ y,
                                                  size_t y_poff) {
-  const int row = row0 + (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= n_rows) return;
-  const int start = __ldg(row_ptr + row), len = __ldg(row_ptr + row + 1) - start;
+  constexpr int U = 3;
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = row0 + (int)(gt / G);
+  const int lane = (int)(threadIdx.x & (G - 1));
+  const bool live = row < n_rows;
+  int start = 0, len = 0;
+  if (live) {
+    start = __ldg(row_ptr + row);
+    len = __ldg(row_ptr + row + 1) - start;
+  }
   const size_t s9 = (size_t)start * 9, s3 = (size_t)start * 3;
   const int len3 = 3 * len;
   f64 y0 = 0.0, y1 = 0.0, y2 = 0.0, yp = 0.0;
-  for (int t = lane; t < len3; t += 32) {
-    const int k = t / 3, l = t - 3 * k;
-    const int c = __ldg(col_ind + start + k);
-    const f64 xv = __ldg(x + (size_t)c * 3 + l);
-    y0 = fma(__ldcs(A00 + s9 + t), xv, y0);
-    y1 = fma(__ldcs(A00 + s9 + len3 + t), xv, y1);
-    y2 = fma(__ldcs(A00 + s9 + 2 * len3 + t), xv, y2);
-    yp = fma(__ldcs(A10 + s3 + t), xv, yp);
+  for (int t0 = 0; t0 < len3; t0 += U * G) {
+    f64 a0[U], a1[U], a2[U], ap[U], xv[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int t = t0 + u * G + lane;
+      const bool ok = t < len3;
+      const int tt = ok ? t : 0;
+      const int k = tt / 3, l = tt - 3 * k;
+      const int c = __ldg(col_ind + start + k);
+      xv[u] = ok ? __ldg(x + (size_t)c * 3 + l) : 0.0;
+      a0[u] = ok ? __ldcs(A00 + s9 + tt) : 0.0;
+      a1[u] = ok ? __ldcs(A00 + s9 + len3 + tt) : 0.0;
+      a2[u] = ok ? __ldcs(A00 + s9 + 2 * len3 + tt) : 0.0;
+      ap[u] = ok ? __ldcs(A10 + s3 + tt) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      y0 = fma(a0[u], xv[u], y0);
+      y1 = fma(a1[u], xv[u], y1);
+      y2 = fma(a2[u], xv[u], y2);
+      yp = fma(ap[u], xv[u], yp);
+    }
   }
-  for (int k = lane; k < len; k += 32) {
+  for (int k = lane; k < len; k += G) {
     const int c = __ldg(col_ind + start + k);
     const f64 xp = __ldg(x + x_poff + c);
     y0 = fma(__ldcs(A01 + s3 + k), xp, y0);
@@ -63,13 +87,13 @@ __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int
     yp = fma(__ldcs(A11 + start + k), xp, yp);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = G / 2; o > 0; o >>= 1) {
     y0 += __shfl_xor_sync(FULLM, y0, o);
     y1 += __shfl_xor_sync(FULLM, y1, o);
     y2 += __shfl_xor_sync(FULLM, y2, o);
     yp += __shfl_xor_sync(FULLM, yp, o);
   }
-  if (lane == 0) {
+  if (live && lane == 0) {
     f64* yu = y + (size_t)row * 3;
     f64* ypp = y + y_poff + row;
     if (beta == 0.0) {
@@ -81,12 +105,31 @@ __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int
   }
 }
 
+static int spmv_group() {
+  static int g = 0;
+  if (g == 0) {
+    const char* e = getenv("DFB_SPMV_G");
+    g = e ? atoi(e) : 16;
+    if (g != 4 && g != 8 && g != 16 && g != 32) g = 16;
+  }
+  return g;
+}
+
 // rows [row0, row1)
 int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, const f64* A00, const f64* A01, const f64* A10,
                 const f64* A11, f64 alpha, const f64* x, size_t x_poff, f64 beta, f64* y, size_t y_poff, cudaStream_t st) {
   if (row1 <= row0) return DFB_OK;
-  k_spmv_fs<<<ceil_div((i64)(row1 - row0) * 32, 256), 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x,
-                                                                   x_poff, beta, y, y_poff);
+  const i64 rows = row1 - row0;
+#define DFB_SPMV(G)                                                                                                          \
+  k_spmv_fs<G><<<ceil_div(rows * G, 256), 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x, x_poff, \
+                                                       beta, y, y_poff)
+  switch (spmv_group()) {
+    case 4: DFB_SPMV(4); break;
+    case 8: DFB_SPMV(8); break;
+    case 32: DFB_SPMV(32); break;
+    default: DFB_SPMV(16); break;
+  }
+#undef DFB_SPMV
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
@@ -153,6 +196,25 @@ __global__ void k_pc_apply(int n, const f64* __restrict__ dinv00, const f64* __r
   for (size_t t = i; t < tail_n; t += n) y[y_toff + t] = x[x_toff + t];
 }
 
+// Fused normalisation + preconditioner (one pass instead of k_scale + k_pc_apply): q = w * (*scale) is written back over
+// w (compact layout) and z = P^-1 q is written in the local layout.
+__global__ void k_scale_pc_apply(int n, const f64* __restrict__ scale, const f64* __restrict__ dinv00,
+                                 const f64* __restrict__ dinv11, f64* __restrict__ w, size_t w_poff, f64* __restrict__ z,
+                                 size_t z_poff) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const f64 s = *scale;
+  const f64* D = dinv00 + (size_t)i * 9;
+  f64* wu = w + (size_t)i * 3;
+  const f64 x0 = wu[0] * s, x1 = wu[1] * s, x2 = wu[2] * s, xp = w[w_poff + i] * s;
+  wu[0] = x0; wu[1] = x1; wu[2] = x2; w[w_poff + i] = xp;
+  f64* zu = z + (size_t)i * 3;
+  zu[0] = D[0] * x0 + D[3] * x1 + D[6] * x2;
+  zu[1] = D[1] * x0 + D[4] * x1 + D[7] * x2;
+  zu[2] = D[2] * x0 + D[5] * x1 + D[8] * x2;
+  z[z_poff + i] = xp * dinv11[i];
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Krylov vector kernels.  A "live" vector has nl = 4*n_own entries stored compactly: u of the owned nodes
 // [0, 3 n_own) followed by p [3 n_own, 4 n_own).
@@ -176,9 +238,26 @@ __device__ __forceinline__ f64 block_sum_256(f64 v, f64* sm) {
   return r;  // valid in warp 0
 }
 
-// part[j*NCHUNK + chunk] = sum over the chunk's rows of Q[i, j] * w[i],  j in [0, ncol)
+// "last block done" election: every block publishes its partial sums, fences, and bumps a counter; the block that sees
+// the final count performs the second reduction stage in a FIXED order (results are run-to-run deterministic no matter
+// which block is last) and re-arms the counter.
+__device__ __forceinline__ bool last_block(unsigned* ctr, unsigned total) {
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = atomicAdd(ctr, 1u) == total - 1;
+  }
+  __syncthreads();
+  return is_last;
+}
+
+struct GmresScalars;
+__device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist);
+
+// h[j] = sum_i Q[i, j] * w[i],  j in [0, ncol): stage 1 = per-(chunk, column) partials, stage 2 by the last block
 __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restrict__ Q, size_t ldq, int ncol,
-                                                  const f64* __restrict__ w, f64* __restrict__ part) {
+                                                  const f64* __restrict__ w, f64* part, f64* __restrict__ h,
+                                                  unsigned* ctr) {
   __shared__ f64 sm[8];
   const int j0 = blockIdx.y * JT;
   const int nj = min(JT, ncol - j0);
@@ -197,22 +276,23 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
     f64 r = block_sum_256(acc[j], sm);
     if (threadIdx.x == 0 && j < nj) part[(size_t)(j0 + j) * NCHUNK + blockIdx.x] = r;
   }
-}
-
-// out[j] = sum_chunk part[j*NCHUNK + chunk]  (fixed order); one block of 32*8 threads handles 8 columns
-__global__ void k_reduce_parts(int ncol, const f64* __restrict__ part, f64* __restrict__ out) {
-  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (j >= ncol) return;
-  f64 s = 0.0;
-  for (int c = lane; c < NCHUNK; c += 32) s += part[(size_t)j * NCHUNK + c];
+  if (!last_block(ctr, gridDim.x * gridDim.y)) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < ncol; j += 8) {
+    f64 s = 0.0;
+    for (int c = lane; c < NCHUNK; c += 32) s += __ldcg(part + (size_t)j * NCHUNK + c);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULLM, s, o);
-  if (lane == 0) out[j] = s;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULLM, s, o);
+    if (lane == 0) h[j] = s;
+  }
+  if (threadIdx.x == 0) *ctr = 0u;
 }
 
-// w[i] -= sum_j Q[i,j] h[j];  part[chunk] = sum of squares of the new w over the chunk
-__global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict__ Q, size_t ldq, int ncol,
-                                                const f64* __restrict__ h, f64* __restrict__ w, f64* __restrict__ part) {
+// w[i] -= sum_j Q[i,j] h[j], fused with the sum of squares of the new w (stage 2 by the last block -> *nrm2).
+// With do_step the last block also runs the scalar Arnoldi/Givens step (single GPU: no cross-rank sum needed).
+__global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict__ Q, size_t ldq, int ncol, f64* h,
+                                                f64* __restrict__ w, f64* part, f64* nrm2, unsigned* ctr, int do_step,
+                                                GmresScalars* S, f64* gv, f64* beta, f64* tailc, f64* res_hist) {
   __shared__ f64 sh[128];
   __shared__ f64 sm[8];
   for (int j = threadIdx.x; j < ncol; j += 256) sh[j] = h[j];
@@ -234,6 +314,18 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
   }
   f64 r = block_sum_256(ss, sm);
   if (threadIdx.x == 0) part[blockIdx.x] = r;
+  if (!last_block(ctr, gridDim.x)) return;
+  if (threadIdx.x < 32) {
+    f64 s = 0.0;
+    for (int c = threadIdx.x; c < NCHUNK; c += 32) s += __ldcg(part + c);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULLM, s, o);
+    if (threadIdx.x == 0) {
+      *nrm2 = s;
+      *ctr = 0u;
+      if (do_step) gmres_step_dev(ncol - 1, S, h, gv, beta, tailc, res_hist);
+    }
+  }
 }
 
 // out[i] = sum_j Q[i,j] y[j]   (solution combination, krylov.c:303-311)
@@ -336,7 +428,7 @@ __global__ void k_gmres_begin(GmresScalars* S, f64* beta, f64* tailc, f64* res_h
 
 // one Arnoldi step's scalar work (krylov.c:229-277 + krylov_util.cu:5-19) for column `it`:
 //   hcol[0..it] holds h = Q^T w (already reduced), S->nrm2_live the sum of squares of the updated live w.
-__global__ void k_gmres_step(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist) {
+__device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist) {
   // dead tail: every basis vector's rows [4N,6N) equal tailc[j] * b_tail (D4): w_tail = -sum_j h_j tailc[j] b_tail
   f64 cw = 0.0;
   for (int j = 0; j <= it; j++) cw -= hcol[j] * tailc[j];
@@ -362,6 +454,10 @@ __global__ void k_gmres_step(int it, GmresScalars* S, f64* hcol, f64* gv, f64* b
   res_hist[it + 1] = fabs(beta[it + 1]);
 }
 
+__global__ void k_gmres_step(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist) {
+  gmres_step_dev(it, S, hcol, gv, beta, tailc, res_hist);
+}
+
 // back substitution H[0:m,0:m] y = beta (krylov.c:297-301), then tail coefficient sum_j tailc[j] y[j]
 __global__ void k_gmres_trsv(int m, const f64* __restrict__ H, int ldh, f64* beta, const f64* tailc, f64* tail_coef) {
   for (int i = m - 1; i >= 0; i--) {
@@ -384,6 +480,7 @@ struct dfb_gmres {
   f64 *Q = nullptr, *H = nullptr, *gv = nullptr, *beta = nullptr, *tailc = nullptr, *res_hist = nullptr;
   f64 *z = nullptr, *t = nullptr, *part = nullptr, *dinv00 = nullptr, *dinv11 = nullptr, *tail_coef = nullptr;
   GmresScalars* S = nullptr;
+  unsigned* ctr = nullptr;  // [2] last-block election counters (multi-dot, update)
   size_t bytes = 0;
   int n_interior = 0;
   dfb_parallel_ops par = {0, 0, nullptr, nullptr, nullptr, nullptr};
@@ -435,6 +532,8 @@ int dfb_gmres_create(dfb_gmres** out, int N, int maxit) {
     w->bytes += a.n * sizeof(f64);
   }
   DFB_CUDA(cudaMalloc(&w->S, sizeof(GmresScalars)));
+  DFB_CUDA(cudaMalloc(&w->ctr, 2 * sizeof(unsigned)));
+  DFB_CUDA(cudaMemset(w->ctr, 0, 2 * sizeof(unsigned)));
   DFB_CUDA(cudaMemset(w->z, 0, sizeof(f64) * 6 * (size_t)N));
   DFB_CUDA(cudaMemset(w->t, 0, sizeof(f64) * 6 * (size_t)N));
   *out = w;
@@ -445,7 +544,7 @@ void dfb_gmres_destroy(dfb_gmres* w) {
   if (!w) return;
   cudaFree(w->Q); cudaFree(w->H); cudaFree(w->gv); cudaFree(w->beta); cudaFree(w->tailc); cudaFree(w->res_hist);
   cudaFree(w->z); cudaFree(w->t); cudaFree(w->part); cudaFree(w->dinv00); cudaFree(w->dinv11); cudaFree(w->tail_coef);
-  cudaFree(w->S);
+  cudaFree(w->S); cudaFree(w->ctr);
   delete w;
 }
 
@@ -509,36 +608,33 @@ int dfb_gmres_solve(dfb_gmres* W, int N, const int* rp, const int* ci, const dou
   if (W->parallel) DFB_CHECK(W->par.allreduce(&W->S->nrm2_live, 2, st, W->par.user));
   k_gmres_begin<<<1, 1, 0, st>>>(W->S, W->beta, W->tailc, W->res_hist);
   DFB_LAUNCH_CHECK();
-  k_scale<<<vgrid, 256, 0, st>>>(nl, QCOL(0), &W->S->inv_norm);
-  DFB_LAUNCH_CHECK();
+  DFB_CUDA(cudaMemsetAsync(W->ctr, 0, 2 * sizeof(unsigned), st));
 
   int iter = 0;
   bool converged = false;
   f64 rnrm_init = 0.0;
   std::vector<f64> hist((size_t)maxit + 1, 0.0);
   while (!converged && iter < maxit) {
-    // z = P^-1 q_iter (local layout), w = A z
-    k_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, W->dinv00, W->dinv11, QCOL(iter), poffC, W->z, poffN, 0, 0, 0);
+    // q_iter = w / ||w|| written back in place, z = P^-1 q_iter (local layout); then w = A z
+    k_scale_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, &W->S->inv_norm, W->dinv00, W->dinv11, QCOL(iter), poffC,
+                                                          W->z, poffN);
     DFB_LAUNCH_CHECK();
     f64* w = QCOL(iter + 1);
     DFB_CHECK(matvec(1.0, W->z, 0.0, w));
     // h = Q^T w  (krylov.c:166-174)
     const int ncol = iter + 1;
-    k_multidot<<<dim3(NCHUNK, ceil_div(ncol, JT)), 256, 0, st>>>(nl, Q, ldq, ncol, w, W->part);
-    DFB_LAUNCH_CHECK();
-    k_reduce_parts<<<ceil_div(ncol, 8), 256, 0, st>>>(ncol, W->part, HCOL(iter));
+    k_multidot<<<dim3(NCHUNK, ceil_div(ncol, JT)), 256, 0, st>>>(nl, Q, ldq, ncol, w, W->part, HCOL(iter), W->ctr);
     DFB_LAUNCH_CHECK();
     if (W->parallel) DFB_CHECK(W->par.allreduce(HCOL(iter), ncol, st, W->par.user));
-    // w -= Q h, fused with ||w||^2  (krylov.c:176-183, 229-231)
-    k_update<<<NCHUNK, 256, 0, st>>>(nl, Q, ldq, ncol, HCOL(iter), w, W->part);
+    // w -= Q h, fused with ||w||^2 and (single GPU) the scalar Givens step  (krylov.c:176-183, 229-277)
+    k_update<<<NCHUNK, 256, 0, st>>>(nl, Q, ldq, ncol, HCOL(iter), w, W->part, &W->S->nrm2_live, W->ctr + 1, W->parallel ? 0 : 1,
+                                    W->S, W->gv, W->beta, W->tailc, W->res_hist);
     DFB_LAUNCH_CHECK();
-    k_final_sum<<<1, 32, 0, st>>>(W->part, &W->S->nrm2_live);
-    DFB_LAUNCH_CHECK();
-    if (W->parallel) DFB_CHECK(W->par.allreduce(&W->S->nrm2_live, 1, st, W->par.user));
-    k_gmres_step<<<1, 1, 0, st>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist);
-    DFB_LAUNCH_CHECK();
-    k_scale<<<vgrid, 256, 0, st>>>(nl, w, &W->S->inv_norm);
-    DFB_LAUNCH_CHECK();
+    if (W->parallel) {
+      DFB_CHECK(W->par.allreduce(&W->S->nrm2_live, 1, st, W->par.user));
+      k_gmres_step<<<1, 1, 0, st>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist);
+      DFB_LAUNCH_CHECK();
+    }
     if ((iter + 1) % 20 == 0) {  // the reference's only convergence test (krylov.c:281-290)
       DFB_CUDA(cudaMemcpyAsync(hist.data(), W->res_hist, sizeof(f64) * ((size_t)iter + 2), cudaMemcpyDeviceToHost, st));
       DFB_CUDA(cudaStreamSynchronize(st));
