@@ -592,6 +592,7 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
   if (!P || !d_xg || !d_wg || !d_dwg) { set_error("dfb_assemble_tet: bad argument"); return DFB_ERR_ARG; }
   const bool doJ = d_A00 != nullptr;
   if (doJ && (!d_A01 || !d_A10 || !d_A11)) { set_error("dfb_assemble_tet: all four sub-block arrays are required"); return DFB_ERR_ARG; }
+  if (doJ && !P->slot) { set_error("dfb_assemble_tet: the plan was created without a sparsity pattern (residual only)"); return DFB_ERR_ARG; }
   if (mode == DFB_MODE_AUTO) mode = DFB_MODE_GATHER;
   if (mode == DFB_MODE_COLORED && (P->num_batch <= 0 || !P->batch_ind)) { set_error("dfb_assemble_tet: plan has no color batches"); return DFB_ERR_ARG; }
   if (overwrite && mode != DFB_MODE_GATHER) { set_error("dfb_assemble_tet: overwrite needs DFB_MODE_GATHER"); return DFB_ERR_ARG; }
@@ -676,6 +677,7 @@ int dfb_assemble_face(const dfb_plan* P, int nf, const int* d_f2e, const int* d_
   if (!P || nf < 0 || !d_xg || !d_wg || !d_dwg) { set_error("dfb_assemble_face: bad argument"); return DFB_ERR_ARG; }
   if (nf == 0 || (!d_F && !d_A00)) return DFB_OK;
   if (d_A00 && (!d_A01 || !d_A10 || !d_A11)) { set_error("dfb_assemble_face: all four sub-block arrays are required"); return DFB_ERR_ARG; }
+  if (d_A00 && !P->slot) { set_error("dfb_assemble_face: the plan was created without a sparsity pattern (residual only)"); return DFB_ERR_ARG; }
   k_face<<<ceil_div(nf, 128), 128, 0, st>>>(nf, d_f2e, d_forn, P->N, P->ien, d_xg, d_wg, d_dwg, P->row_ptr,
                                           reinterpret_cast<const u32*>(P->slot), d_F, d_A00, d_A01, d_A10, d_A11);
   DFB_LAUNCH_CHECK();

@@ -256,21 +256,25 @@ int dfb_pattern_expand(int N, const int* d_row_ptr, const int* d_col_ind, int br
 int dfb_plan_create(dfb_plan** out, int N, int E, const int* d_ien, const int* d_row_ptr, const int* d_col_ind,
                     int num_batch, const int* h_batch_offset, const int* d_batch_ind, void* stream) {
   cudaStream_t st = as_stream(stream);
-  if (!out || N <= 0 || E <= 0 || !d_ien || !d_row_ptr || !d_col_ind) { set_error("dfb_plan_create: bad argument"); return DFB_ERR_ARG; }
+  if (!out || N <= 0 || E <= 0 || !d_ien || (!d_row_ptr) != (!d_col_ind)) { set_error("dfb_plan_create: bad argument"); return DFB_ERR_ARG; }
   dfb_plan* p = new dfb_plan();
   p->N = N; p->E = E; p->n_rows = N; p->ien = d_ien; p->row_ptr = d_row_ptr; p->col_ind = d_col_ind;
   int s = build_v2c(N, E, d_ien, &p->v2c_ptr, &p->v2c, st);
   if (s != DFB_OK) { delete p; return s; }
-  DFB_CUDA(cudaMalloc(&p->slot, (size_t)E * 16));
-  k_slot_map<<<ceil_div(4 * (i64)E, 256), 256, 0, st>>>(E, d_ien, d_row_ptr, d_col_ind, p->slot);
-  DFB_LAUNCH_CHECK();
+  if (d_row_ptr) {  // without a pattern the plan serves residual (F) assembly only
+    DFB_CUDA(cudaMalloc(&p->slot, (size_t)E * 16));
+    k_slot_map<<<ceil_div(4 * (i64)E, 256), 256, 0, st>>>(E, d_ien, d_row_ptr, d_col_ind, p->slot);
+    DFB_LAUNCH_CHECK();
+  }
   int* d_max = nullptr;
   DFB_CUDA(cudaMalloc(&d_max, 2 * sizeof(int)));
   DFB_CUDA(cudaMemsetAsync(d_max, 0, 2 * sizeof(int), st));
   k_max_reduce<<<ceil_div(N, 256), 256, 0, st>>>(N, p->v2c_ptr, d_max);
   DFB_LAUNCH_CHECK();
-  k_max_reduce<<<ceil_div(N, 256), 256, 0, st>>>(N, d_row_ptr, d_max + 1);
-  DFB_LAUNCH_CHECK();
+  if (d_row_ptr) {
+    k_max_reduce<<<ceil_div(N, 256), 256, 0, st>>>(N, d_row_ptr, d_max + 1);
+    DFB_LAUNCH_CHECK();
+  }
   int h_max[2] = {0, 0};
   DFB_CUDA(cudaMemcpyAsync(h_max, d_max, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   DFB_CUDA(cudaStreamSynchronize(st));

@@ -562,6 +562,13 @@ int dfb_gmres_set_parallel(dfb_gmres* w, const dfb_parallel_ops* ops) {
 int dfb_gmres_solve(dfb_gmres* W, int N, const int* rp, const int* ci, const double* A00, const double* A01,
                     const double* A10, const double* A11, double* d_x, const double* d_b, double atol, double rtol,
                     int* iters, double* res_hist, void* stream) {
+  return dfb_gmres_solve_pc(W, N, rp, ci, A00, A01, A10, A11, nullptr, nullptr, d_x, d_b, atol, rtol, iters, res_hist, stream);
+}
+
+int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const double* A00, const double* A01,
+                       const double* A10, const double* A11, const double* ext_dinv00, const double* ext_dinv11,
+                       double* d_x, const double* d_b, double atol, double rtol, int* iters, double* res_hist,
+                       void* stream) {
   cudaStream_t st = as_stream(stream);
   if (!W || N != W->N || !rp || !ci || !A00 || !A01 || !A10 || !A11 || !d_x || !d_b || !iters) { set_error("dfb_gmres_solve: bad argument"); return DFB_ERR_ARG; }
   const int n_own = W->n_own, maxit = W->maxit, ldh = W->ldh;
@@ -586,9 +593,14 @@ int dfb_gmres_solve(dfb_gmres* W, int N, const int* rp, const int* ci, const dou
     }
     return DFB_OK;
   };
-  // preconditioner setup on every solve, like KrylovSolve -> PCSetup (krylov.c:453)
-  k_pc_setup<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, rp, ci, A00, A11, W->dinv00, W->dinv11);
-  DFB_LAUNCH_CHECK();
+  if ((!ext_dinv00) != (!ext_dinv11)) { set_error("dfb_gmres_solve_pc: pass both preconditioner arrays or neither"); return DFB_ERR_ARG; }
+  const f64 *dinv00 = W->dinv00, *dinv11 = W->dinv11;
+  if (ext_dinv00) {  // the caller has run PCSetup already (drop-in layer: the PC tree owns the arrays)
+    dinv00 = ext_dinv00; dinv11 = ext_dinv11;
+  } else {           // preconditioner setup on every solve, like KrylovSolve -> PCSetup (krylov.c:453)
+    k_pc_setup<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, rp, ci, A00, A11, W->dinv00, W->dinv11);
+    DFB_LAUNCH_CHECK();
+  }
   DFB_CUDA(cudaMemsetAsync(W->H, 0, sizeof(f64) * (size_t)ldh * maxit, st));
   // r0 = b - A x  (krylov.c:114-118)
   k_pack_live<<<vgrid, 256, 0, st>>>(n_own, d_b, poffN, QCOL(0));
@@ -616,7 +628,7 @@ int dfb_gmres_solve(dfb_gmres* W, int N, const int* rp, const int* ci, const dou
   std::vector<f64> hist((size_t)maxit + 1, 0.0);
   while (!converged && iter < maxit) {
     // q_iter = w / ||w|| written back in place, z = P^-1 q_iter (local layout); then w = A z
-    k_scale_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, &W->S->inv_norm, W->dinv00, W->dinv11, QCOL(iter), poffC,
+    k_scale_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, &W->S->inv_norm, dinv00, dinv11, QCOL(iter), poffC,
                                                           W->z, poffN);
     DFB_LAUNCH_CHECK();
     f64* w = QCOL(iter + 1);
@@ -650,7 +662,7 @@ int dfb_gmres_solve(dfb_gmres* W, int N, const int* rp, const int* ci, const dou
     k_combine<<<NCHUNK, 256, 0, st>>>(nl, Q, ldq, iter, W->beta, W->t);
     DFB_LAUNCH_CHECK();
     // P^-1 on the combination, written compactly into z, then x += z (krylov.c:313-319)
-    k_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, W->dinv00, W->dinv11, W->t, poffC, W->z, poffC, 0, 0, 0);
+    k_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, dinv00, dinv11, W->t, poffC, W->z, poffC, 0, 0, 0);
     DFB_LAUNCH_CHECK();
     k_add_live<<<vgrid, 256, 0, st>>>(n_own, W->z, d_x, poffN);
     DFB_LAUNCH_CHECK();

@@ -92,7 +92,8 @@ typedef enum dfb_assemble_mode {
 
 /* Integer plan of one mesh: vertex->corner lists, corner->CSR-slot map, (optional) color batches.
  * d_ien, d_row_ptr, d_col_ind are borrowed and must outlive the plan.  h_batch_offset/d_batch_ind may be NULL
- * (then DFB_MODE_COLORED is unavailable). */
+ * (then DFB_MODE_COLORED is unavailable).  d_row_ptr and d_col_ind may both be NULL: the plan then serves residual
+ * (F) assembly only. */
 int dfb_plan_create(dfb_plan** plan, int num_node, int num_tet, const int* d_ien, const int* d_row_ptr,
                     const int* d_col_ind, int num_batch, const int* h_batch_offset, const int* d_batch_ind,
                     void* stream);
@@ -160,6 +161,13 @@ int dfb_gmres_set_parallel(dfb_gmres* ws, const dfb_parallel_ops* ops);
 int dfb_gmres_solve(dfb_gmres* ws, int num_node, const int* d_row_ptr, const int* d_col_ind, const double* d_A00,
                     const double* d_A01, const double* d_A10, const double* d_A11, double* d_x, const double* d_b,
                     double atol, double rtol, int* iters, double* res_hist, void* stream);
+
+/* Same solve with the preconditioner arrays supplied by the caller (layouts of dfb_pc_setup); both NULL = set up
+ * internally, which is what dfb_gmres_solve does. */
+int dfb_gmres_solve_pc(dfb_gmres* ws, int num_node, const int* d_row_ptr, const int* d_col_ind, const double* d_A00,
+                       const double* d_A01, const double* d_A10, const double* d_A11, const double* d_dinv00,
+                       const double* d_dinv11, double* d_x, const double* d_b, double atol, double rtol, int* iters,
+                       double* res_hist, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Data-parallel communicator (NCCL over NVLink 5 / NVSwitch, resolved with dlopen at run time so that the

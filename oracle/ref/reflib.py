@@ -21,6 +21,9 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 REF_SO = HERE.parent / "_ref" / "libdedflow_ref.so"
+# the reference's remaining host code (Mesh.c MeshData.c common.c alloc.c) linked against the PRODUCT library:
+# the same driver below then exercises dedflow_b200's drop-in entry points (include/dedflow_compat.h)
+HYBRID_SO = HERE.parent / "_ref" / "libdedflow_hybrid.so"
 
 i32p = C.POINTER(C.c_int32)
 f64p = C.POINTER(C.c_double)
@@ -74,6 +77,10 @@ def available() -> bool:
     return REF_SO.exists()
 
 
+def hybrid_available() -> bool:
+    return HYBRID_SO.exists()
+
+
 class CaptureStdout:
     """Capture what C code printf()s to fd 1 (the reference reports its GMRES residuals only there)."""
 
@@ -102,11 +109,11 @@ class CaptureStdout:
 class RefProblem:
     """One mesh set up exactly as reference main.c does, driven through the reference's own entry points."""
 
-    def __init__(self, mesh, patch_d1: bool = True, quiet: bool = True):
+    def __init__(self, mesh, patch_d1: bool = True, quiet: bool = True, so_path=None):
         import torch
         self.torch = torch
         self.quiet = quiet
-        L = C.CDLL(str(REF_SO), mode=C.RTLD_LOCAL)
+        L = C.CDLL(str(so_path or REF_SO), mode=C.RTLD_LOCAL)
         self.L = L
         self.mesh_np = mesh
         N, E = mesh.num_node, mesh.num_tet

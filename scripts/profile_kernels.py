@@ -12,7 +12,8 @@ m = int(sys.argv[1]) if len(sys.argv) > 1 else 55
 mode = sys.argv[2] if len(sys.argv) > 2 else "gather"
 mesh = boxmesh.make_box(m)
 N = mesh.num_node
-fs = api.FlowSystem(mesh, max_iter=20, atol=0.0, rtol=0.0)
+maxit = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+fs = api.FlowSystem(mesh, max_iter=maxit, atol=0.0, rtol=0.0)
 wg, dwg = boxmesh.state_random(N)
 d_wg, d_dwg = torch.from_numpy(wg).cuda(), torch.from_numpy(dwg).cuda()
 F = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
