@@ -21,7 +21,10 @@
 //     inside an iteration; the host reads the residual only at the reference's every-20th-iteration test.
 //   * Workspace is persistent (dfb_gmres), nothing is allocated or memset per solve.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -29,6 +32,42 @@
 namespace dfb {
 
 constexpr unsigned FULLM = 0xffffffffu;
+
+// DFB_PROFILE=1: CUDA events around every launch of a solve, aggregated per kernel and printed to stderr when the solve
+// returns (diagnostics only; the events serialise nothing but add ~2 us of host work per launch).
+struct SolveProfiler {
+  struct Rec { const char* name; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  bool on;
+  SolveProfiler() { const char* e = getenv("DFB_PROFILE"); on = e && *e && *e != '0'; }
+  void begin(const char* name, cudaStream_t st) {
+    if (!on) return;
+    Rec r; r.name = name;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    recs.push_back(r);
+  }
+  void end(cudaStream_t st) { if (on) cudaEventRecord(recs.back().b, st); }
+  void report() {
+    if (!on) return;
+    struct Agg { const char* name; int n; double ms; };
+    std::vector<Agg> agg;
+    double total = 0.0;
+    for (auto& r : recs) {
+      cudaEventSynchronize(r.b);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, r.a, r.b);
+      cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+      total += ms;
+      bool found = false;
+      for (auto& g : agg) if (!strcmp(g.name, r.name)) { g.n++; g.ms += ms; found = true; break; }
+      if (!found) agg.push_back({r.name, 1, (double)ms});
+    }
+    for (auto& g : agg) fprintf(stderr, "[dfb profile] %-18s n=%4d total=%9.3f ms avg=%8.2f us\n", g.name, g.n, g.ms, 1e3 * g.ms / g.n);
+    fprintf(stderr, "[dfb profile] sum of kernels %.3f ms\n", total);
+    recs.clear();
+  }
+};
 
 // ------------------------------------------------------------------------------------------------------------
 // SpMV.  Row i of the output: u -> y[3*i + ii], p -> y[y_poff + i]; input x: u -> x[3*c + l], p -> x[x_poff + c].
@@ -219,8 +258,9 @@ __global__ void k_scale_pc_apply(int n, const f64* __restrict__ scale, const f64
 // Krylov vector kernels.  A "live" vector has nl = 4*n_own entries stored compactly: u of the owned nodes
 // [0, 3 n_own) followed by p [3 n_own, 4 n_own).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int NCHUNK = 296;  // 2 x 148 SMs: partial-sum slots of the two-stage reductions
-constexpr int JT = 8;        // basis columns per block in the multi-dot
+constexpr int NCHUNK = 296;    // 2 x 148 SMs: row chunks (partial-sum slots) of the multi-dot and the plain reductions
+constexpr int UCHUNK = 9472;   // 64 x 148 SMs: most blocks of the update kernel (one partial sum each)
+constexpr int JT = 8;          // basis columns per block in the multi-dot
 
 __device__ __forceinline__ f64 block_sum_256(f64 v, f64* sm) {
 #pragma unroll
@@ -254,33 +294,64 @@ __device__ __forceinline__ bool last_block(unsigned* ctr, unsigned total) {
 struct GmresScalars;
 __device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist);
 
-// h[j] = sum_i Q[i, j] * w[i],  j in [0, ncol): stage 1 = per-(chunk, column) partials, stage 2 by the last block
+// h[j] = sum_i Q[i, j] * w[i],  j in [0, ncol): stage 1 = per-(chunk, column) partials, stage 2 by the last block.
+// nl is a multiple of 4 and every column starts 32-byte aligned, so a thread streams 16-byte pairs of rows: up to
+// (JT + 1) x 16 B in flight per thread.
 __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restrict__ Q, size_t ldq, int ncol,
                                                   const f64* __restrict__ w, f64* part, f64* __restrict__ h,
                                                   unsigned* ctr) {
-  __shared__ f64 sm[8];
+  __shared__ f64 smj[8][JT];
   const int j0 = blockIdx.y * JT;
   const int nj = min(JT, ncol - j0);
   f64 acc[JT];
 #pragma unroll
   for (int j = 0; j < JT; j++) acc[j] = 0.0;
-  const f64* q = Q + (size_t)j0 * ldq;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nl; i += (size_t)NCHUNK * 256) {
-    const f64 wi = w[i];
+  const double2* q2 = reinterpret_cast<const double2*>(Q + (size_t)j0 * ldq);
+  const double2* w2 = reinterpret_cast<const double2*>(w);
+  const size_t np = nl >> 1, ld2 = ldq >> 1;
+  if (nj == JT) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < np; i += (size_t)gridDim.x * 256) {
+      const double2 wi = w2[i];
+      double2 qv[JT];
 #pragma unroll
-    for (int j = 0; j < JT; j++)
-      if (j < nj) acc[j] = fma(q[(size_t)j * ldq + i], wi, acc[j]);
+      for (int j = 0; j < JT; j++) qv[j] = q2[(size_t)j * ld2 + i];
+#pragma unroll
+      for (int j = 0; j < JT; j++) acc[j] = fma(qv[j].y, wi.y, fma(qv[j].x, wi.x, acc[j]));
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < np; i += (size_t)gridDim.x * 256) {
+      const double2 wi = w2[i];
+#pragma unroll
+      for (int j = 0; j < JT; j++)
+        if (j < nj) {
+          const double2 qv = q2[(size_t)j * ld2 + i];
+          acc[j] = fma(qv.y, wi.y, fma(qv.x, wi.x, acc[j]));
+        }
+    }
   }
+  {  // block reduction of the JT accumulators with a single barrier: warp shuffles, then thread j sums the 8 warps
+    const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
 #pragma unroll
-  for (int j = 0; j < JT; j++) {
-    f64 r = block_sum_256(acc[j], sm);
-    if (threadIdx.x == 0 && j < nj) part[(size_t)(j0 + j) * NCHUNK + blockIdx.x] = r;
+    for (int j = 0; j < JT; j++) {
+      f64 v = acc[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLM, v, o);
+      if (ln == 0) smj[wid][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < nj) {
+      f64 r = 0.0;
+#pragma unroll
+      for (int wv = 0; wv < 8; wv++) r += smj[wv][threadIdx.x];
+      part[(size_t)(j0 + threadIdx.x) * NCHUNK + blockIdx.x] = r;
+    }
   }
   if (!last_block(ctr, gridDim.x * gridDim.y)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunk = gridDim.x;
   for (int j = warp; j < ncol; j += 8) {
     f64 s = 0.0;
-    for (int c = lane; c < NCHUNK; c += 32) s += __ldcg(part + (size_t)j * NCHUNK + c);
+    for (int c = lane; c < nchunk; c += 32) s += __ldcg(part + (size_t)j * NCHUNK + c);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULLM, s, o);
     if (lane == 0) h[j] = s;
@@ -290,41 +361,72 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
 
 // w[i] -= sum_j Q[i,j] h[j], fused with the sum of squares of the new w (stage 2 by the last block -> *nrm2).
 // With do_step the last block also runs the scalar Arnoldi/Givens step (single GPU: no cross-rank sum needed).
+// One resident wave of blocks (4 per SM) strides over 16-byte row pairs; a thread keeps 8 independent 16-byte loads in
+// flight.  (USPLIT > 1 splits the columns of a row pair over lane groups; measured slower, kept as a compile-time knob.)
+constexpr int USPLIT = 1;   // measured on B200 (m=55): 1 -> 27 us average per launch, 4 -> 37 us
 __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict__ Q, size_t ldq, int ncol, f64* h,
                                                 f64* __restrict__ w, f64* part, f64* nrm2, unsigned* ctr, int do_step,
                                                 GmresScalars* S, f64* gv, f64* beta, f64* tailc, f64* res_hist) {
+  constexpr int PW = 32 / USPLIT;  // row pairs per warp
   __shared__ f64 sh[128];
   __shared__ f64 sm[8];
   for (int j = threadIdx.x; j < ncol; j += 256) sh[j] = h[j];
   __syncthreads();
+  const double2* q2 = reinterpret_cast<const double2*>(Q);
+  double2* w2 = reinterpret_cast<double2*>(w);
+  const size_t np = nl >> 1, ld2 = ldq >> 1;
+  const int lane = threadIdx.x & 31, sub = lane / PW, pl = lane % PW;
+  const size_t warp0 = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5, nwarp = ((size_t)gridDim.x * 256) >> 5;
   f64 ss = 0.0;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nl; i += (size_t)NCHUNK * 256) {
-    f64 s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int j = 0;
-    for (; j + 4 <= ncol; j += 4) {
-      s0 = fma(Q[(size_t)j * ldq + i], sh[j], s0);
-      s1 = fma(Q[(size_t)(j + 1) * ldq + i], sh[j + 1], s1);
-      s2 = fma(Q[(size_t)(j + 2) * ldq + i], sh[j + 2], s2);
-      s3 = fma(Q[(size_t)(j + 3) * ldq + i], sh[j + 3], s3);
+  for (size_t base = warp0 * PW; base < np; base += nwarp * PW) {   // warp-uniform trip count
+    const size_t i = base + pl;
+    const bool ok = i < np;
+    f64 ax[2] = {0.0, 0.0}, ay[2] = {0.0, 0.0};
+    if (ok) {
+      const double2* qi = q2 + i;
+      for (int j = sub * 8; j < ncol; j += 8 * USPLIT) {
+        if (j + 8 <= ncol) {
+          double2 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) v[u] = __ldcs(qi + (size_t)(j + u) * ld2);
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            ax[u & 1] = fma(v[u].x, sh[j + u], ax[u & 1]);
+            ay[u & 1] = fma(v[u].y, sh[j + u], ay[u & 1]);
+          }
+        } else {
+          for (int jj = j; jj < ncol; jj++) {
+            const double2 v = __ldcs(qi + (size_t)jj * ld2);
+            ax[0] = fma(v.x, sh[jj], ax[0]);
+            ay[0] = fma(v.y, sh[jj], ay[0]);
+          }
+        }
+      }
     }
-    for (; j < ncol; j++) s0 = fma(Q[(size_t)j * ldq + i], sh[j], s0);
-    const f64 wn = w[i] - ((s0 + s1) + (s2 + s3));
-    w[i] = wn;
-    ss = fma(wn, wn, ss);
+    f64 sx = ax[0] + ax[1], sy = ay[0] + ay[1];
+#pragma unroll
+    for (int o = PW; o < 32; o <<= 1) {
+      sx += __shfl_xor_sync(FULLM, sx, o);
+      sy += __shfl_xor_sync(FULLM, sy, o);
+    }
+    if (ok && sub == 0) {
+      double2 wn = w2[i];
+      wn.x -= sx;
+      wn.y -= sy;
+      w2[i] = wn;
+      ss = fma(wn.y, wn.y, fma(wn.x, wn.x, ss));
+    }
   }
   f64 r = block_sum_256(ss, sm);
   if (threadIdx.x == 0) part[blockIdx.x] = r;
   if (!last_block(ctr, gridDim.x)) return;
-  if (threadIdx.x < 32) {
-    f64 s = 0.0;
-    for (int c = threadIdx.x; c < NCHUNK; c += 32) s += __ldcg(part + c);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULLM, s, o);
-    if (threadIdx.x == 0) {
-      *nrm2 = s;
-      *ctr = 0u;
-      if (do_step) gmres_step_dev(ncol - 1, S, h, gv, beta, tailc, res_hist);
-    }
+  f64 s = 0.0;
+  for (int c = threadIdx.x; c < (int)gridDim.x; c += 256) s += __ldcg(part + c);
+  s = block_sum_256(s, sm);
+  if (threadIdx.x == 0) {
+    *nrm2 = s;
+    *ctr = 0u;
+    if (do_step) gmres_step_dev(ncol - 1, S, h, gv, beta, tailc, res_hist);
   }
 }
 
@@ -334,10 +436,25 @@ __global__ void __launch_bounds__(256) k_combine(size_t nl, const f64* __restric
   __shared__ f64 sh[128];
   for (int j = threadIdx.x; j < ncol; j += 256) sh[j] = yv[j];
   __syncthreads();
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nl; i += (size_t)gridDim.x * 256) {
-    f64 s = 0.0;
-    for (int j = 0; j < ncol; j++) s = fma(Q[(size_t)j * ldq + i], sh[j], s);
-    out[i] = s;
+  const double2* q2 = reinterpret_cast<const double2*>(Q);
+  double2* o2 = reinterpret_cast<double2*>(out);
+  const size_t np = nl >> 1, ld2 = ldq >> 1;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < np; i += (size_t)gridDim.x * 256) {
+    f64 sx = 0.0, sy = 0.0;
+    const double2* qi = q2 + i;
+    int j = 0;
+    for (; j + 8 <= ncol; j += 8) {
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = __ldcs(qi + (size_t)(j + u) * ld2);
+#pragma unroll
+      for (int u = 0; u < 8; u++) { sx = fma(v[u].x, sh[j + u], sx); sy = fma(v[u].y, sh[j + u], sy); }
+    }
+    for (; j < ncol; j++) {
+      const double2 v = __ldcs(qi + (size_t)j * ld2);
+      sx = fma(v.x, sh[j], sx); sy = fma(v.y, sh[j], sy);
+    }
+    o2[i] = make_double2(sx, sy);
   }
 }
 
@@ -521,7 +638,7 @@ int dfb_gmres_create(dfb_gmres** out, int N, int maxit) {
   struct { f64** p; size_t n; } allocs[] = {
       {&w->Q, nl * ((size_t)maxit + 1)}, {&w->H, (size_t)w->ldh * maxit}, {&w->gv, (size_t)2 * maxit},
       {&w->beta, (size_t)maxit + 1},    {&w->tailc, (size_t)maxit + 1},  {&w->res_hist, (size_t)maxit + 1},
-      {&w->z, (size_t)6 * N},           {&w->t, (size_t)6 * N},          {&w->part, (size_t)NCHUNK * (maxit + 2)},
+      {&w->z, (size_t)6 * N},           {&w->t, (size_t)6 * N},          {&w->part, (size_t)NCHUNK * (maxit + 2) + UCHUNK},
       {&w->dinv00, (size_t)9 * N},      {&w->dinv11, (size_t)N},         {&w->tail_coef, 8}};
   for (auto& a : allocs) {
     if (cudaMalloc(a.p, a.n * sizeof(f64)) != cudaSuccess) {
@@ -581,6 +698,10 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
 #define QCOL(c) (Q + (size_t)(c)*ldq)
 #define HCOL(c) (W->H + (size_t)(c)*ldh)
   const int vgrid = ceil_div((i64)nl, 256);
+  const int mgrid = std::min(NCHUNK, ceil_div((i64)(nl / 2), 256));   // row chunks of the multi-dot
+  // update kernel: one resident wave (4 blocks per SM; measured 27.4 us vs 30.4 us for one row pair per thread)
+  const int ugrid = std::min(std::min(UCHUNK, 4 * num_sms()), ceil_div((i64)(nl / 2) * USPLIT, 256));
+  const int cgrid = std::min(1184, ceil_div((i64)(nl / 2), 256));              // blocks of the combine kernel
   // y(compact) = beta*y + alpha * A x(local layout): interior rows overlap the ghost exchange of x
   auto matvec = [&](f64 alpha, f64* x, f64 beta, f64* y) -> int {
     if (W->parallel) {
@@ -626,22 +747,33 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   bool converged = false;
   f64 rnrm_init = 0.0;
   std::vector<f64> hist((size_t)maxit + 1, 0.0);
+  SolveProfiler prof;
   while (!converged && iter < maxit) {
     // q_iter = w / ||w|| written back in place, z = P^-1 q_iter (local layout); then w = A z
+    prof.begin("scale_pc_apply", st);
     k_scale_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, &W->S->inv_norm, dinv00, dinv11, QCOL(iter), poffC,
                                                           W->z, poffN);
     DFB_LAUNCH_CHECK();
+    prof.end(st);
     f64* w = QCOL(iter + 1);
+    prof.begin("spmv", st);
     DFB_CHECK(matvec(1.0, W->z, 0.0, w));
+    prof.end(st);
     // h = Q^T w  (krylov.c:166-174)
     const int ncol = iter + 1;
-    k_multidot<<<dim3(NCHUNK, ceil_div(ncol, JT)), 256, 0, st>>>(nl, Q, ldq, ncol, w, W->part, HCOL(iter), W->ctr);
+    prof.begin("multidot", st);
+    const int ny = ceil_div(ncol, JT);
+    const int mg = std::max(1, std::min(mgrid, (4 * num_sms()) / ny));   // one resident wave of (row chunk, column group) blocks
+    k_multidot<<<dim3(mg, ny), 256, 0, st>>>(nl, Q, ldq, ncol, w, W->part, HCOL(iter), W->ctr);
     DFB_LAUNCH_CHECK();
+    prof.end(st);
     if (W->parallel) DFB_CHECK(W->par.allreduce(HCOL(iter), ncol, st, W->par.user));
     // w -= Q h, fused with ||w||^2 and (single GPU) the scalar Givens step  (krylov.c:176-183, 229-277)
-    k_update<<<NCHUNK, 256, 0, st>>>(nl, Q, ldq, ncol, HCOL(iter), w, W->part, &W->S->nrm2_live, W->ctr + 1, W->parallel ? 0 : 1,
+    prof.begin("update", st);
+    k_update<<<ugrid, 256, 0, st>>>(nl, Q, ldq, ncol, HCOL(iter), w, W->part, &W->S->nrm2_live, W->ctr + 1, W->parallel ? 0 : 1,
                                     W->S, W->gv, W->beta, W->tailc, W->res_hist);
     DFB_LAUNCH_CHECK();
+    prof.end(st);
     if (W->parallel) {
       DFB_CHECK(W->par.allreduce(&W->S->nrm2_live, 1, st, W->par.user));
       k_gmres_step<<<1, 1, 0, st>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist);
@@ -657,9 +789,10 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     iter++;
   }
   if (iter) {
+    prof.begin("trsv..axpy", st);
     k_gmres_trsv<<<1, 1, 0, st>>>(iter, W->H, ldh, W->beta, W->tailc, W->tail_coef);
     DFB_LAUNCH_CHECK();
-    k_combine<<<NCHUNK, 256, 0, st>>>(nl, Q, ldq, iter, W->beta, W->t);
+    k_combine<<<cgrid, 256, 0, st>>>(nl, Q, ldq, iter, W->beta, W->t);
     DFB_LAUNCH_CHECK();
     // P^-1 on the combination, written compactly into z, then x += z (krylov.c:313-319)
     k_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, dinv00, dinv11, W->t, poffC, W->z, poffC, 0, 0, 0);
@@ -668,6 +801,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     DFB_LAUNCH_CHECK();
     k_axpy_dev<<<ceil_div((i64)tail_n, 256), 256, 0, st>>>(tail_n, W->tail_coef, d_b + (size_t)4 * N, d_x + (size_t)4 * N);
     DFB_LAUNCH_CHECK();
+    prof.end(st);
     if (W->parallel) {  // leave the ghosts of the solution consistent
       DFB_CHECK(W->par.halo_begin(d_x, st, W->par.user));
       DFB_CHECK(W->par.halo_end(d_x, st, W->par.user));
@@ -678,6 +812,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   if (res_hist)
     for (int k = 0; k <= iter; k++) res_hist[k] = hist[k];
   *iters = iter;
+  prof.report();
 #undef QCOL
 #undef HCOL
   return DFB_OK;
