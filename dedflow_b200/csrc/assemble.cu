@@ -18,6 +18,9 @@
 //   * J, COLORED: same kernel without atomics, one launch per color batch (the reference's structure).
 //   * F: one thread per element evaluates the residual once; GATHER writes the 24 values to an L2-friendly
 //     scratch and a node-gather kernel sums them in fixed order; ATOMIC / COLORED scatter directly.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "elem_math.cuh"
 #include "plan.cuh"
@@ -494,6 +497,161 @@ __global__ void __launch_bounds__(128) k_rowJ2(int N, const f64* __restrict__ re
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// J, PULL (default).  Phase 1 (k_jprep2) evaluates the per-element part of the hoisted Jacobian once per element and
+// parks it in a 384-byte record (three 128-byte lines).  Phase 2 (k_pullJ) runs one thread per WORK ITEM of the plan
+// (plan.cuh): an off-diagonal nodal nonzero, or one of the four virtual items of a diagonal entry.  The thread walks the
+// (element, a, b) contributions of its item in fixed order, forms each 4x4 block from the two corner sub-records and the
+// element tail (13 16-byte loads, ~75 fp64 instructions) and accumulates the 16 values in registers; the four diagonal
+// items of a row then fold their partial sums with a two-step butterfly inside their lane quad.  Every CSR value is
+// written exactly once: no atomics, no colors, no memset, no shared-memory staging, deterministic.
+// Record (doubles): corner x at [10x, 10x+10): g0 g1 | g2 P | c0 c1 | c2 c3 | R pad   (c_q = u(q).grad N_x)
+//                   tail at [40,48): w sTM | sTC pad | tM0 tM1 | tM2 tM3
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PREC = 48;
+
+// The 32 records of a warp are contiguous in global memory (32 x 384 B): each lane parks its record in shared memory
+// (stride 49 doubles: conflict-free), then the warp streams the 12 KB out with fully coalesced 8-byte stores.
+constexpr int PREC_S = 49;
+__global__ void __launch_bounds__(128) k_jprep2(int E, const int* __restrict__ ien, const f64* __restrict__ xg,
+                                                const f64* __restrict__ wg, f64* __restrict__ rec) {
+  extern __shared__ f64 stage_rec[];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  f64* mine = stage_rec + (size_t)(warp * 32 + lane) * PREC_S;
+  if (e < E) {
+    int nodes[4];
+    load_nodes(ien, e, nodes);
+    f64 x[4][3], u[4][3];
+    load_xyz(xg, nodes, x);
+    load_xyz(wg, nodes, u);
+    Geom g;
+    geometry(x, g);
+    JPrep p;
+    jac_prep(g, u, p);
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      mine[a * 10 + 0] = g.sh[a][0]; mine[a * 10 + 1] = g.sh[a][1]; mine[a * 10 + 2] = g.sh[a][2]; mine[a * 10 + 3] = p.P[a];
+      mine[a * 10 + 4] = p.c[0][a]; mine[a * 10 + 5] = p.c[1][a]; mine[a * 10 + 6] = p.c[2][a]; mine[a * 10 + 7] = p.c[3][a];
+      mine[a * 10 + 8] = p.R[a]; mine[a * 10 + 9] = 0.0;
+    }
+    mine[40] = p.w; mine[41] = p.sTM; mine[42] = p.sTC; mine[43] = 0.0;
+    mine[44] = p.tM[0]; mine[45] = p.tM[1]; mine[46] = p.tM[2]; mine[47] = p.tM[3];
+  }
+  __syncwarp();
+  const int e0 = (blockIdx.x * blockDim.x) + warp * 32;           // first element of this warp
+  const int nrec = min(32, E - e0);
+  if (nrec <= 0) return;
+  f64* dst = rec + (size_t)e0 * PREC;
+  const f64* src = stage_rec + (size_t)warp * 32 * PREC_S;
+  const int total = nrec * PREC;
+  for (int t = lane; t < total; t += 32) {
+    const int r = t / PREC, o = t - r * PREC;
+    dst[t] = src[r * PREC_S + o];
+  }
+}
+
+template <int OVERWRITE>
+__global__ void __launch_bounds__(128) k_pullJ(int n_items, const uint2* __restrict__ item_meta, const int* __restrict__ item_ptr,
+                                               const u32* __restrict__ contrib, const f64* __restrict__ rec,
+                                               const int* __restrict__ row_ptr, f64* __restrict__ A00, f64* __restrict__ A01,
+                                               f64* __restrict__ A10, f64* __restrict__ A11) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = item < n_items;
+  uint2 meta = make_uint2(0xffffffffu, 0u);
+  int cs = 0, ce = 0;
+  if (valid) {
+    meta = item_meta[item];
+    cs = __ldg(item_ptr + item);
+    ce = __ldg(item_ptr + item + 1);
+  }
+  f64 acc[16];
+#pragma unroll
+  for (int v = 0; v < 16; v++) acc[v] = 0.0;
+  for (int idx = cs; idx < ce; idx++) {
+    const u32 cid = __ldg(contrib + idx);
+    const int a = (int)((cid >> 2) & 3u), b = (int)(cid & 3u);
+    const double2* R = reinterpret_cast<const double2*>(rec + (size_t)(cid >> 4) * PREC);
+    const double2 a0 = R[a * 5], a1 = R[a * 5 + 1], a2 = R[a * 5 + 2], a3 = R[a * 5 + 3];
+    const double2 b0 = R[b * 5], b1 = R[b * 5 + 1], b2 = R[b * 5 + 2], b3 = R[b * 5 + 3], b4 = R[b * 5 + 4];
+    const double2 t0 = R[20], t1 = R[21], t2 = R[22], t3 = R[23];
+    const f64 ga[3] = {a0.x, a0.y, a1.x}, gb[3] = {b0.x, b0.y, b1.x};
+    const f64 Pa = a1.y, Pb = b1.y, Rb = b4.x;
+    const f64 w = t0.x, sTM = t0.y, sTC = t1.x;
+    const f64 tMb = sel4(b, t2.x, t2.y, t3.x, t3.y);
+    const f64 cab = sel4(a, b2.x, b2.y, b3.x, b3.y);          // c[q=a][b]
+    const f64 cba = sel4(b, a2.x, a2.y, a3.x, a3.y);          // c[q=b][a]
+    const f64 stc = (t2.x * a2.x) * b2.x + (t2.y * a2.y) * b2.y + (t3.x * a3.x) * b3.x + (t3.y * a3.y) * b3.y;
+    const f64 eK = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
+    const f64 mab = (a == b) ? (SA * SA + 3.0 * SB * SB) : (2.0 * SA * SB + 2.0 * SB * SB);
+    const f64 T = w * (FACT1 * RHO * mab + FACT1 * RHO * RHO * (SB * Pa + SD * (tMb * cba)) + FACT2 * RHO * (SB * Rb + SD * cab) +
+                       FACT2 * RHO * RHO * stc + 4.0 * FACT2 * MU * eK);
+    const f64 k1 = 4.0 * w * FACT2 * MU, k2 = w * FACT2 * RHO * sTC;
+#pragma unroll
+    for (int ii = 0; ii < 3; ii++)
+#pragma unroll
+      for (int jj = 0; jj < 3; jj++) acc[ii * 4 + jj] += k1 * ga[jj] * gb[ii] + k2 * ga[ii] * gb[jj] + (ii == jj ? T : 0.0);
+    const f64 k3 = w * SN, k4 = RHO * w * Pa;
+    const f64 k5 = w * RHO * (FACT1 * (SB * sTM + SD * tMb) + FACT2 * Pb);
+    const f64 k6 = FACT2 * w * SN;
+#pragma unroll
+    for (int ii = 0; ii < 3; ii++) {
+      acc[ii * 4 + 3] += -k3 * ga[ii] + k4 * gb[ii];
+      acc[12 + ii] += k5 * ga[ii] + k6 * gb[ii];
+    }
+    acc[15] += w * sTM * eK;
+  }
+  // fold the four diagonal items of a row (an aligned lane quad): after two exchange steps lane q of the quad holds
+  // block row q.  Executed by every lane (no divergence); only diagonal items use the result.
+  const int lane = threadIdx.x & 31;
+  const bool hi = lane & 2, odd = lane & 1;
+  f64 t[2][4], u[4];
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const f64 send = hi ? acc[r * 4 + j] : acc[(r + 2) * 4 + j];
+      const f64 keep = hi ? acc[(r + 2) * 4 + j] : acc[r * 4 + j];
+      t[r][j] = keep + __shfl_xor_sync(FULL, send, 2);
+    }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const f64 send = odd ? t[0][j] : t[1][j];
+    const f64 keep = odd ? t[1][j] : t[0][j];
+    u[j] = keep + __shfl_xor_sync(FULL, send, 1);
+  }
+  if (!valid || meta.x == 0xffffffffu) return;
+  const int row = (int)meta.x, k = (int)(meta.y & 0xffu);
+  const int start = __ldg(row_ptr + row), len = __ldg(row_ptr + row + 1) - start;
+  const size_t st = (size_t)start;
+  f64* p00 = A00 + st * 9 + (size_t)k * 3;
+  f64* p01 = A01 + st * 3 + k;
+  f64* p10 = A10 + st * 3 + (size_t)k * 3;
+  f64* p11 = A11 + st + k;
+  if (meta.y & 0x100u) {
+    const int q = lane & 3;
+    if (q < 3) {
+      f64* d = p00 + (size_t)q * len * 3;
+      f64* d1 = p01 + (size_t)q * len;
+      if (OVERWRITE) { d[0] = u[0]; d[1] = u[1]; d[2] = u[2]; *d1 = u[3]; }
+      else { d[0] += u[0]; d[1] += u[1]; d[2] += u[2]; *d1 += u[3]; }
+    } else {
+      if (OVERWRITE) { p10[0] = u[0]; p10[1] = u[1]; p10[2] = u[2]; *p11 = u[3]; }
+      else { p10[0] += u[0]; p10[1] += u[1]; p10[2] += u[2]; *p11 += u[3]; }
+    }
+  } else {
+#pragma unroll
+    for (int ii = 0; ii < 3; ii++) {
+      f64* d = p00 + (size_t)ii * len * 3;
+      f64* d1 = p01 + (size_t)ii * len;
+      if (OVERWRITE) { d[0] = acc[ii * 4]; d[1] = acc[ii * 4 + 1]; d[2] = acc[ii * 4 + 2]; *d1 = acc[ii * 4 + 3]; }
+      else { d[0] += acc[ii * 4]; d[1] += acc[ii * 4 + 1]; d[2] += acc[ii * 4 + 2]; *d1 += acc[ii * 4 + 3]; }
+    }
+    if (OVERWRITE) { p10[0] = acc[12]; p10[1] = acc[13]; p10[2] = acc[14]; *p11 = acc[15]; }
+    else { p10[0] += acc[12]; p10[1] += acc[13]; p10[2] += acc[14]; *p11 += acc[15]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // boundary faces (tiny: O(N^(2/3)) faces): one thread per face, atomic scatter
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_face(int nf, const int* __restrict__ f2e, const int* __restrict__ forn, int N,
@@ -623,9 +781,39 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
   if (doJ) {
     if (mode == DFB_MODE_GATHER) {
       const int grid = ceil_div(P->n_rows, 4);
-      // measured on B200 (m=55): fused single kernel 1.07 ms, two-phase (k_jprep + k_rowJ2) 1.21 ms -> fused is the default
-      static const bool twophase = getenv("DFB_J_TWOPHASE") != nullptr;
-      if (!twophase) {
+      // variants of the atomic-free assembly: pull (default), fused row gather (DFB_J_VARIANT=fused), two-phase row
+      // gather (DFB_J_VARIANT=twophase); measured on B200 at 1M tets: see DESIGN.md section 3
+      static const int variant = [] {
+        const char* e = getenv("DFB_J_VARIANT");
+        if (e && !strcmp(e, "fused")) return 1;
+        if (e && !strcmp(e, "twophase")) return 2;
+        return 0;
+      }();
+      if (variant == 0) {
+        DFB_CHECK(build_pull(P, st));
+        if (P->items_rows != P->n_rows) {
+          if (P->n_rows == P->N) {
+            P->items_active = P->n_items;
+          } else {
+            DFB_CUDA(cudaMemcpyAsync(&P->items_active, P->row_item + P->n_rows, sizeof(int), cudaMemcpyDeviceToHost, st));
+            DFB_CUDA(cudaStreamSynchronize(st));
+          }
+          P->items_rows = P->n_rows;
+        }
+        static bool jprep2_attr = false;
+        if (!jprep2_attr) {
+          DFB_CUDA(cudaFuncSetAttribute(k_jprep2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(f64) * 128 * PREC_S)));
+          jprep2_attr = true;
+        }
+        k_jprep2<<<ceil_div(E, 128), 128, sizeof(f64) * 128 * PREC_S, st>>>(E, P->ien, d_xg, d_wg, P->prec);
+        DFB_LAUNCH_CHECK();
+        const int ni = P->items_active;
+        if (overwrite)
+          k_pullJ<1><<<ceil_div(ni, 128), 128, 0, st>>>(ni, P->item_meta, P->item_ptr, P->contrib, P->prec, P->row_ptr, d_A00, d_A01, d_A10, d_A11);
+        else
+          k_pullJ<0><<<ceil_div(ni, 128), 128, 0, st>>>(ni, P->item_meta, P->item_ptr, P->contrib, P->prec, P->row_ptr, d_A00, d_A01, d_A10, d_A11);
+        DFB_LAUNCH_CHECK();
+      } else if (variant == 1) {
         if (P->max_row_len <= 16)
           k_rowJ<1><<<grid, 128, 0, st>>>(P->n_rows, P->ien, d_xg, d_wg, P->row_ptr, P->v2c_ptr, P->v2c, slot32, d_A00, d_A01, d_A10, d_A11, overwrite);
         else if (P->max_row_len <= 32)

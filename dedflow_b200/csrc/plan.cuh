@@ -25,8 +25,20 @@ struct dfb_plan {
   // lazily allocated per-element Jacobian records of the two-phase J gather (44 doubles per element)
   mutable f64* jrec = nullptr;
   mutable size_t jrec_bytes = 0;
+  // lazily built work lists of the PULL Jacobian assembly (setup.cu build_pull): one work item per off-diagonal nodal
+  // nonzero plus four "virtual" items per diagonal entry (its contributions dealt round-robin), rows padded to multiples
+  // of four items so that the four diagonal items of a row sit in one aligned lane quad.
+  mutable int n_items = 0;            // total work items (multiple of 4)
+  mutable int* row_item = nullptr;    // [N+1] first item of every row
+  mutable uint2* item_meta = nullptr; // [n_items] {row (0xffffffff: padding), k | 0x100 for a diagonal item}
+  mutable int* item_ptr = nullptr;    // [n_items+1] offsets into contrib
+  mutable u32* contrib = nullptr;     // [16E] corner*4 + b, ascending inside an item
+  mutable f64* prec = nullptr;        // [48E] element records of the pull assembly (assemble.cu k_jprep2)
+  mutable size_t pull_bytes = 0;
+  mutable int items_rows = -1, items_active = 0;  // cache: items of the first n_rows rows
 };
 
 namespace dfb {
 int build_v2c(int N, int E, const int* d_ien, int** d_ptr_out, int** d_v2c_out, cudaStream_t st);
+int build_pull(const dfb_plan* plan, cudaStream_t st);
 }

@@ -185,6 +185,137 @@ __global__ void k_slot_map(int E, const int* __restrict__ ien, const int* __rest
   reinterpret_cast<u32*>(slot)[c] = packed;
 }
 
+// ------------------------------------------------------------------------------------------
+// work lists of the pull Jacobian assembly (plan.cuh)
+// ------------------------------------------------------------------------------------------
+__global__ void k_row_item_count(int N, const int* __restrict__ row_ptr, int* __restrict__ cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > N) return;
+  if (i == N) { cnt[i] = 0; return; }
+  const int len = row_ptr[i + 1] - row_ptr[i];
+  cnt[i] = 4 + ((len - 1 + 3) & ~3);   // 4 diagonal items + the off-diagonal entries, padded to a multiple of 4
+}
+
+__device__ __forceinline__ int lower_bound_dev(const int* __restrict__ a, int n, int v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void k_item_meta(int N, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
+                            const int* __restrict__ row_item, uint2* __restrict__ meta) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int s = row_ptr[i], len = row_ptr[i + 1] - s;
+  const int kd = lower_bound_dev(col_ind + s, len, i);
+  const int base = row_item[i], n = row_item[i + 1] - base;
+  for (int t = 0; t < n; t++) {
+    uint2 m;
+    if (t < 4) { m.x = (u32)i; m.y = (u32)kd | 0x100u; }
+    else if (t - 4 < len - 1) { const int o = t - 4; m.x = (u32)i; m.y = (u32)(o < kd ? o : o + 1); }
+    else { m.x = 0xffffffffu; m.y = 0u; }
+    meta[base + t] = m;
+  }
+}
+
+// item of contribution (corner c = e*4+a, b): diagonal contributions of a row are dealt round-robin (by the rank of the
+// corner in the row's sorted corner list) to the four diagonal items
+__device__ __forceinline__ int item_of(int c, int b, const int* __restrict__ ien, const int* __restrict__ row_ptr,
+                                       const int* __restrict__ col_ind, const int* __restrict__ v2c_ptr,
+                                       const int* __restrict__ v2c, const u32* __restrict__ slot32,
+                                       const int* __restrict__ row_item) {
+  const int row = ien[c];
+  const int k = (int)((slot32[c] >> (8 * b)) & 0xffu);
+  const int s = row_ptr[row], len = row_ptr[row + 1] - s;
+  const int kd = lower_bound_dev(col_ind + s, len, row);
+  const int base = row_item[row];
+  if (k == kd) {
+    const int vs = v2c_ptr[row];
+    const int r = lower_bound_dev(v2c + vs, v2c_ptr[row + 1] - vs, c);
+    return base + (r & 3);
+  }
+  return base + 4 + (k < kd ? k : k - 1);
+}
+
+template <bool FILL>
+__global__ void k_contrib(int E, const int* __restrict__ ien, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
+                          const int* __restrict__ v2c_ptr, const int* __restrict__ v2c, const u32* __restrict__ slot32,
+                          const int* __restrict__ row_item, int* __restrict__ cnt, const int* __restrict__ item_ptr,
+                          u32* __restrict__ contrib) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)16 * E) return;
+  const int c = (int)(t >> 2), b = (int)(t & 3);
+  const int it = item_of(c, b, ien, row_ptr, col_ind, v2c_ptr, v2c, slot32, row_item);
+  const int pos = atomicAdd(cnt + it, 1);
+  if (FILL) contrib[item_ptr[it] + pos] = (u32)t;
+}
+
+__global__ void k_sort_contrib(int n_items, const int* __restrict__ item_ptr, u32* __restrict__ contrib) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  const int s = item_ptr[i], e = item_ptr[i + 1];
+  for (int j = s + 1; j < e; j++) {
+    u32 key = contrib[j];
+    int k = j - 1;
+    while (k >= s && contrib[k] > key) { contrib[k + 1] = contrib[k]; k--; }
+    contrib[k + 1] = key;
+  }
+}
+
+int build_pull(const dfb_plan* p, cudaStream_t st) {
+  if (p->item_meta) return DFB_OK;
+  if (!p->slot) { set_error("pull assembly needs a plan with a sparsity pattern"); return DFB_ERR_ARG; }
+  if ((i64)p->E * 16 > 0xffffffffLL) { set_error("pull assembly: more than 2^28 elements per GPU"); return DFB_ERR_OVERFLOW; }
+  const int N = p->N, E = p->E;
+  const u32* slot32 = reinterpret_cast<const u32*>(p->slot);
+  int* cnt = nullptr;
+  DFB_CUDA(cudaMalloc(&cnt, sizeof(int) * ((size_t)N + 1)));
+  DFB_CUDA(cudaMalloc(&p->row_item, sizeof(int) * ((size_t)N + 1)));
+  k_row_item_count<<<ceil_div((i64)N + 1, 256), 256, 0, st>>>(N, p->row_ptr, cnt);
+  DFB_LAUNCH_CHECK();
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, p->row_item, N + 1, st);
+  void* tmp = nullptr;
+  DFB_CUDA(cudaMalloc(&tmp, tmp_bytes));
+  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, p->row_item, N + 1, st);
+  DFB_LAUNCH_CHECK();
+  int n_items = 0;
+  DFB_CUDA(cudaMemcpyAsync(&n_items, p->row_item + N, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DFB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(tmp); cudaFree(cnt);
+  p->n_items = n_items;
+  DFB_CUDA(cudaMalloc(&p->item_meta, sizeof(uint2) * (size_t)n_items));
+  DFB_CUDA(cudaMalloc(&p->item_ptr, sizeof(int) * ((size_t)n_items + 1)));
+  DFB_CUDA(cudaMalloc(&p->contrib, sizeof(u32) * (size_t)E * 16));
+  int* icnt = nullptr;
+  DFB_CUDA(cudaMalloc(&icnt, sizeof(int) * ((size_t)n_items + 1)));
+  DFB_CUDA(cudaMemsetAsync(icnt, 0, sizeof(int) * ((size_t)n_items + 1), st));
+  k_item_meta<<<ceil_div(N, 128), 128, 0, st>>>(N, p->row_ptr, p->col_ind, p->row_item, p->item_meta);
+  DFB_LAUNCH_CHECK();
+  const int cgrid = ceil_div((i64)E * 16, 256);
+  k_contrib<false><<<cgrid, 256, 0, st>>>(E, p->ien, p->row_ptr, p->col_ind, p->v2c_ptr, p->v2c, slot32, p->row_item, icnt, nullptr, nullptr);
+  DFB_LAUNCH_CHECK();
+  tmp_bytes = 0; tmp = nullptr;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, icnt, p->item_ptr, n_items + 1, st);
+  DFB_CUDA(cudaMalloc(&tmp, tmp_bytes));
+  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, icnt, p->item_ptr, n_items + 1, st);
+  DFB_LAUNCH_CHECK();
+  DFB_CUDA(cudaMemsetAsync(icnt, 0, sizeof(int) * ((size_t)n_items + 1), st));
+  k_contrib<true><<<cgrid, 256, 0, st>>>(E, p->ien, p->row_ptr, p->col_ind, p->v2c_ptr, p->v2c, slot32, p->row_item, icnt, p->item_ptr, p->contrib);
+  DFB_LAUNCH_CHECK();
+  k_sort_contrib<<<ceil_div(n_items, 128), 128, 0, st>>>(n_items, p->item_ptr, p->contrib);
+  DFB_LAUNCH_CHECK();
+  DFB_CUDA(cudaMalloc(&p->prec, sizeof(f64) * 48 * (size_t)E));
+  DFB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(tmp); cudaFree(icnt);
+  p->pull_bytes = sizeof(int) * ((size_t)N + 1) + sizeof(uint2) * (size_t)n_items + sizeof(int) * ((size_t)n_items + 1) +
+                  sizeof(u32) * (size_t)E * 16 + sizeof(f64) * 48 * (size_t)E;
+  return DFB_OK;
+}
+
 __global__ void k_max_reduce(int n, const int* __restrict__ ptr, int* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int v = 0;
@@ -294,18 +425,20 @@ int dfb_plan_create(dfb_plan** out, int N, int E, const int* d_ien, const int* d
 int dfb_plan_set_rows(dfb_plan* p, int n_rows) {
   if (!p || n_rows <= 0 || n_rows > p->N) { set_error("dfb_plan_set_rows: bad argument"); return DFB_ERR_ARG; }
   p->n_rows = n_rows;
+  p->items_rows = -1;
   return DFB_OK;
 }
 
 void dfb_plan_destroy(dfb_plan* p) {
   if (!p) return;
   cudaFree(p->v2c_ptr); cudaFree(p->v2c); cudaFree(p->slot); cudaFree(p->elemF); cudaFree(p->jrec);
+  cudaFree(p->row_item); cudaFree(p->item_meta); cudaFree(p->item_ptr); cudaFree(p->contrib); cudaFree(p->prec);
   delete p;
 }
 
 size_t dfb_plan_bytes(const dfb_plan* p) {
   if (!p) return 0;
-  return sizeof(int) * ((size_t)p->N + 1) + sizeof(int) * (size_t)p->E * 4 + (size_t)p->E * 16 + p->elemF_bytes + p->jrec_bytes;
+  return sizeof(int) * ((size_t)p->N + 1) + sizeof(int) * (size_t)p->E * 4 + (size_t)p->E * 16 + p->elemF_bytes + p->jrec_bytes + p->pull_bytes;
 }
 
 }  // extern "C"
