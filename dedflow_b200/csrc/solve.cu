@@ -72,20 +72,22 @@ struct SolveProfiler {
 // ------------------------------------------------------------------------------------------------------------
 // SpMV.  Row i of the output: u -> y[3*i + ii], p -> y[y_poff + i]; input x: u -> x[3*c + l], p -> x[x_poff + c].
 // ------------------------------------------------------------------------------------------------------------
-// G lanes cooperate on one nodal row (32/G rows per warp in flight).  The row's value streams are contiguous, so a
-// group reads G consecutive doubles per load; U iterations are issued back to back before the first FMA so that every
-// lane keeps 4*U independent 8-byte loads (plus the column/x gathers) in flight.
+// G lanes cooperate on one nodal row (32/G rows per warp in flight).  The row's value streams are contiguous, so a group
+// reads G consecutive doubles per load.  Per chunk of G nodal nonzeros a lane issues its 16 value loads and ONE column
+// index load back to back; the column indices are then exchanged inside the group with shuffles (no lane reads an index
+// twice, no second dependent index->x chain), so only the x gathers wait on a previous load.
 template <int G>
 __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
                                                  const f64* __restrict__ A00, const f64* __restrict__ A01,
                                                  const f64* __restrict__ A10, const f64* __restrict__ A11, f64 alpha,
                                                  const f64* __restrict__ x, size_t x_poff, f64 beta, f64* __restrict__ y,
                                                  size_t y_poff) {
-  constexpr int U = 3;
   const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int row = row0 + (int)(gt / G);
   const int lane = (int)(threadIdx.x & (G - 1));
   const bool live = row < n_rows;
+  // the lanes of THIS group (the groups of a warp may run different trip counts)
+  const unsigned gmask = G == 32 ? FULLM : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
   int start = 0, len = 0;
   if (live) {
     start = __ldg(row_ptr + row);
@@ -94,36 +96,45 @@ __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int
   const size_t s9 = (size_t)start * 9, s3 = (size_t)start * 3;
   const int len3 = 3 * len;
   f64 y0 = 0.0, y1 = 0.0, y2 = 0.0, yp = 0.0;
-  for (int t0 = 0; t0 < len3; t0 += U * G) {
-    f64 a0[U], a1[U], a2[U], ap[U], xv[U];
+  for (int c0 = 0; c0 < len; c0 += G) {   // group-uniform trip count (one trip for rows of up to G nonzeros)
+    const int k = c0 + lane;
+    const bool okk = k < len;
+    const int kk = okk ? k : 0;
+    f64 a0[3], a1[3], a2[3], ap[3];
+    bool oku[3];
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      const int t = t0 + u * G + lane;
-      const bool ok = t < len3;
-      const int tt = ok ? t : 0;
-      const int k = tt / 3, l = tt - 3 * k;
-      const int c = __ldg(col_ind + start + k);
-      xv[u] = ok ? __ldg(x + (size_t)c * 3 + l) : 0.0;
-      a0[u] = ok ? __ldcs(A00 + s9 + tt) : 0.0;
-      a1[u] = ok ? __ldcs(A00 + s9 + len3 + tt) : 0.0;
-      a2[u] = ok ? __ldcs(A00 + s9 + 2 * len3 + tt) : 0.0;
-      ap[u] = ok ? __ldcs(A10 + s3 + tt) : 0.0;
+    for (int u = 0; u < 3; u++) {
+      const int t = 3 * c0 + u * G + lane;
+      oku[u] = t < len3;
+      const int tt = oku[u] ? t : 0;
+      a0[u] = __ldcs(A00 + s9 + tt);
+      a1[u] = __ldcs(A00 + s9 + len3 + tt);
+      a2[u] = __ldcs(A00 + s9 + 2 * len3 + tt);
+      ap[u] = __ldcs(A10 + s3 + tt);
+    }
+    const f64 b0 = __ldcs(A01 + s3 + kk), b1 = __ldcs(A01 + s3 + len + kk), b2 = __ldcs(A01 + s3 + 2 * len + kk);
+    const f64 bp = __ldcs(A11 + start + kk);
+    const int col = __ldg(col_ind + start + kk);
+    const f64 xp = okk ? __ldg(x + x_poff + col) : 0.0;
+    f64 xv[3];
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+      const int q = u * G + lane;          // position inside the chunk's 3*G velocity entries
+      const int kl = q / 3, l = q - 3 * kl;
+      const int cu = __shfl_sync(gmask, col, kl, G);
+      xv[u] = oku[u] ? __ldg(x + (size_t)cu * 3 + l) : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < U; u++) {
+    for (int u = 0; u < 3; u++) {
       y0 = fma(a0[u], xv[u], y0);
       y1 = fma(a1[u], xv[u], y1);
       y2 = fma(a2[u], xv[u], y2);
       yp = fma(ap[u], xv[u], yp);
     }
-  }
-  for (int k = lane; k < len; k += G) {
-    const int c = __ldg(col_ind + start + k);
-    const f64 xp = __ldg(x + x_poff + c);
-    y0 = fma(__ldcs(A01 + s3 + k), xp, y0);
-    y1 = fma(__ldcs(A01 + s3 + len + k), xp, y1);
-    y2 = fma(__ldcs(A01 + s3 + 2 * len + k), xp, y2);
-    yp = fma(__ldcs(A11 + start + k), xp, yp);
+    y0 = fma(b0, xp, y0);
+    y1 = fma(b1, xp, y1);
+    y2 = fma(b2, xp, y2);
+    yp = fma(bp, xp, yp);
   }
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) {
@@ -148,8 +159,8 @@ static int spmv_group() {
   static int g = 0;
   if (g == 0) {
     const char* e = getenv("DFB_SPMV_G");
-    g = e ? atoi(e) : 16;
-    if (g != 4 && g != 8 && g != 16 && g != 32) g = 16;
+    g = e ? atoi(e) : 8;   // measured in-solve on B200 (1M tets): G=8 67.8 us, G=16 71.8 us, G=32 122 us per mat-vec
+    if (g != 4 && g != 8 && g != 16 && g != 32) g = 8;
   }
   return g;
 }
@@ -164,9 +175,9 @@ int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, cons
                                                        beta, y, y_poff)
   switch (spmv_group()) {
     case 4: DFB_SPMV(4); break;
-    case 8: DFB_SPMV(8); break;
     case 32: DFB_SPMV(32); break;
-    default: DFB_SPMV(16); break;
+    case 16: DFB_SPMV(16); break;
+    default: DFB_SPMV(8); break;
   }
 #undef DFB_SPMV
   DFB_LAUNCH_CHECK();
