@@ -31,6 +31,24 @@ sys.path.insert(0, str(ROOT))
 METRIC = "assembled elems/s"
 UNIT = "elems/s"
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, the reference's printf logging) write to fd 1
+# too, so everything else is routed to stderr while the benchmark runs and the line goes to the original stdout.
+_STDOUT_FD = None
+
+
+def protect_stdout():
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_STDOUT_FD if _STDOUT_FD is not None else 1, data)
+
 
 def measured_hbm_peak():
     p = ROOT / "MEASURED_PEAKS.json"
@@ -231,7 +249,7 @@ def run_reference(args, rank, world):
         ms = (time.time() - t0) / max(1, min(args.steps, 2)) * 1e3
         line.update({"value": cb["value"], "ms_per_step": ms, "cpu_baseline": cb,
                      "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -244,7 +262,7 @@ def run_ours(args, rank, world):
     torch.cuda.set_device(local_rank)
     if world > 1:
         from dedflow_b200 import dist as ddist
-        return ddist.bench_main(args, rank, world, local_rank)
+        return ddist.bench_main(args, rank, world, local_rank, sys.modules[__name__])
     from dedflow_b200 import api
     mesh = boxmesh.make_box(args.m)
     N, E = mesh.num_node, mesh.num_tet
@@ -370,7 +388,7 @@ def run_ours(args, rank, world):
     }
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(mesh, wg, dwg)
-    print(json.dumps(line), flush=True)
+    emit(line)
     fs.close()
 
 
@@ -388,6 +406,7 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -63,4 +63,52 @@ constexpr f64 kGW = 0.0416666666666667;
 constexpr f64 kSHA = 0.5854101966249685;
 constexpr f64 kSHB = 0.1381966011250105;
 
+// ------------------------------------------------------------------------------------------------------------
+// Peer-memory view of the data-parallel communicator (dist.cu builds it, the Krylov kernels in solve.cu consume it): the
+// collectives of a GMRES iteration are FUSED into the compute kernels -- partial sums and halo values are stored straight
+// into the peers' memory over NVLink (CUDA IPC mappings), flags carry monotonically increasing sequence numbers.
+// Mailbox layout in 8-byte words, R = nranks:   A: multi-dot partials [2][R][128] + flags [2][R]
+//                                               B: norm partials      [2][R]      + flags [2][R]      H: halo flags [R]
+// ------------------------------------------------------------------------------------------------------------
+constexpr int P2P_MAXR = 8;
+constexpr int P2P_ACAP = 128;
+constexpr size_t P2P_MBOX_WORDS = 4096;   // mailbox size (words); the shared z vector follows it in the same allocation
+
+struct P2PView {
+  int rank, nranks;
+  unsigned long long* mbox_local;
+  unsigned long long* mbox_peer[P2P_MAXR];
+  f64* z_local;
+  f64* z_peer[P2P_MAXR];
+  int n_nbr;
+  int nbr[P2P_MAXR];
+  int send_off[P2P_MAXR + 1];
+  unsigned long long nbr_poff[P2P_MAXR];   // 3 * N_local of the neighbour (offset of p inside its z)
+  const int* send_nodes;                   // [n_send] my local ids
+  const int* remote_nodes;                 // [n_send] the same nodes in the neighbour's local numbering (its ghosts)
+  unsigned* push_ctr;                      // last-block counter of the halo push kernel
+};
+
+struct P2PHandle { P2PView host; const P2PView* dev; };   // what dfb_comm_p2p_view() returns
+
+__host__ __device__ inline size_t p2p_a_data(int R, int par, int r, int j) { return ((size_t)par * R + r) * P2P_ACAP + j; }
+__host__ __device__ inline size_t p2p_a_flag(int R, int par, int r) { return (size_t)2 * R * P2P_ACAP + (size_t)par * R + r; }
+__host__ __device__ inline size_t p2p_b_data(int R, int par, int r) { return (size_t)2 * R * P2P_ACAP + (size_t)2 * R + (size_t)par * R + r; }
+__host__ __device__ inline size_t p2p_b_flag(int R, int par, int r) { return (size_t)2 * R * P2P_ACAP + (size_t)4 * R + (size_t)par * R + r; }
+__host__ __device__ inline size_t p2p_h_flag(int R, int r) { return (size_t)2 * R * P2P_ACAP + (size_t)6 * R + r; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void p2p_signal(unsigned long long* flag, unsigned long long seq) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+}
+__device__ __forceinline__ void p2p_wait(const unsigned long long* flag, unsigned long long seq) {
+  unsigned long long v;
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= seq) break;
+    __nanosleep(32);
+  } while (true);
+}
+#endif
+
 }  // namespace dfb

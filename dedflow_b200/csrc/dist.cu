@@ -103,6 +103,16 @@ struct dfb_comm {
   int *d_send_nodes = nullptr, *d_recv_nodes = nullptr;
   f64 *d_send_buf = nullptr, *d_recv_buf = nullptr;
   int n_send = 0, n_recv = 0;
+  // peer-memory mode
+  void* shared = nullptr;               // my region: mailbox words, then z
+  size_t shared_bytes = 0;
+  void* peer_base[P2P_MAXR] = {nullptr};
+  int* d_remote_nodes = nullptr;
+  unsigned* d_push_ctr = nullptr;
+  P2PView* d_view = nullptr;
+  P2PView h_view;
+  P2PHandle handle;
+  bool p2p_ready = false;
 };
 
 extern "C" {
@@ -133,6 +143,9 @@ int dfb_comm_create(dfb_comm** out, int rank, int nranks, const void* id128) {
 void dfb_comm_destroy(dfb_comm* c) {
   if (!c) return;
   cudaFree(c->d_send_nodes); cudaFree(c->d_recv_nodes); cudaFree(c->d_send_buf); cudaFree(c->d_recv_buf);
+  for (int r = 0; r < c->nranks && r < P2P_MAXR; r++)
+    if (c->peer_base[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_base[r]);
+  cudaFree(c->shared); cudaFree(c->d_remote_nodes); cudaFree(c->d_push_ctr); cudaFree(c->d_view);
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
   if (c->ev_done) cudaEventDestroy(c->ev_done);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
@@ -210,6 +223,73 @@ int dfb_comm_halo_end(double* d_x, void* stream, void* user) {
   if (c->nranks == 1 || c->nbr.empty()) return DFB_OK;
   DFB_CUDA(cudaStreamWaitEvent(as_stream(stream), c->ev_done, 0));
   return DFB_OK;
+}
+
+int dfb_comm_p2p_alloc(dfb_comm* c, void* handle64) {
+  if (!c || !handle64 || c->n_local <= 0) { set_error("dfb_comm_p2p_alloc: bad argument (call dfb_comm_set_halo first)"); return DFB_ERR_ARG; }
+  if (c->nranks > P2P_MAXR) { set_error("dfb_comm_p2p_alloc: at most %d ranks", P2P_MAXR); return DFB_ERR_ARG; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!c->shared) {
+    c->shared_bytes = sizeof(unsigned long long) * P2P_MBOX_WORDS + sizeof(f64) * 6 * (size_t)c->n_local;
+    DFB_CUDA(cudaMalloc(&c->shared, c->shared_bytes));
+    DFB_CUDA(cudaMemset(c->shared, 0, c->shared_bytes));
+  }
+  cudaIpcMemHandle_t h;
+  DFB_CUDA(cudaIpcGetMemHandle(&h, c->shared));
+  memcpy(handle64, &h, 64);
+  return DFB_OK;
+}
+
+int dfb_comm_p2p_connect(dfb_comm* c, const void* handles, const int* h_remote_nodes, const int* h_nbr_num_local) {
+  if (!c || !handles || !c->shared || (c->n_send && !h_remote_nodes) || (!c->nbr.empty() && !h_nbr_num_local)) { set_error("dfb_comm_p2p_connect: bad argument"); return DFB_ERR_ARG; }
+  if ((int)c->nbr.size() > P2P_MAXR) { set_error("dfb_comm_p2p_connect: too many neighbours"); return DFB_ERR_ARG; }
+  const char* hb = static_cast<const char*>(handles);
+  for (int r = 0; r < c->nranks; r++) {
+    if (r == c->rank) { c->peer_base[r] = c->shared; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hb + (size_t)64 * r, 64);
+    DFB_CUDA(cudaIpcOpenMemHandle(&c->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  P2PView& v = c->h_view;
+  memset(&v, 0, sizeof(v));
+  v.rank = c->rank; v.nranks = c->nranks;
+  for (int r = 0; r < c->nranks; r++) {
+    v.mbox_peer[r] = static_cast<unsigned long long*>(c->peer_base[r]);
+    v.z_peer[r] = reinterpret_cast<f64*>(static_cast<unsigned long long*>(c->peer_base[r]) + P2P_MBOX_WORDS);
+  }
+  v.mbox_local = v.mbox_peer[c->rank];
+  v.z_local = v.z_peer[c->rank];
+  v.n_nbr = (int)c->nbr.size();
+  for (int q = 0; q < v.n_nbr; q++) {
+    v.nbr[q] = c->nbr[q];
+    v.send_off[q] = c->send_off[q];
+    v.nbr_poff[q] = (unsigned long long)3 * (unsigned long long)h_nbr_num_local[q];
+  }
+  v.send_off[v.n_nbr] = c->n_send;
+  if (c->n_send) {
+    cudaFree(c->d_remote_nodes);
+    DFB_CUDA(cudaMalloc(&c->d_remote_nodes, sizeof(int) * (size_t)c->n_send));
+    DFB_CUDA(cudaMemcpy(c->d_remote_nodes, h_remote_nodes, sizeof(int) * (size_t)c->n_send, cudaMemcpyHostToDevice));
+  }
+  v.send_nodes = c->d_send_nodes;
+  v.remote_nodes = c->d_remote_nodes;
+  if (!c->d_push_ctr) {
+    DFB_CUDA(cudaMalloc(&c->d_push_ctr, sizeof(unsigned)));
+    DFB_CUDA(cudaMemset(c->d_push_ctr, 0, sizeof(unsigned)));
+  }
+  v.push_ctr = c->d_push_ctr;
+  if (!c->d_view) DFB_CUDA(cudaMalloc(&c->d_view, sizeof(P2PView)));
+  DFB_CUDA(cudaMemcpy(c->d_view, &v, sizeof(P2PView), cudaMemcpyHostToDevice));
+  c->p2p_ready = true;
+  return DFB_OK;
+}
+
+// host copy of the view (solve.cu reads sizes from it and passes the device copy, stored right behind it, to kernels)
+const void* dfb_comm_p2p_view(dfb_comm* c) {
+  if (!c || !c->p2p_ready) return nullptr;
+  c->handle.host = c->h_view;
+  c->handle.dev = c->d_view;
+  return &c->handle;
 }
 
 int dfb_comm_halo(dfb_comm* c, double* d_x, void* stream) {

@@ -76,12 +76,26 @@ struct SolveProfiler {
 // reads G consecutive doubles per load.  Per chunk of G nodal nonzeros a lane issues its 16 value loads and ONE column
 // index load back to back; the column indices are then exchanged inside the group with shuffles (no lane reads an index
 // twice, no second dependent index->x chain), so only the x gathers wait on a previous load.
-template <int G>
+// PEER = true (data-parallel, peer-memory mode): x is the shared z vector whose ghost entries are stored by the
+// neighbouring GPUs; a block that owns rows >= n_interior first waits for this mat-vec's halo flags, and x is read
+// through L2 (ld.cg) instead of the non-coherent path.
+template <bool PEER>
+__device__ __forceinline__ f64 ld_x(const f64* p) { return PEER ? __ldcg(p) : __ldg(p); }
+
+template <int G, bool PEER>
 __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
                                                  const f64* __restrict__ A00, const f64* __restrict__ A01,
                                                  const f64* __restrict__ A10, const f64* __restrict__ A11, f64 alpha,
                                                  const f64* __restrict__ x, size_t x_poff, f64 beta, f64* __restrict__ y,
-                                                 size_t y_poff) {
+                                                 size_t y_poff, const P2PView* __restrict__ pv, unsigned long long hseq,
+                                                 int n_interior) {
+  if (PEER) {
+    const int last_row = row0 + (int)((((size_t)blockIdx.x + 1) * blockDim.x - 1) / G);
+    if (last_row >= n_interior) {   // block-uniform
+      if ((int)threadIdx.x < pv->n_nbr) p2p_wait(pv->mbox_local + p2p_h_flag(pv->nranks, pv->nbr[threadIdx.x]), hseq);
+      __syncthreads();
+    }
+  }
   const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int row = row0 + (int)(gt / G);
   const int lane = (int)(threadIdx.x & (G - 1));
@@ -115,14 +129,14 @@ __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int
     const f64 b0 = __ldcs(A01 + s3 + kk), b1 = __ldcs(A01 + s3 + len + kk), b2 = __ldcs(A01 + s3 + 2 * len + kk);
     const f64 bp = __ldcs(A11 + start + kk);
     const int col = __ldg(col_ind + start + kk);
-    const f64 xp = okk ? __ldg(x + x_poff + col) : 0.0;
+    const f64 xp = okk ? ld_x<PEER>(x + x_poff + col) : 0.0;
     f64 xv[3];
 #pragma unroll
     for (int u = 0; u < 3; u++) {
       const int q = u * G + lane;          // position inside the chunk's 3*G velocity entries
       const int kl = q / 3, l = q - 3 * kl;
       const int cu = __shfl_sync(gmask, col, kl, G);
-      xv[u] = oku[u] ? __ldg(x + (size_t)cu * 3 + l) : 0.0;
+      xv[u] = oku[u] ? ld_x<PEER>(x + (size_t)cu * 3 + l) : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < 3; u++) {
@@ -167,12 +181,19 @@ static int spmv_group() {
 
 // rows [row0, row1)
 int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, const f64* A00, const f64* A01, const f64* A10,
-                const f64* A11, f64 alpha, const f64* x, size_t x_poff, f64 beta, f64* y, size_t y_poff, cudaStream_t st) {
+                const f64* A11, f64 alpha, const f64* x, size_t x_poff, f64 beta, f64* y, size_t y_poff, cudaStream_t st,
+                const P2PView* pv = nullptr, unsigned long long hseq = 0, int n_interior = 0) {
   if (row1 <= row0) return DFB_OK;
   const i64 rows = row1 - row0;
-#define DFB_SPMV(G)                                                                                                          \
-  k_spmv_fs<G><<<ceil_div(rows * G, 256), 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x, x_poff, \
-                                                       beta, y, y_poff)
+#define DFB_SPMV(G)                                                                                                              \
+  do {                                                                                                                           \
+    if (pv)                                                                                                                      \
+      k_spmv_fs<G, true><<<ceil_div(rows * G, 256), 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x,   \
+                                                                  x_poff, beta, y, y_poff, pv, hseq, n_interior);               \
+    else                                                                                                                         \
+      k_spmv_fs<G, false><<<ceil_div(rows * G, 256), 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x,  \
+                                                                   x_poff, beta, y, y_poff, nullptr, 0ull, 0);                  \
+  } while (0)
   switch (spmv_group()) {
     case 4: DFB_SPMV(4); break;
     case 32: DFB_SPMV(32); break;
@@ -182,6 +203,34 @@ int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, cons
 #undef DFB_SPMV
   DFB_LAUNCH_CHECK();
   return DFB_OK;
+}
+
+// halo push (peer-memory mode): the (u,p) of every boundary-owned node of z is stored into the ghost slot of the
+// neighbouring GPU's z; the last block to finish raises this mat-vec's flag on every neighbour.
+__global__ void __launch_bounds__(128) k_halo_push(const P2PView* __restrict__ pv, int n_send, size_t poff_local,
+                                                   unsigned long long hseq) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_send) {
+    int q = 0;
+    while (q + 1 < pv->n_nbr && t >= pv->send_off[q + 1]) q++;
+    const int node = pv->send_nodes[t], rid = pv->remote_nodes[t];
+    const f64* zl = pv->z_local;
+    f64* zr = pv->z_peer[pv->nbr[q]];
+    const f64 a = zl[(size_t)node * 3], b = zl[(size_t)node * 3 + 1], c = zl[(size_t)node * 3 + 2], d = zl[poff_local + node];
+    zr[(size_t)rid * 3] = a; zr[(size_t)rid * 3 + 1] = b; zr[(size_t)rid * 3 + 2] = c;
+    zr[pv->nbr_poff[q] + rid] = d;
+  }
+  __shared__ bool is_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(pv->push_ctr, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  if (threadIdx.x == 0) *pv->push_ctr = 0u;
+  if ((int)threadIdx.x < pv->n_nbr) {
+    __threadfence_system();
+    p2p_signal(pv->mbox_peer[pv->nbr[threadIdx.x]] + p2p_h_flag(pv->nranks, pv->rank), hseq);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -310,8 +359,9 @@ __device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64*
 // (JT + 1) x 16 B in flight per thread.
 __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restrict__ Q, size_t ldq, int ncol,
                                                   const f64* __restrict__ w, f64* part, f64* __restrict__ h,
-                                                  unsigned* ctr) {
+                                                  unsigned* ctr, const P2PView* __restrict__ pv, unsigned long long seq) {
   __shared__ f64 smj[8][JT];
+  __shared__ f64 hsum[P2P_ACAP];
   const int j0 = blockIdx.y * JT;
   const int nj = min(JT, ncol - j0);
   f64 acc[JT];
@@ -365,7 +415,20 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
     for (int c = lane; c < nchunk; c += 32) s += __ldcg(part + (size_t)j * NCHUNK + c);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULLM, s, o);
-    if (lane == 0) h[j] = s;
+    if (lane == 0) {
+      if (pv) hsum[j] = s; else h[j] = s;
+    }
+  }
+  if (pv) {   // publish this rank's partial to every rank (itself included); k_update sums them in rank order
+    __syncthreads();
+    const int R = pv->nranks, par = (int)(seq & 1ull);
+    for (int t = threadIdx.x; t < R * ncol; t += 256) {
+      const int r = t / ncol, j = t - r * ncol;
+      reinterpret_cast<f64*>(pv->mbox_peer[r])[p2p_a_data(R, par, pv->rank, j)] = hsum[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < pv->nranks) p2p_signal(pv->mbox_peer[threadIdx.x] + p2p_a_flag(pv->nranks, (int)(seq & 1ull), pv->rank), seq);
   }
   if (threadIdx.x == 0) *ctr = 0u;
 }
@@ -377,11 +440,25 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
 constexpr int USPLIT = 1;   // measured on B200 (m=55): 1 -> 27 us average per launch, 4 -> 37 us
 __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict__ Q, size_t ldq, int ncol, f64* h,
                                                 f64* __restrict__ w, f64* part, f64* nrm2, unsigned* ctr, int do_step,
-                                                GmresScalars* S, f64* gv, f64* beta, f64* tailc, f64* res_hist) {
+                                                GmresScalars* S, f64* gv, f64* beta, f64* tailc, f64* res_hist,
+                                                const P2PView* __restrict__ pv, unsigned long long seq) {
   constexpr int PW = 32 / USPLIT;  // row pairs per warp
   __shared__ f64 sh[128];
   __shared__ f64 sm[8];
-  for (int j = threadIdx.x; j < ncol; j += 256) sh[j] = h[j];
+  if (pv) {   // fused all-reduce of h: wait for every rank's partial (stored into OUR mailbox), sum in rank order
+    const int R = pv->nranks, par = (int)(seq & 1ull);
+    if ((int)threadIdx.x < R) p2p_wait(pv->mbox_local + p2p_a_flag(R, par, threadIdx.x), seq);
+    __syncthreads();
+    const f64* mb = reinterpret_cast<const f64*>(pv->mbox_local);
+    for (int j = threadIdx.x; j < ncol; j += 256) {
+      f64 s = 0.0;
+      for (int r = 0; r < R; r++) s += __ldcg(mb + p2p_a_data(R, par, r, j));
+      sh[j] = s;
+      if (blockIdx.x == 0) h[j] = s;
+    }
+  } else {
+    for (int j = threadIdx.x; j < ncol; j += 256) sh[j] = h[j];
+  }
   __syncthreads();
   const double2* q2 = reinterpret_cast<const double2*>(Q);
   double2* w2 = reinterpret_cast<double2*>(w);
@@ -435,9 +512,16 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
   for (int c = threadIdx.x; c < (int)gridDim.x; c += 256) s += __ldcg(part + c);
   s = block_sum_256(s, sm);
   if (threadIdx.x == 0) {
-    *nrm2 = s;
     *ctr = 0u;
-    if (do_step) gmres_step_dev(ncol - 1, S, h, gv, beta, tailc, res_hist);
+    if (pv) {   // publish the partial sum of squares; k_gmres_step_peer sums the ranks
+      const int R = pv->nranks, par = (int)(seq & 1ull);
+      for (int r = 0; r < R; r++) reinterpret_cast<f64*>(pv->mbox_peer[r])[p2p_b_data(R, par, pv->rank)] = s;
+      __threadfence_system();
+      for (int r = 0; r < R; r++) p2p_signal(pv->mbox_peer[r] + p2p_b_flag(R, par, pv->rank), seq);
+    } else {
+      *nrm2 = s;
+      if (do_step) gmres_step_dev(ncol - 1, S, h, gv, beta, tailc, res_hist);
+    }
   }
 }
 
@@ -565,12 +649,13 @@ __device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64*
   const f64 inv = 1.0 / nrm;
   S->inv_norm = inv;
   tailc[it + 1] = cw * inv;
-  for (int i = 0; i < it; i++) {  // cublasDrot, n = 1 (krylov.c:258-263)
-    const f64 c = gv[2 * i], s = gv[2 * i + 1], xx = hcol[i], yy = hcol[i + 1];
+  f64 xx = hcol[0];
+  for (int i = 0; i < it; i++) {  // cublasDrot, n = 1 (krylov.c:258-263); the running entry stays in a register so that
+    const f64 c = gv[2 * i], s = gv[2 * i + 1], yy = hcol[i + 1];   // no load waits for a previous store
     hcol[i] = c * xx + s * yy;
-    hcol[i + 1] = c * yy - s * xx;
+    xx = c * yy - s * xx;
   }
-  f64 a = hcol[it], b = hcol[it + 1], c, s;
+  f64 a = xx, b = nrm, c, s;
   drotg_dev(a, b, c, s);
   hcol[it] = a;
   hcol[it + 1] = 0.0;  // krylov.c:267
@@ -586,16 +671,49 @@ __global__ void k_gmres_step(int it, GmresScalars* S, f64* hcol, f64* gv, f64* b
   gmres_step_dev(it, S, hcol, gv, beta, tailc, res_hist);
 }
 
-// back substitution H[0:m,0:m] y = beta (krylov.c:297-301), then tail coefficient sum_j tailc[j] y[j]
-__global__ void k_gmres_trsv(int m, const f64* __restrict__ H, int ldh, f64* beta, const f64* tailc, f64* tail_coef) {
-  for (int i = m - 1; i >= 0; i--) {
-    f64 s = beta[i];
-    for (int j = i + 1; j < m; j++) s -= H[(size_t)j * ldh + i] * beta[j];
-    beta[i] = s / H[(size_t)i * ldh + i];
+// peer-memory mode: fused all-reduce of ||w||^2 (rank order) + the scalar Arnoldi/Givens step; one warp
+__global__ void k_gmres_step_peer(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist,
+                                  const P2PView* __restrict__ pv, unsigned long long seq) {
+  const int R = pv->nranks, par = (int)(seq & 1ull);
+  if ((int)threadIdx.x < R) p2p_wait(pv->mbox_local + p2p_b_flag(R, par, threadIdx.x), seq);
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    const f64* mb = reinterpret_cast<const f64*>(pv->mbox_local);
+    f64 s = 0.0;
+    for (int r = 0; r < R; r++) s += __ldcg(mb + p2p_b_data(R, par, r));
+    S->nrm2_live = s;
+    gmres_step_dev(it, S, hcol, gv, beta, tailc, res_hist);
   }
-  f64 tc = 0.0;
-  for (int j = 0; j < m; j++) tc += tailc[j] * beta[j];
-  *tail_coef = tc;
+}
+
+// back substitution H[0:m,0:m] y = beta (krylov.c:297-301), then tail coefficient sum_j tailc[j] y[j].
+// One block of 128 threads (m <= 127): H is staged in shared memory, thread i owns the right-hand side entry i, the
+// column-oriented sweep needs one broadcast + one FMA per unknown instead of a serial O(m^2) chain of dependent loads.
+__global__ void __launch_bounds__(128) k_gmres_trsv(int m, const f64* __restrict__ H, int ldh, f64* beta, const f64* tailc,
+                                                    f64* tail_coef) {
+  extern __shared__ f64 hs[];   // [m][m] column-major copy of the triangle
+  __shared__ f64 ycur;
+  __shared__ f64 red[4];
+  const int i = threadIdx.x;
+  for (int t = threadIdx.x; t < m * m; t += blockDim.x) {
+    const int c = t / m, r = t - c * m;
+    hs[t] = r <= c ? H[(size_t)c * ldh + r] : 0.0;
+  }
+  f64 b = i < m ? beta[i] : 0.0;
+  __syncthreads();
+  for (int j = m - 1; j >= 0; j--) {
+    if (i == j) { b = b / hs[j * m + j]; ycur = b; }
+    __syncthreads();
+    if (i < j) b -= hs[j * m + i] * ycur;
+    __syncthreads();
+  }
+  if (i < m) beta[i] = b;
+  f64 tc = i < m ? tailc[i] * b : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tc += __shfl_xor_sync(FULLM, tc, o);
+  if ((i & 31) == 0) red[i >> 5] = tc;
+  __syncthreads();
+  if (i == 0) *tail_coef = (red[0] + red[1]) + (red[2] + red[3]);
 }
 
 }  // namespace dfb
@@ -611,7 +729,8 @@ struct dfb_gmres {
   unsigned* ctr = nullptr;  // [2] last-block election counters (multi-dot, update)
   size_t bytes = 0;
   int n_interior = 0;
-  dfb_parallel_ops par = {0, 0, nullptr, nullptr, nullptr, nullptr};
+  dfb_parallel_ops par = {0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
+  unsigned long long seq = 0, hseq = 0;   // sequence numbers of the fused peer-memory collectives (identical on all ranks)
   bool parallel = false;
 };
 
@@ -714,8 +833,21 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   const int ugrid = std::min(std::min(UCHUNK, 4 * num_sms()), ceil_div((i64)(nl / 2) * USPLIT, 256));
   const int cgrid = std::min(1184, ceil_div((i64)(nl / 2), 256));              // blocks of the combine kernel
   // y(compact) = beta*y + alpha * A x(local layout): interior rows overlap the ghost exchange of x
+  const P2PHandle* ph = W->parallel ? static_cast<const P2PHandle*>(W->par.p2p) : nullptr;
+  const P2PView* pv = ph ? ph->dev : nullptr;
+  f64* const zvec = ph ? ph->host.z_local : W->z;   // peer-memory mode: z lives in the IPC-shared region
+  const int n_send = ph ? ph->host.send_off[ph->host.n_nbr] : 0;
   auto matvec = [&](f64 alpha, f64* x, f64 beta, f64* y) -> int {
-    if (W->parallel) {
+    if (pv && x == zvec) {
+      // fused halo: neighbours' ghost values are stored straight into their z over NVLink; ONE mat-vec launch whose
+      // boundary-row blocks wait for the flags (they are scheduled last, after all interior blocks)
+      const unsigned long long hseq = ++W->hseq;
+      if (ph->host.n_nbr > 0) {
+        k_halo_push<<<std::max(1, ceil_div(n_send, 128)), 128, 0, st>>>(pv, n_send, poffN, hseq);
+        DFB_LAUNCH_CHECK();
+      }
+      DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, alpha, x, poffN, beta, y, poffC, st, pv, hseq, W->n_interior));
+    } else if (W->parallel) {
       DFB_CHECK(W->par.halo_begin(x, st, W->par.user));
       DFB_CHECK(launch_spmv(0, W->n_interior, rp, ci, A00, A01, A10, A11, alpha, x, poffN, beta, y, poffC, st));
       DFB_CHECK(W->par.halo_end(x, st, W->par.user));
@@ -763,32 +895,44 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     // q_iter = w / ||w|| written back in place, z = P^-1 q_iter (local layout); then w = A z
     prof.begin("scale_pc_apply", st);
     k_scale_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, &W->S->inv_norm, dinv00, dinv11, QCOL(iter), poffC,
-                                                          W->z, poffN);
+                                                          zvec, poffN);
     DFB_LAUNCH_CHECK();
     prof.end(st);
     f64* w = QCOL(iter + 1);
     prof.begin("spmv", st);
-    DFB_CHECK(matvec(1.0, W->z, 0.0, w));
+    DFB_CHECK(matvec(1.0, zvec, 0.0, w));
     prof.end(st);
     // h = Q^T w  (krylov.c:166-174)
     const int ncol = iter + 1;
+    const unsigned long long seq = pv ? ++W->seq : 0ull;
     prof.begin("multidot", st);
     const int ny = ceil_div(ncol, JT);
     const int mg = std::max(1, std::min(mgrid, (4 * num_sms()) / ny));   // one resident wave of (row chunk, column group) blocks
-    k_multidot<<<dim3(mg, ny), 256, 0, st>>>(nl, Q, ldq, ncol, w, W->part, HCOL(iter), W->ctr);
+    k_multidot<<<dim3(mg, ny), 256, 0, st>>>(nl, Q, ldq, ncol, w, W->part, HCOL(iter), W->ctr, pv, seq);
     DFB_LAUNCH_CHECK();
     prof.end(st);
-    if (W->parallel) DFB_CHECK(W->par.allreduce(HCOL(iter), ncol, st, W->par.user));
+    if (W->parallel && !pv) {
+      prof.begin("allreduce h", st);
+      DFB_CHECK(W->par.allreduce(HCOL(iter), ncol, st, W->par.user));
+      prof.end(st);
+    }
     // w -= Q h, fused with ||w||^2 and (single GPU) the scalar Givens step  (krylov.c:176-183, 229-277)
     prof.begin("update", st);
     k_update<<<ugrid, 256, 0, st>>>(nl, Q, ldq, ncol, HCOL(iter), w, W->part, &W->S->nrm2_live, W->ctr + 1, W->parallel ? 0 : 1,
-                                    W->S, W->gv, W->beta, W->tailc, W->res_hist);
+                                    W->S, W->gv, W->beta, W->tailc, W->res_hist, pv, seq);
     DFB_LAUNCH_CHECK();
     prof.end(st);
-    if (W->parallel) {
+    if (pv) {
+      prof.begin("step (peer sum)", st);
+      k_gmres_step_peer<<<1, 32, 0, st>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist, pv, seq);
+      DFB_LAUNCH_CHECK();
+      prof.end(st);
+    } else if (W->parallel) {
+      prof.begin("allreduce nrm+step", st);
       DFB_CHECK(W->par.allreduce(&W->S->nrm2_live, 1, st, W->par.user));
       k_gmres_step<<<1, 1, 0, st>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist);
       DFB_LAUNCH_CHECK();
+      prof.end(st);
     }
     if ((iter + 1) % 20 == 0) {  // the reference's only convergence test (krylov.c:281-290)
       DFB_CUDA(cudaMemcpyAsync(hist.data(), W->res_hist, sizeof(f64) * ((size_t)iter + 2), cudaMemcpyDeviceToHost, st));
@@ -801,12 +945,17 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   }
   if (iter) {
     prof.begin("trsv..axpy", st);
-    k_gmres_trsv<<<1, 1, 0, st>>>(iter, W->H, ldh, W->beta, W->tailc, W->tail_coef);
+    static bool trsv_attr = false;
+    if (!trsv_attr) {
+      DFB_CUDA(cudaFuncSetAttribute(k_gmres_trsv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(f64) * 127 * 127)));
+      trsv_attr = true;
+    }
+    k_gmres_trsv<<<1, 128, sizeof(f64) * (size_t)iter * iter, st>>>(iter, W->H, ldh, W->beta, W->tailc, W->tail_coef);
     DFB_LAUNCH_CHECK();
     k_combine<<<cgrid, 256, 0, st>>>(nl, Q, ldq, iter, W->beta, W->t);
     DFB_LAUNCH_CHECK();
     // P^-1 on the combination, written compactly into z, then x += z (krylov.c:313-319)
-    k_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, dinv00, dinv11, W->t, poffC, W->z, poffC, 0, 0, 0);
+    k_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, dinv00, dinv11, W->t, poffC, W->z, poffC, 0, 0, 0);   // W->z: private scratch
     DFB_LAUNCH_CHECK();
     k_add_live<<<vgrid, 256, 0, st>>>(n_own, W->z, d_x, poffN);
     DFB_LAUNCH_CHECK();

@@ -17,6 +17,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
+import sys
 import time
 from dataclasses import dataclass
 
@@ -149,13 +150,13 @@ def partition(mesh, npart: np.ndarray, rank: int, world: int, weak_group: int = 
 # ----------------------------------------------------------------------------------------------------------------
 class ParallelOps(C.Structure):
     _fields_ = [("n_own", C.c_int), ("n_interior", C.c_int), ("allreduce", C.c_void_p), ("halo_begin", C.c_void_p),
-                ("halo_end", C.c_void_p), ("user", C.c_void_p)]
+                ("halo_end", C.c_void_p), ("user", C.c_void_p), ("p2p", C.c_void_p)]
 
 
 class DistFlowSystem:
     """The hot path of one rank.  Needs torch.distributed initialised (any backend) for the NCCL id broadcast."""
 
-    def __init__(self, lm: LocalMesh, device, bcs=None, max_iter=120, atol=1e-12, rtol=1e-4):
+    def __init__(self, lm: LocalMesh, device, bcs=None, max_iter=120, atol=1e-12, rtol=1e-4, peer_memory=True):
         import torch
         import torch.distributed as dist
         from . import api, lib as _lib
@@ -208,13 +209,54 @@ class DistFlowSystem:
                                                                      lm.recv_offset, lm.recv_nodes)]
         _lib.check(L.dfb_comm_set_halo(comm, self.N, lm.neighbors.size, *[a.ctypes.data_as(C.c_void_p) for a in self._halo_keep]),
                    "dfb_comm_set_halo")
+        self.p2p = self._connect_peer_memory(dist) if (peer_memory and lm.world > 1) else None
         ws = C.c_void_p()
         _lib.check(L.dfb_gmres_create(C.byref(ws), self.N, max_iter), "dfb_gmres_create")
         self.gmres = ws
         fn = lambda name: C.cast(getattr(L, name), C.c_void_p).value
         self.ops = ParallelOps(self.n_own, self.n_int, fn("dfb_comm_allreduce"), fn("dfb_comm_halo_begin"),
-                               fn("dfb_comm_halo_end"), comm.value)
+                               fn("dfb_comm_halo_end"), comm.value, self.p2p)
         _lib.check(L.dfb_gmres_set_parallel(ws, C.byref(self.ops)), "dfb_gmres_set_parallel")
+
+    def _connect_peer_memory(self, dist):
+        """CUDA IPC over NVLink: every rank maps every other rank's mailbox + z vector; the collectives of a GMRES iteration
+        are then fused into the compute kernels (include/dedflow_b200.h, dfb_comm_p2p_*).  Returns the view pointer, or
+        None (NCCL path) when the mapping is not possible on this box -- decided collectively so that all ranks agree."""
+        torch, L, lm = self.torch, self.L, self.lm
+        if lm.world > 8 or os.environ.get("DFB_NO_PEER_MEMORY"):
+            return None
+        handle = (C.c_ubyte * 64)()
+        ok = L.dfb_comm_p2p_alloc(self.comm, handle) == 0
+        mine = {"rank": lm.rank, "handle": bytes(handle), "ok": ok, "n_local": lm.num_node, "neighbors": lm.neighbors.tolist(),
+                "recv_offset": lm.recv_offset.tolist(), "recv_nodes": lm.recv_nodes.astype(np.int32)}
+        everyone = [None] * lm.world
+        dist.all_gather_object(everyone, mine)
+        everyone.sort(key=lambda d: d["rank"])
+        view = None
+        if all(d["ok"] for d in everyone):
+            handles = b"".join(d["handle"] for d in everyone)
+            remote = np.zeros(max(1, lm.send_nodes.size), np.int32)
+            nloc = np.zeros(max(1, lm.neighbors.size), np.int32)
+            for q, nb in enumerate(lm.neighbors.tolist()):
+                d = everyone[nb]
+                qq = d["neighbors"].index(lm.rank)              # my position in the neighbour's own neighbour list
+                ghosts = d["recv_nodes"][d["recv_offset"][qq]:d["recv_offset"][qq + 1]]
+                s0, s1 = int(lm.send_offset[q]), int(lm.send_offset[q + 1])
+                assert ghosts.size == s1 - s0, "halo lists of neighbouring ranks disagree"
+                remote[s0:s1] = ghosts                          # both sides list the nodes in ascending global id
+                nloc[q] = d["n_local"]
+            hb = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+            ok = L.dfb_comm_p2p_connect(self.comm, hb, remote.ctypes.data_as(C.c_void_p), nloc.ctypes.data_as(C.c_void_p)) == 0
+            if ok:
+                view = L.dfb_comm_p2p_view(self.comm)
+        flag = torch.tensor([1 if view else 0], device=self.dev if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if lm.rank == 0:
+                print("dedflow_b200: peer-memory mode unavailable (%s); using the NCCL path" %
+                      L.dfb_last_error().decode(errors="replace"), file=sys.stderr)
+            return None
+        return view
 
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
@@ -272,12 +314,14 @@ def weak_scaling_m(m1: int, world: int) -> int:
     return int(round(m1 * world ** (1.0 / 3.0)))
 
 
-def bench_main(args, rank, world, local_rank):
-    """bench.py --gpus N (N > 1): weak scaling, ~the configs[1] element count per GPU."""
+def bench_main(args, rank, world, local_rank, B=None):
+    """bench.py --gpus N (N > 1): weak scaling, ~the configs[1] element count per GPU.  B = the bench module (it owns the
+    protected stdout the JSON line goes to)."""
     import torch
     import torch.distributed as dist
     from . import boxmesh, lib as dlib
-    import bench as B
+    if B is None:
+        import bench as B
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     m = args.m if args.fixed_m else weak_scaling_m(args.m, world)
     t0 = time.time()
@@ -385,6 +429,6 @@ def bench_main(args, rank, world, local_rank):
                           "gmres_iters": its, "setup_s": setup_s, "final_residual": float(state["hist"][-1]),
                           "initial_residual": float(state["hist"][0])},
         }
-        print(json.dumps(line), flush=True)
+        B.emit(line)
     fs.close()
     dist.destroy_process_group()

@@ -53,6 +53,10 @@ _SIGS = {
     "dfb_comm_halo_begin": (ci, [vp, vp, vp]),
     "dfb_comm_halo_end": (ci, [vp, vp, vp]),
     "dfb_comm_halo": (ci, [vp, vp, vp]),
+    "dfb_comm_p2p_alloc": (ci, [vp, vp]),
+    "dfb_comm_p2p_connect": (ci, [vp, vp, vp, vp]),
+    "dfb_comm_p2p_view": (vp, [vp]),
+    "dfb_gmres_solve_pc": (ci, [vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.POINTER(ci), vp, vp]),
     "dfb_gmres_solve": (ci, [vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.POINTER(ci), vp, vp]),
 }
 

@@ -153,6 +153,11 @@ typedef struct dfb_parallel_ops {
   int (*halo_begin)(double* d_x, void* stream, void* user);
   int (*halo_end)(double* d_x, void* stream, void* user);
   void* user;
+  /* Optional (may be NULL): dfb_comm_p2p_view().  When set, the collectives INSIDE a GMRES iteration are fused into the
+   * compute kernels over NVLink peer memory (partial sums and halo values are stored directly into the peers' memory,
+   * summed in rank order): no NCCL call and no extra launch per reduction.  The callbacks above are still used outside
+   * the iteration loop (initial residual, final ghost refresh). */
+  const void* p2p;
 } dfb_parallel_ops;
 int dfb_gmres_set_parallel(dfb_gmres* ws, const dfb_parallel_ops* ops);
 /* Solve A x = b (x in/out, b in; both 6N device vectors).  Convergence is tested only when (iter+1)%20==0 against
@@ -190,6 +195,15 @@ int dfb_comm_halo_begin(double* d_x, void* stream, void* user);
 int dfb_comm_halo_end(double* d_x, void* stream, void* user);
 /* blocking convenience: refresh the ghosts of a 6N-layout vector */
 int dfb_comm_halo(dfb_comm* comm, double* d_x, void* stream);
+/* Peer-memory (CUDA IPC over NVLink) mode, one node only.  (1) every rank allocates its shared region (mailbox + the
+ * preconditioned Krylov vector z with num_local_nodes*6 doubles) and gets a 64-byte IPC handle; (2) the host gathers the
+ * handles of all ranks (rank order) and every rank connects; (3) the halo plan gains, for every node it sends, the node's
+ * local id on the receiving rank and that rank's local node count.  dfb_comm_p2p_view() is then passed in
+ * dfb_parallel_ops.p2p.  Call dfb_comm_set_halo first. */
+int dfb_comm_p2p_alloc(dfb_comm* comm, void* handle64);
+int dfb_comm_p2p_connect(dfb_comm* comm, const void* handles /* nranks x 64 bytes */, const int* h_remote_nodes,
+                         const int* h_neighbor_num_local);
+const void* dfb_comm_p2p_view(dfb_comm* comm);
 
 #pragma GCC visibility pop
 #ifdef __cplusplus
