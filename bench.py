@@ -342,7 +342,21 @@ def run_ours(args, rank, world):
     def spmv_loop():
         for _ in range(20):
             fs.matrix_matvec(xs, ys)
-    t_spmv = ev_ms(torch, spmv_loop, 5) / 20
+    t_spmv_b2b = ev_ms(torch, spmv_loop, 5) / 20
+    # the roofline number: every launch starts from a flushed L2 (a 256 MB buffer is read in between), which is the
+    # state the mat-vec finds inside a solve, where ~230 MB of Krylov basis stream through L2 between two mat-vecs
+    flush = torch.ones(64 * 1024 * 1024, dtype=torch.float32, device="cuda")   # 256 MB, READ so that L2 holds clean lines
+    ts = []
+    for _ in range(20):
+        flush.sum()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fs.matrix_matvec(xs, ys)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    t_spmv = float(np.median(ts))
+    del flush
 
     def solve():
         dx.zero_()
@@ -354,7 +368,7 @@ def run_ours(args, rank, world):
     krylov_bytes = its * ab["spmv"] + sum(16 * nl * (j + 1) + 48 * nl for j in range(its)) + 8 * nl * its + 32 * nl
     roofs = {
         "k_spmv_fs": {"ms": t_spmv, "bytes": ab["spmv"]},
-        "k_rowJ (assemble J, gather)": {"ms": tJk, "bytes": ab["assemble_J"]},
+        "k_jprep2+k_pullJ (assemble J, pull)": {"ms": tJk, "bytes": ab["assemble_J"]},
         "k_elemF+k_gatherF (assemble F, gather)": {"ms": tFk, "bytes": ab["assemble_F"]},
         "KrylovSolve (all kernels)": {"ms": t_solve, "bytes": krylov_bytes},
     }
@@ -364,8 +378,15 @@ def run_ours(args, rank, world):
     # dominant kernel of the step: the Krylov solve is >90% of it; inside it the SpMV, the multi-dot and the update each
     # stream comparable bytes.  The named kernel is the SpMV (the one BASELINE.json's metric quotes).
     spmv_share = its * t_spmv / ms
+    traffic = None                      # dram__bytes_read+write per launch from the committed `ncu --set full` capture
+    tp = ROOT / "profiles" / "r01_ncu_traffic.json"
+    if tp.exists() and args.m == 55:
+        try:
+            traffic = json.loads(tp.read_text())["k_spmv_fs"]["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
     roofline = {"kernel": "k_spmv_fs", "bound": "hbm", "achieved": roofs["k_spmv_fs"]["achieved"], "peak": hbm, "unit": "GB/s",
-                "frac": roofs["k_spmv_fs"]["frac"], "traffic": None, "peak_source": hbm_src,
+                "frac": roofs["k_spmv_fs"]["frac"], "traffic": traffic, "peak_source": hbm_src,
                 "bytes_per_launch": ab["spmv"], "ms_per_launch": t_spmv, "share_of_step": spmv_share,
                 "achieved_reference_format": ab["spmv_reference_format"] / (t_spmv * 1e-3) / 1e9}
     line = {
@@ -374,7 +395,8 @@ def run_ours(args, rank, world):
         "config": {"workload": f"BASELINE configs[1]: Kuhn box m={args.m}, {E} tets, {N} nodes, nnz {Z}; step = AssembleSystem(F) + "
                                f"AssembleSystem(J) (tets+weak-BC faces+Dirichlet) + KrylovSolve (GMRES(120), {its} iterations to the "
                                "reference's stopping rule), state B", "assembly_mode": args.mode,
-                   "l2": "working set (matrix 16*nnz*8 B + Krylov basis) exceeds the 126 MB L2; no explicit flush"},
+                   "l2": "step: working set (matrix 16*nnz*8 B = 328 MB + Krylov basis) exceeds the 126 MB L2, no explicit flush; "
+                         "roofline kernel: L2 flushed (256 MB read) before every timed launch"},
         "clocks": clocks,
         "e2e": {"value": E / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 2 * 6 * N * 8,
                 "d2h_bytes_per_step": 6 * N * 8 + 8 * (its + 1)},
@@ -382,7 +404,7 @@ def run_ours(args, rank, world):
         "roofline": roofline,
         "roofline_all": roofs,
         "breakdown": {"assemble_F_ms": tF, "assemble_J_ms": tJ, "assemble_elems_per_s": E / ((tF + tJ) * 1e-3),
-                      "assemble_J_kernel_elems_per_s": E / (tJk * 1e-3), "spmv_ms": t_spmv, "spmv_gbs": roofs["k_spmv_fs"]["achieved"],
+                      "assemble_J_kernel_elems_per_s": E / (tJk * 1e-3), "spmv_ms": t_spmv, "spmv_back_to_back_ms": t_spmv_b2b, "spmv_gbs": roofs["k_spmv_fs"]["achieved"],
                       "spmv_pct_hbm": 100 * roofs["k_spmv_fs"]["frac"], "solve_s_per_step": t_solve * 1e-3, "gmres_iters": its,
                       "setup_s": setup_s, "final_residual": float(state["hist"][-1]), "initial_residual": float(state["hist"][0])},
     }

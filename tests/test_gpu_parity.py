@@ -219,13 +219,15 @@ def test_gmres_dead_tail_rank_one(api, oracle):
     fs.close()
 
 
-def test_full_size_properties_1m(api):
-    """BASELINE config 2 (1M-element mesh): size-independent properties -- linearity of the mat-vec, agreement of the
-    three assembly variants, GMRES residual equals the true residual."""
-    mesh = boxmesh.make_box(55)
+@pytest.mark.parametrize("m,num_tet", [(55, 998250), (139, 16113714)])
+def test_full_size_properties(api, m, num_tet):
+    """BASELINE configs 2 and 3 (1M- and 16M-element meshes, the latter beyond the reference's own i32 limit, defect D17) on
+    one GPU: size-independent properties -- valid coloring, agreement of the three assembly variants, linearity of the
+    mat-vec, GMRES residual equals the true residual and decreases monotonically."""
+    mesh = boxmesh.make_box(m)
     fs = api.FlowSystem(mesh)
     N = mesh.num_node
-    assert mesh.num_tet == 998250
+    assert mesh.num_tet == num_tet
     wg, dwg = boxmesh.state_random(N)
     d_wg, d_dwg = torch.from_numpy(wg).cuda(), torch.from_numpy(dwg).cuda()
     # coloring validity (no two same-color elements share a node)
