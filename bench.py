@@ -419,7 +419,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--m", type=int, default=55, help="cells per direction of the box mesh (55 -> 998,250 tets)")
+    ap.add_argument("--m", "--cells", dest="m", type=int, default=55,
+                    help="cells per direction of the box mesh (55 -> 998,250 tets); use --cells under torchrun, which claims --m")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="gather", choices=["gather", "atomic", "colored", "auto"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -86,7 +86,13 @@ struct P2PView {
   unsigned long long nbr_poff[P2P_MAXR];   // 3 * N_local of the neighbour (offset of p inside its z)
   const int* send_nodes;                   // [n_send] my local ids
   const int* remote_nodes;                 // [n_send] the same nodes in the neighbour's local numbering (its ghosts)
-  unsigned* push_ctr;                      // last-block counter of the halo push kernel
+  unsigned* push_ctr;                      // last-block counter of the kernel that pushes the halo
+  // the send lists inverted: boundary-owned node i (tgt_base <= i < tgt_base + tgt_n) goes to the targets
+  // [tgt_ptr[i - tgt_base], tgt_ptr[i - tgt_base + 1]) = (neighbour slot q, local id on that neighbour)
+  int tgt_base, tgt_n;
+  const int* tgt_ptr;
+  const int* tgt_q;
+  const int* tgt_rid;
 };
 
 struct P2PHandle { P2PView host; const P2PView* dev; };   // what dfb_comm_p2p_view() returns

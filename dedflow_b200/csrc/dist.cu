@@ -108,6 +108,7 @@ struct dfb_comm {
   size_t shared_bytes = 0;
   void* peer_base[P2P_MAXR] = {nullptr};
   int* d_remote_nodes = nullptr;
+  int *d_tgt_ptr = nullptr, *d_tgt_q = nullptr, *d_tgt_rid = nullptr;
   unsigned* d_push_ctr = nullptr;
   P2PView* d_view = nullptr;
   P2PView h_view;
@@ -145,6 +146,7 @@ void dfb_comm_destroy(dfb_comm* c) {
   cudaFree(c->d_send_nodes); cudaFree(c->d_recv_nodes); cudaFree(c->d_send_buf); cudaFree(c->d_recv_buf);
   for (int r = 0; r < c->nranks && r < P2P_MAXR; r++)
     if (c->peer_base[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_base[r]);
+  cudaFree(c->d_tgt_ptr); cudaFree(c->d_tgt_q); cudaFree(c->d_tgt_rid);
   cudaFree(c->shared); cudaFree(c->d_remote_nodes); cudaFree(c->d_push_ctr); cudaFree(c->d_view);
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
   if (c->ev_done) cudaEventDestroy(c->ev_done);
@@ -273,6 +275,34 @@ int dfb_comm_p2p_connect(dfb_comm* c, const void* handles, const int* h_remote_n
   }
   v.send_nodes = c->d_send_nodes;
   v.remote_nodes = c->d_remote_nodes;
+  // invert the send lists: per boundary-owned node the (neighbour slot, remote id) targets
+  v.tgt_base = 0; v.tgt_n = 0;
+  if (c->n_send) {
+    std::vector<int> sn((size_t)c->n_send);
+    DFB_CUDA(cudaMemcpy(sn.data(), c->d_send_nodes, sizeof(int) * (size_t)c->n_send, cudaMemcpyDeviceToHost));
+    int lo = sn[0], hi = sn[0];
+    for (int x : sn) { lo = x < lo ? x : lo; hi = x > hi ? x : hi; }
+    const int n = hi - lo + 1;
+    std::vector<int> ptr((size_t)n + 1, 0), tq((size_t)c->n_send), trid((size_t)c->n_send);
+    for (int x : sn) ptr[(size_t)(x - lo) + 1]++;
+    for (int i = 0; i < n; i++) ptr[(size_t)i + 1] += ptr[i];
+    std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+    for (int q = 0; q < v.n_nbr; q++)
+      for (int t = c->send_off[q]; t < c->send_off[q + 1]; t++) {
+        const int pos = fill[(size_t)(sn[t] - lo)]++;
+        tq[pos] = q;
+        trid[pos] = h_remote_nodes[t];
+      }
+    cudaFree(c->d_tgt_ptr); cudaFree(c->d_tgt_q); cudaFree(c->d_tgt_rid);
+    DFB_CUDA(cudaMalloc(&c->d_tgt_ptr, sizeof(int) * ((size_t)n + 1)));
+    DFB_CUDA(cudaMalloc(&c->d_tgt_q, sizeof(int) * (size_t)c->n_send));
+    DFB_CUDA(cudaMalloc(&c->d_tgt_rid, sizeof(int) * (size_t)c->n_send));
+    DFB_CUDA(cudaMemcpy(c->d_tgt_ptr, ptr.data(), sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice));
+    DFB_CUDA(cudaMemcpy(c->d_tgt_q, tq.data(), sizeof(int) * (size_t)c->n_send, cudaMemcpyHostToDevice));
+    DFB_CUDA(cudaMemcpy(c->d_tgt_rid, trid.data(), sizeof(int) * (size_t)c->n_send, cudaMemcpyHostToDevice));
+    v.tgt_base = lo; v.tgt_n = n;
+    v.tgt_ptr = c->d_tgt_ptr; v.tgt_q = c->d_tgt_q; v.tgt_rid = c->d_tgt_rid;
+  }
   if (!c->d_push_ctr) {
     DFB_CUDA(cudaMalloc(&c->d_push_ctr, sizeof(unsigned)));
     DFB_CUDA(cudaMemset(c->d_push_ctr, 0, sizeof(unsigned)));

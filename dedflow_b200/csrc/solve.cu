@@ -69,6 +69,17 @@ struct SolveProfiler {
   }
 };
 
+// ---- scalar state of the Arnoldi/Givens recurrence, all on the device --------------------------------------
+struct GmresScalars {
+  f64 nrm2_live;   // sum of squares of the live part (after the cross-rank reduction)
+  f64 tail2;       // |b[4N:6N)|^2 (after the cross-rank reduction)
+  f64 inv_norm;    // 1/||w||
+  f64 rnrm_init;
+  f64 cw;          // peer-memory mode: dead-tail coefficient of the current w, -sum_j h_j tailc_j (set by k_update)
+};
+
+__device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist);
+
 // ------------------------------------------------------------------------------------------------------------
 // SpMV.  Row i of the output: u -> y[3*i + ii], p -> y[y_poff + i]; input x: u -> x[3*c + l], p -> x[x_poff + c].
 // ------------------------------------------------------------------------------------------------------------
@@ -78,9 +89,9 @@ struct SolveProfiler {
 // twice, no second dependent index->x chain), so only the x gathers wait on a previous load.
 // PEER = true (data-parallel, peer-memory mode): x is the shared z vector whose ghost entries are stored by the
 // neighbouring GPUs; a block that owns rows >= n_interior first waits for this mat-vec's halo flags, and x is read
-// through L2 (ld.cg) instead of the non-coherent path.
+// through L2 (ld.cg) for the ghost columns (>= n_rows) instead of the non-coherent path.
 template <bool PEER>
-__device__ __forceinline__ f64 ld_x(const f64* p) { return PEER ? __ldcg(p) : __ldg(p); }
+__device__ __forceinline__ f64 ld_x(const f64* p, bool ghost) { return (PEER && ghost) ? __ldcg(p) : __ldg(p); }
 
 template <int G, bool PEER>
 __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
@@ -129,14 +140,14 @@ __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int
     const f64 b0 = __ldcs(A01 + s3 + kk), b1 = __ldcs(A01 + s3 + len + kk), b2 = __ldcs(A01 + s3 + 2 * len + kk);
     const f64 bp = __ldcs(A11 + start + kk);
     const int col = __ldg(col_ind + start + kk);
-    const f64 xp = okk ? ld_x<PEER>(x + x_poff + col) : 0.0;
+    const f64 xp = okk ? ld_x<PEER>(x + x_poff + col, col >= n_rows) : 0.0;
     f64 xv[3];
 #pragma unroll
     for (int u = 0; u < 3; u++) {
       const int q = u * G + lane;          // position inside the chunk's 3*G velocity entries
       const int kl = q / 3, l = q - 3 * kl;
       const int cu = __shfl_sync(gmask, col, kl, G);
-      xv[u] = oku[u] ? ld_x<PEER>(x + (size_t)cu * 3 + l) : 0.0;
+      xv[u] = oku[u] ? ld_x<PEER>(x + (size_t)cu * 3 + l, cu >= n_rows) : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < 3; u++) {
@@ -203,34 +214,6 @@ int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, cons
 #undef DFB_SPMV
   DFB_LAUNCH_CHECK();
   return DFB_OK;
-}
-
-// halo push (peer-memory mode): the (u,p) of every boundary-owned node of z is stored into the ghost slot of the
-// neighbouring GPU's z; the last block to finish raises this mat-vec's flag on every neighbour.
-__global__ void __launch_bounds__(128) k_halo_push(const P2PView* __restrict__ pv, int n_send, size_t poff_local,
-                                                   unsigned long long hseq) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n_send) {
-    int q = 0;
-    while (q + 1 < pv->n_nbr && t >= pv->send_off[q + 1]) q++;
-    const int node = pv->send_nodes[t], rid = pv->remote_nodes[t];
-    const f64* zl = pv->z_local;
-    f64* zr = pv->z_peer[pv->nbr[q]];
-    const f64 a = zl[(size_t)node * 3], b = zl[(size_t)node * 3 + 1], c = zl[(size_t)node * 3 + 2], d = zl[poff_local + node];
-    zr[(size_t)rid * 3] = a; zr[(size_t)rid * 3 + 1] = b; zr[(size_t)rid * 3 + 2] = c;
-    zr[pv->nbr_poff[q] + rid] = d;
-  }
-  __shared__ bool is_last;
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(pv->push_ctr, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!is_last) return;
-  if (threadIdx.x == 0) *pv->push_ctr = 0u;
-  if ((int)threadIdx.x < pv->n_nbr) {
-    __threadfence_system();
-    p2p_signal(pv->mbox_peer[pv->nbr[threadIdx.x]] + p2p_h_flag(pv->nranks, pv->rank), hseq);
-  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -314,6 +297,75 @@ __global__ void k_scale_pc_apply(int n, const f64* __restrict__ scale, const f64
   z[z_poff + i] = xp * dinv11[i];
 }
 
+// Peer-memory variant of the kernel above, with both neighbouring collectives fused in:
+//   prologue (seq != 0): every block waits for all ranks' partial ||w||^2 of the previous Arnoldi step (stored into OUR
+//     mailbox by their k_update), sums them in rank order and forms 1/||w||; block 0 also runs the scalar Givens step;
+//   epilogue: boundary-owned nodes store their (u,p) of z straight into the ghost slots of the neighbours' z; the last
+//     block to finish raises this mat-vec's halo flag on every neighbour.
+__global__ void __launch_bounds__(128) k_scale_pc_apply_peer(int n, const f64* __restrict__ dinv00, const f64* __restrict__ dinv11,
+                                                             f64* __restrict__ w, size_t w_poff, f64* __restrict__ z, size_t z_poff,
+                                                             const P2PView* __restrict__ pv, unsigned long long seq,
+                                                             unsigned long long hseq, int it_prev, GmresScalars* S, f64* hcol_prev,
+                                                             f64* gv, f64* beta, f64* tailc, f64* res_hist) {
+  __shared__ f64 s_scale;
+  __shared__ bool is_last;
+  if (seq) {
+    const int R = pv->nranks, par = (int)(seq & 1ull);
+    if ((int)threadIdx.x < R) p2p_wait(pv->mbox_local + p2p_b_flag(R, par, threadIdx.x), seq);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const f64* mb = reinterpret_cast<const f64*>(pv->mbox_local);
+      f64 nrm2 = 0.0;
+      for (int r = 0; r < R; r++) nrm2 += __ldcg(mb + p2p_b_data(R, par, r));
+      const f64 cw = S->cw;
+      s_scale = 1.0 / sqrt(nrm2 + cw * cw * S->tail2);
+      if (blockIdx.x == 0) {
+        S->nrm2_live = nrm2;
+        gmres_step_dev(it_prev, S, hcol_prev, gv, beta, tailc, res_hist);
+      }
+    }
+  } else if (threadIdx.x == 0) {
+    s_scale = S->inv_norm;
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const f64 s = s_scale;
+    const f64* D = dinv00 + (size_t)i * 9;
+    f64* wu = w + (size_t)i * 3;
+    const f64 x0 = wu[0] * s, x1 = wu[1] * s, x2 = wu[2] * s, xp = w[w_poff + i] * s;
+    wu[0] = x0; wu[1] = x1; wu[2] = x2; w[w_poff + i] = xp;
+    const f64 z0 = D[0] * x0 + D[3] * x1 + D[6] * x2, z1 = D[1] * x0 + D[4] * x1 + D[7] * x2, z2 = D[2] * x0 + D[5] * x1 + D[8] * x2;
+    const f64 zp = xp * dinv11[i];
+    f64* zu = z + (size_t)i * 3;
+    zu[0] = z0; zu[1] = z1; zu[2] = z2;
+    z[z_poff + i] = zp;
+    const int b = i - pv->tgt_base;
+    if (b >= 0 && b < pv->tgt_n) {
+      for (int t = pv->tgt_ptr[b]; t < pv->tgt_ptr[b + 1]; t++) {
+        const int q = pv->tgt_q[t], rid = pv->tgt_rid[t];
+        f64* zr = pv->z_peer[pv->nbr[q]];
+        zr[(size_t)rid * 3] = z0; zr[(size_t)rid * 3 + 1] = z1; zr[(size_t)rid * 3 + 2] = z2;
+        zr[pv->nbr_poff[q] + rid] = zp;
+      }
+      __threadfence_system();
+    }
+  }
+  if (pv->n_nbr == 0) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = atomicAdd(pv->push_ctr, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  if (threadIdx.x == 0) *pv->push_ctr = 0u;
+  if ((int)threadIdx.x < pv->n_nbr) {
+    __threadfence_system();
+    p2p_signal(pv->mbox_peer[pv->nbr[threadIdx.x]] + p2p_h_flag(pv->nranks, pv->rank), hseq);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Krylov vector kernels.  A "live" vector has nl = 4*n_own entries stored compactly: u of the owned nodes
 // [0, 3 n_own) followed by p [3 n_own, 4 n_own).
@@ -351,8 +403,6 @@ __device__ __forceinline__ bool last_block(unsigned* ctr, unsigned total) {
   return is_last;
 }
 
-struct GmresScalars;
-__device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist);
 
 // h[j] = sum_i Q[i, j] * w[i],  j in [0, ncol): stage 1 = per-(chunk, column) partials, stage 2 by the last block.
 // nl is a multiple of 4 and every column starts 32-byte aligned, so a thread streams 16-byte pairs of rows: up to
@@ -513,8 +563,11 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
   s = block_sum_256(s, sm);
   if (threadIdx.x == 0) {
     *ctr = 0u;
-    if (pv) {   // publish the partial sum of squares; k_gmres_step_peer sums the ranks
+    if (pv) {   // publish the partial sum of squares; the next kernel (scale+PC or the step kernel) sums the ranks
       const int R = pv->nranks, par = (int)(seq & 1ull);
+      f64 cw = 0.0;
+      for (int j = 0; j < ncol; j++) cw -= sh[j] * tailc[j];   // same expression and order as gmres_step_dev
+      S->cw = cw;
       for (int r = 0; r < R; r++) reinterpret_cast<f64*>(pv->mbox_peer[r])[p2p_b_data(R, par, pv->rank)] = s;
       __threadfence_system();
       for (int r = 0; r < R; r++) p2p_signal(pv->mbox_peer[r] + p2p_b_flag(R, par, pv->rank), seq);
@@ -589,14 +642,6 @@ __global__ void k_axpy_dev(size_t n, const f64* __restrict__ coef, const f64* __
   const f64 a = *coef;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] += a * b[i];
 }
-
-// ---- scalar state of the Arnoldi/Givens recurrence, all on the device --------------------------------------
-struct GmresScalars {
-  f64 nrm2_live;   // sum of squares of the live part (after the cross-rank reduction)
-  f64 tail2;       // |b[4N:6N)|^2 (after the cross-rank reduction)
-  f64 inv_norm;    // 1/||w||
-  f64 rnrm_init;
-};
 
 // reference BLAS drotg (krylov.c:266 calls cublasDrotg)
 __device__ void drotg_dev(f64& a, f64& b, f64& c, f64& s) {
@@ -836,18 +881,8 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   const P2PHandle* ph = W->parallel ? static_cast<const P2PHandle*>(W->par.p2p) : nullptr;
   const P2PView* pv = ph ? ph->dev : nullptr;
   f64* const zvec = ph ? ph->host.z_local : W->z;   // peer-memory mode: z lives in the IPC-shared region
-  const int n_send = ph ? ph->host.send_off[ph->host.n_nbr] : 0;
   auto matvec = [&](f64 alpha, f64* x, f64 beta, f64* y) -> int {
-    if (pv && x == zvec) {
-      // fused halo: neighbours' ghost values are stored straight into their z over NVLink; ONE mat-vec launch whose
-      // boundary-row blocks wait for the flags (they are scheduled last, after all interior blocks)
-      const unsigned long long hseq = ++W->hseq;
-      if (ph->host.n_nbr > 0) {
-        k_halo_push<<<std::max(1, ceil_div(n_send, 128)), 128, 0, st>>>(pv, n_send, poffN, hseq);
-        DFB_LAUNCH_CHECK();
-      }
-      DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, alpha, x, poffN, beta, y, poffC, st, pv, hseq, W->n_interior));
-    } else if (W->parallel) {
+    if (W->parallel) {
       DFB_CHECK(W->par.halo_begin(x, st, W->par.user));
       DFB_CHECK(launch_spmv(0, W->n_interior, rp, ci, A00, A01, A10, A11, alpha, x, poffN, beta, y, poffC, st));
       DFB_CHECK(W->par.halo_end(x, st, W->par.user));
@@ -891,17 +926,34 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   f64 rnrm_init = 0.0;
   std::vector<f64> hist((size_t)maxit + 1, 0.0);
   SolveProfiler prof;
+  unsigned long long pending_seq = 0;   // peer-memory mode: norm reduction + Givens step of the previous iteration still to run
   while (!converged && iter < maxit) {
     // q_iter = w / ||w|| written back in place, z = P^-1 q_iter (local layout); then w = A z
-    prof.begin("scale_pc_apply", st);
-    k_scale_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, &W->S->inv_norm, dinv00, dinv11, QCOL(iter), poffC,
-                                                          zvec, poffN);
-    DFB_LAUNCH_CHECK();
-    prof.end(st);
     f64* w = QCOL(iter + 1);
-    prof.begin("spmv", st);
-    DFB_CHECK(matvec(1.0, zvec, 0.0, w));
-    prof.end(st);
+    if (pv) {
+      // one kernel: [norm all-reduce + Givens step of iteration iter-1] + scale + P^-1 + [halo push]; then ONE mat-vec launch
+      // whose boundary-row blocks (scheduled last) wait for the neighbours' halo flags
+      const unsigned long long hseq = ++W->hseq;
+      prof.begin("scale_pc_apply", st);
+      k_scale_pc_apply_peer<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, dinv00, dinv11, QCOL(iter), poffC, zvec, poffN, pv, pending_seq,
+                                                                  hseq, iter - 1, W->S, iter ? HCOL(iter - 1) : HCOL(0), W->gv, W->beta,
+                                                                  W->tailc, W->res_hist);
+      DFB_LAUNCH_CHECK();
+      prof.end(st);
+      pending_seq = 0;
+      prof.begin("spmv", st);
+      DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, poffN, 0.0, w, poffC, st, pv, hseq, W->n_interior));
+      prof.end(st);
+    } else {
+      prof.begin("scale_pc_apply", st);
+      k_scale_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, &W->S->inv_norm, dinv00, dinv11, QCOL(iter), poffC,
+                                                            zvec, poffN);
+      DFB_LAUNCH_CHECK();
+      prof.end(st);
+      prof.begin("spmv", st);
+      DFB_CHECK(matvec(1.0, zvec, 0.0, w));
+      prof.end(st);
+    }
     // h = Q^T w  (krylov.c:166-174)
     const int ncol = iter + 1;
     const unsigned long long seq = pv ? ++W->seq : 0ull;
@@ -923,10 +975,16 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     DFB_LAUNCH_CHECK();
     prof.end(st);
     if (pv) {
-      prof.begin("step (peer sum)", st);
-      k_gmres_step_peer<<<1, 32, 0, st>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist, pv, seq);
-      DFB_LAUNCH_CHECK();
-      prof.end(st);
+      // the norm reduction + Givens step are folded into the NEXT iteration's first kernel; they run on their own only
+      // when the host needs the residual now (the every-20th test) or the loop ends
+      pending_seq = seq;
+      if ((iter + 1) % 20 == 0 || iter + 1 == maxit) {
+        prof.begin("step (peer sum)", st);
+        k_gmres_step_peer<<<1, 32, 0, st>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist, pv, seq);
+        DFB_LAUNCH_CHECK();
+        prof.end(st);
+        pending_seq = 0;
+      }
     } else if (W->parallel) {
       prof.begin("allreduce nrm+step", st);
       DFB_CHECK(W->par.allreduce(&W->S->nrm2_live, 1, st, W->par.user));
