@@ -487,6 +487,12 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
 // With do_step the last block also runs the scalar Arnoldi/Givens step (single GPU: no cross-rank sum needed).
 // One resident wave of blocks (4 per SM) strides over 16-byte row pairs; a thread keeps 8 independent 16-byte loads in
 // flight.  (USPLIT > 1 splits the columns of a row pair over lane groups; measured slower, kept as a compile-time knob.)
+#ifndef UPDATE_REVERSE
+#define UPDATE_REVERSE 1
+#endif
+#ifndef UPDATE_LD
+#define UPDATE_LD __ldcs
+#endif
 constexpr int USPLIT = 1;   // measured on B200 (m=55): 1 -> 27 us average per launch, 4 -> 37 us
 __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict__ Q, size_t ldq, int ncol, f64* h,
                                                 f64* __restrict__ w, f64* part, f64* nrm2, unsigned* ctr, int do_step,
@@ -516,9 +522,13 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
   const int lane = threadIdx.x & 31, sub = lane / PW, pl = lane % PW;
   const size_t warp0 = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5, nwarp = ((size_t)gridDim.x * 256) >> 5;
   f64 ss = 0.0;
+  // The multi-dot has just swept the rows in ASCENDING order, so the highest rows of every column are what the 126 MB L2
+  // still holds: sweep DESCENDING here (and leave the lowest rows behind for the next multi-dot's ascending sweep).
+  const bool reverse = UPDATE_REVERSE;
   for (size_t base = warp0 * PW; base < np; base += nwarp * PW) {   // warp-uniform trip count
-    const size_t i = base + pl;
-    const bool ok = i < np;
+    const size_t ib = base + pl;
+    const bool ok = ib < np;
+    const size_t i = reverse ? (np - 1 - (ok ? ib : 0)) : ib;
     f64 ax[2] = {0.0, 0.0}, ay[2] = {0.0, 0.0};
     if (ok) {
       const double2* qi = q2 + i;
@@ -526,7 +536,7 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
         if (j + 8 <= ncol) {
           double2 v[8];
 #pragma unroll
-          for (int u = 0; u < 8; u++) v[u] = __ldcs(qi + (size_t)(j + u) * ld2);
+          for (int u = 0; u < 8; u++) v[u] = UPDATE_LD(qi + (size_t)(j + u) * ld2);
 #pragma unroll
           for (int u = 0; u < 8; u++) {
             ax[u & 1] = fma(v[u].x, sh[j + u], ax[u & 1]);
@@ -534,7 +544,7 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
           }
         } else {
           for (int jj = j; jj < ncol; jj++) {
-            const double2 v = __ldcs(qi + (size_t)jj * ld2);
+            const double2 v = UPDATE_LD(qi + (size_t)jj * ld2);
             ax[0] = fma(v.x, sh[jj], ax[0]);
             ay[0] = fma(v.y, sh[jj], ay[0]);
           }

@@ -6,10 +6,12 @@ owned by the caller (torch tensors in the tests / bench); only raw pointers cros
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libdedflow_b200.so"
+# DFB_LIB: load another build of the same library (A/B measurements of kernel variants); there is still no fallback
+LIB_PATH = Path(os.environ["DFB_LIB"]) if os.environ.get("DFB_LIB") else PKG / "libdedflow_b200.so"
 
 vp = C.c_void_p
 ci = C.c_int
