@@ -174,6 +174,50 @@ class FlowSystem:
                                           self._stream()), "dfb_gmres_solve")
         return iters.value, hist[:iters.value + 1]
 
+    # ------------------------------------------------------------------ the driver around the path
+    def solve_flow_system(self, wgold, dwgold, dwg, maxit=4, tol=0.5e-3, mode="auto"):
+        """SolveFlowSystem of main.c:77-283: Newton iteration on the alpha-level states.  dwg is updated in place.
+        Returns a list of (rnorm[4], gmres_iterations) per Newton iteration, entry 0 = initial norms."""
+        L, N, st = self.L, self.N, self._stream()
+        if getattr(self, "_newton_ws", None) is None:
+            mk = lambda: torch.zeros(6 * N, dtype=torch.float64, device=self.dev)
+            self._newton_ws = (mk(), mk(), mk(), mk())
+        wgalpha, dwgalpha, F, dx = self._newton_ws
+        norms = (C.c_double * 4)()
+
+        def stage():
+            _lib.check(L.dfb_genalpha_stage(N, _p(wgold), _p(dwgold), _p(dwg), _p(wgalpha), _p(dwgalpha), st), "dfb_genalpha_stage")
+
+        def residual():
+            self.assemble_system(wgalpha, dwgalpha, F=F, mode=mode)
+            _lib.check(L.dfb_block_norms(N, _p(F), norms, st), "dfb_block_norms")
+            return np.array(norms[:])
+
+        stage()
+        r0 = residual()
+        hist = [(r0.copy(), 0)]
+        r0 = r0 + 1e-16                                   # main.c:153-156
+        it, converged = 0, False
+        while not converged and it < maxit:
+            self.assemble_system(wgalpha, dwgalpha, J=True, mode=mode)
+            dx.zero_()
+            its, _ = self.krylov_solve(dx, F)
+            _lib.check(L.dfb_newton_update(N, _p(dx), _p(dwg), st), "dfb_newton_update")     # main.c:226
+            stage()                                                                          # main.c:232-246
+            r = residual()
+            hist.append((r.copy(), its))
+            converged = bool(np.all(r < tol * r0))                                           # main.c:271-276
+            it += 1
+        return hist
+
+    def time_step(self, wgold, dwgold, dwg, **kw):
+        """One pass of the time loop of main.c:537-565: predictor, Newton solve, corrector.  All three vectors are updated."""
+        L, N, st = self.L, self.N, self._stream()
+        _lib.check(L.dfb_genalpha_predict(N, _p(dwg), st), "dfb_genalpha_predict")
+        hist = self.solve_flow_system(wgold, dwgold, dwg, **kw)
+        _lib.check(L.dfb_genalpha_correct(N, _p(wgold), _p(dwgold), _p(dwg), st), "dfb_genalpha_correct")
+        return hist
+
     def close(self):
         if self.plan is not None:
             self.L.dfb_plan_destroy(self.plan)

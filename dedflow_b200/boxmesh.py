@@ -169,3 +169,13 @@ def state_default(mesh: BoxMesh):
     wgalpha = wgold + fact2[0] * dwgold + fact2[1] * dwg
     wgalpha[3 * n:4 * n] = 0.0
     return wgalpha, dwgalpha
+
+
+def state_initial(mesh: BoxMesh):
+    """(wgold, dwgold, dwg) at step 0: the reference's initial condition (main.c:286-321) with zero rates."""
+    n = mesh.num_node
+    wgold = np.zeros(6 * n)
+    wgold[0:3 * n:3] = 1.0
+    wgold[4 * n:5 * n] = mesh.xg[:, 0]
+    wgold[5 * n:6 * n] = -mesh.xg[:, 0]
+    return wgold, np.zeros(6 * n), np.zeros(6 * n)

@@ -55,6 +55,12 @@ _SIGS = {
     "dfb_comm_halo_begin": (ci, [vp, vp, vp]),
     "dfb_comm_halo_end": (ci, [vp, vp, vp]),
     "dfb_comm_halo": (ci, [vp, vp, vp]),
+    "dfb_genalpha_stage": (ci, [ci, vp, vp, vp, vp, vp, vp]),
+    "dfb_newton_update": (ci, [ci, vp, vp, vp]),
+    "dfb_genalpha_predict": (ci, [ci, vp, vp]),
+    "dfb_genalpha_correct": (ci, [ci, vp, vp, vp, vp]),
+    "dfb_block_sumsq": (ci, [ci, ci, vp, vp, vp]),
+    "dfb_block_norms": (ci, [ci, vp, vp, vp]),
     "dfb_comm_p2p_alloc": (ci, [vp, vp]),
     "dfb_comm_p2p_connect": (ci, [vp, vp, vp, vp]),
     "dfb_comm_p2p_view": (vp, [vp]),

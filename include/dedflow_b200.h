@@ -175,6 +175,26 @@ int dfb_gmres_solve_pc(dfb_gmres* ws, int num_node, const int* d_row_ptr, const 
                        double* res_hist, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Newton / generalised-alpha vector work of the driver around the path.  Replaces the ~25
+ * cuBLAS axpy/copy/scal/memset calls and the 8 blocking cublasDnrm2 of one Newton iteration (src/main.c:107-118, 127-130,
+ * 226-246, 262-265, 544-545, 559-563).  All vectors are 6N device vectors.
+ * ------------------------------------------------------------------------------------------ */
+/* dwgalpha = (1-am) dwgold + am dwg, pressure slot = dwg;  wgalpha = wgold + dt af (1-g) dwgold + dt af g dwg, pressure slot = 0 */
+int dfb_genalpha_stage(int num_node, const double* d_wgold, const double* d_dwgold, const double* d_dwg, double* d_wgalpha,
+                       double* d_dwgalpha, void* stream);
+/* dwg -= dx */
+int dfb_newton_update(int num_node, const double* d_dx, double* d_dwg, void* stream);
+/* predictor: dwg[u, phi, T] *= (g-1)/g (pressure slot untouched) */
+int dfb_genalpha_predict(int num_node, double* d_dwg, void* stream);
+/* corrector: wgold[u, phi, T] += dt (1-g) dwgold + dt g dwg; dwgold = dwg */
+int dfb_genalpha_correct(int num_node, double* d_wgold, double* d_dwgold, const double* d_dwg, void* stream);
+/* d_out4 (device) = sums of squares of the blocks [u | p | phi | T] of F over the first n_own nodes (data-parallel callers sum
+ * them over ranks); one kernel, fixed summation order */
+int dfb_block_sumsq(int num_node, int n_own, const double* d_F, double* d_out4, void* stream);
+/* h_out4 (HOST) = the four block norms of F (synchronises `stream`, like the reference's cublasDnrm2 with a host result) */
+int dfb_block_norms(int num_node, const double* d_F, double* h_out4, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Data-parallel communicator (NCCL over NVLink 5 / NVSwitch, resolved with dlopen at run time so that the
  * single-GPU library has no NCCL dependency).  One process per GPU; the 128-byte unique id is created on rank 0
  * and distributed by the host (torch.distributed in the bench).  New work: the reference is single-GPU

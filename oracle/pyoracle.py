@@ -208,6 +208,102 @@ class Oracle:
         it = self.L.orc_gmres(n, rp, ci, *blocks, maxit, atol, rtol, x, np.ascontiguousarray(b, np.float64), hist)
         return x, int(it), hist[:it + 1]
 
+    # ------------------------------------------------------------------------------------------------------------
+    # the driver around the path: numpy restatement of reference src/main.c:31-75 (AssembleSystem), :77-283
+    # (SolveFlowSystem) and :537-565 (one pass of the time loop).  SURVEY.md section 8(f), rank 1.
+    # ------------------------------------------------------------------------------------------------------------
+    K_RHOC, K_DT = 0.5, 5e-2
+    K_ALPHAM = (3.0 - K_RHOC) / (1.0 + K_RHOC)
+    K_ALPHAF = 1.0 / (1.0 + K_RHOC)
+    K_GAMMA = 0.5 + K_ALPHAM - K_ALPHAF
+    BCS = {0: (1, 1, 1), 2: (0, 1, 0), 3: (0, 0, 1), 4: (0, 0, 0)}          # main.c:454-476
+
+    def driver_setup(self, mesh):
+        """what main() builds once (main.c:377-411): pattern, colors, batches"""
+        N = mesh.num_node
+        rp, ci = self.nodal_pattern(N, mesh.ien)
+        w = self.weights(curand_host_u32(mesh.num_tet))
+        color, nc, ties = self.color_jpl(N, mesh.ien, w)
+        off, ind = self.color_batches(color)
+        return dict(mesh=mesh, pattern=(rp, ci), color=color, nc=nc, off=off, ind=ind)
+
+    def assemble_system(self, ctx, wgalpha, dwgalpha, want_F=False, want_J=False):
+        """AssembleSystem (main.c:31-75): zero, tets, faces of boundary 4, zero the phi/T residual, Dirichlet"""
+        mesh = ctx["mesh"]
+        N = mesh.num_node
+        rp, ci = ctx["pattern"]
+        Z = ci.size
+        F = np.zeros(6 * N) if want_F else None
+        blocks = [np.zeros(9 * Z), np.zeros(3 * Z), np.zeros(3 * Z), np.zeros(Z)] if want_J else None
+        kw = dict(F=F) if want_F else dict(pattern=(rp, ci), blocks=blocks)
+        self.assemble_tet(N, mesh.ien, mesh.xg, ctx["off"], ctx["ind"], wgalpha, dwgalpha, **kw)
+        if mesh.num_bound > 4:
+            f2e, forn = mesh.bound_faces(4)
+            self.assemble_face(f2e, forn, N, mesh.ien, mesh.xg, ctx["color"], ctx["nc"], wgalpha, dwgalpha, **kw)
+        if want_F:
+            F[4 * N:] = 0.0
+        for b, t in self.BCS.items():
+            bt = np.array(t, np.int32)
+            if want_F:
+                self.dirichlet_vec(mesh.bound_nodes(b), bt, F)
+            if want_J:
+                self.dirichlet_mat(mesh.bound_nodes(b), bt, N, (rp, ci), blocks[0], blocks[1])
+        return F if want_F else blocks
+
+    def alpha_states(self, N, wgold, dwgold, dwg):
+        """main.c:107-118: the axpy sequences exactly as written (two accumulating steps each)"""
+        f1 = (1.0 - self.K_ALPHAM, self.K_ALPHAM)
+        f2 = (self.K_DT * self.K_ALPHAF * (1.0 - self.K_GAMMA), self.K_DT * self.K_ALPHAF * self.K_GAMMA)
+        dwgalpha = np.zeros(6 * N)
+        dwgalpha += f1[0] * dwgold
+        dwgalpha += f1[1] * dwg
+        dwgalpha[3 * N:4 * N] = dwg[3 * N:4 * N]
+        wgalpha = wgold.copy()
+        wgalpha += f2[0] * dwgold
+        wgalpha += f2[1] * dwg
+        wgalpha[3 * N:4 * N] = 0.0
+        return wgalpha, dwgalpha
+
+    @staticmethod
+    def block_norms(N, F):
+        return np.array([np.linalg.norm(F[:3 * N]), np.linalg.norm(F[3 * N:4 * N]), np.linalg.norm(F[4 * N:5 * N]),
+                         np.linalg.norm(F[5 * N:])])
+
+    def solve_flow_system(self, ctx, wgold, dwgold, dwg, maxit=4, tol=0.5e-3):
+        """SolveFlowSystem (main.c:77-283); dwg is updated in place; returns [(rnorm[4], gmres its)]"""
+        N = ctx["mesh"].num_node
+        wga, dwga = self.alpha_states(N, wgold, dwgold, dwg)
+        F = self.assemble_system(ctx, wga, dwga, want_F=True)
+        r0 = self.block_norms(N, F)
+        hist = [(r0.copy(), 0)]
+        r0 = r0 + 1e-16
+        it, converged = 0, False
+        while not converged and it < maxit:
+            blocks = self.assemble_system(ctx, wga, dwga, want_J=True)
+            dx, its, _ = self.gmres(ctx["pattern"], blocks, F)
+            dwg -= dx
+            wga, dwga = self.alpha_states(N, wgold, dwgold, dwg)
+            F = self.assemble_system(ctx, wga, dwga, want_F=True)
+            r = self.block_norms(N, F)
+            hist.append((r.copy(), its))
+            converged = bool(np.all(r < tol * r0))
+            it += 1
+        return hist
+
+    def time_step(self, ctx, wgold, dwgold, dwg, **kw):
+        """one pass of the time loop, main.c:537-565; the three vectors are updated in place"""
+        N = ctx["mesh"].num_node
+        fac = (self.K_GAMMA - 1.0) / self.K_GAMMA
+        dwg[:3 * N] *= fac
+        dwg[4 * N:] *= fac
+        hist = self.solve_flow_system(ctx, wgold, dwgold, dwg, **kw)
+        c0, c1 = self.K_DT * (1.0 - self.K_GAMMA), self.K_DT * self.K_GAMMA
+        for sl in (slice(0, 3 * N), slice(4 * N, 6 * N)):
+            wgold[sl] += c0 * dwgold[sl]
+            wgold[sl] += c1 * dwg[sl]
+        dwgold[:] = dwg
+        return hist
+
     def num_threads(self):
         return int(self.L.orc_num_threads())
 

@@ -183,6 +183,66 @@ def test_unstructured_mesh_matches_oracle(api, oracle, mode):
     fs.close()
 
 
+def test_newton_vector_kernels_match_numpy(api, oracle):
+    """the fused driver kernels against the reference's axpy / copy / scal / nrm2 sequences"""
+    import ctypes as C
+    mesh = boxmesh.make_box(5)
+    N = mesh.num_node
+    fs = api.FlowSystem(mesh, with_colors=False)
+    L, P, st = fs.L, (lambda t: C.c_void_p(t.data_ptr())), fs._stream()
+    rng = np.random.default_rng(4)
+    wgold, dwgold, dwg, dx = (rng.standard_normal(6 * N) for _ in range(4))
+    d = [torch.from_numpy(a.copy()).cuda() for a in (wgold, dwgold, dwg, dx)]
+    wga, dwga = torch.empty(6 * N, dtype=torch.float64, device="cuda"), torch.empty(6 * N, dtype=torch.float64, device="cuda")
+    assert L.dfb_genalpha_stage(N, P(d[0]), P(d[1]), P(d[2]), P(wga), P(dwga), st) == 0
+    owga, odwga = oracle.alpha_states(N, wgold, dwgold, dwg)
+    assert rel(wga.cpu().numpy(), owga) <= 1e-15 and rel(dwga.cpu().numpy(), odwga) <= 1e-15
+    assert np.all(wga.cpu().numpy()[3 * N:4 * N] == 0) and np.array_equal(dwga.cpu().numpy()[3 * N:4 * N], dwg[3 * N:4 * N])
+    norms = (C.c_double * 4)()
+    assert L.dfb_block_norms(N, P(d[3]), norms, st) == 0
+    assert np.abs(np.array(norms[:]) / oracle.block_norms(N, dx) - 1).max() <= 1e-14
+    assert L.dfb_newton_update(N, P(d[3]), P(d[2]), st) == 0
+    assert np.array_equal(d[2].cpu().numpy(), dwg - dx)
+    dwg2 = dwg - dx
+    assert L.dfb_genalpha_predict(N, P(d[2]), st) == 0
+    fac = (oracle.K_GAMMA - 1.0) / oracle.K_GAMMA
+    want = dwg2.copy(); want[:3 * N] *= fac; want[4 * N:] *= fac
+    assert np.array_equal(d[2].cpu().numpy(), want)
+    assert L.dfb_genalpha_correct(N, P(d[0]), P(d[1]), P(d[2]), st) == 0
+    c0, c1 = oracle.K_DT * (1 - oracle.K_GAMMA), oracle.K_DT * oracle.K_GAMMA
+    ow = wgold.copy()
+    for sl in (slice(0, 3 * N), slice(4 * N, 6 * N)):
+        ow[sl] += c0 * dwgold[sl]; ow[sl] += c1 * want[sl]
+    assert rel(d[0].cpu().numpy(), ow) <= 1e-15 and np.array_equal(d[0].cpu().numpy()[3 * N:4 * N], wgold[3 * N:4 * N])
+    assert np.array_equal(d[1].cpu().numpy(), want)
+    fs.close()
+
+
+@pytest.mark.parametrize("m,steps", [(6, 3), (10, 2)])
+def test_time_steps_match_oracle(api, oracle, m, steps):
+    """BASELINE config 5 in miniature: time steps with reassembly in every Newton iteration (main.c:537-565 around
+    SolveFlowSystem, main.c:77-283) from the reference's initial condition, against the numpy/C oracle of the same driver.
+    Newton residual norms and GMRES iteration counts per Newton iteration, and the state after every step."""
+    mesh = boxmesh.make_box(m)
+    N = mesh.num_node
+    fs = api.FlowSystem(mesh)
+    ctx = oracle.driver_setup(mesh)
+    h = [a.copy() for a in boxmesh.state_initial(mesh)]
+    d = [torch.from_numpy(a.copy()).cuda() for a in h]
+    for step in range(steps):
+        oh = oracle.time_step(ctx, *h)
+        gh = fs.time_step(*d)
+        assert len(gh) == len(oh)
+        for (gr, gi), (orr, oi) in zip(gh, oh):
+            assert gi == oi
+            assert np.abs(gr - orr).max() <= 1e-8 * max(oh[0][0].max(), 1e-300), (step, gr, orr)
+        for got, want, name in zip(d, h, ("wgold", "dwgold", "dwg")):
+            g = got.cpu().numpy()
+            for lo, hi in ((0, 3 * N), (3 * N, 4 * N), (4 * N, 6 * N)):
+                assert np.abs(g[lo:hi] - want[lo:hi]).max() <= 1e-8 * max(np.abs(want[lo:hi]).max(), 1e-12), (step, name, lo)
+    fs.close()
+
+
 def test_matvec_pc_match_oracle(api, oracle):
     mesh = shuffled_mesh(8)
     fs, wg, dwg = make_pair(api, oracle, mesh)
