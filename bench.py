@@ -270,6 +270,8 @@ def run_ours(args, rank, world):
     fs = api.FlowSystem(mesh, device=f"cuda:{local_rank}")
     torch.cuda.synchronize()
     setup_s = time.time() - t0
+    if args.timesteps > 0:
+        return run_timesteps(args, fs, mesh, lambda t: t, 1, setup_s)
     Z = fs.nnz
     wg, dwg = boxmesh.state_random(N)
     h_wg = torch.from_numpy(wg).pin_memory()
@@ -414,6 +416,54 @@ def run_ours(args, rank, world):
     fs.close()
 
 
+def run_timesteps(args, fs, mesh_or_local, localize, world, setup_s, dist=None, rank=0, Eg=None, Ng=None):
+    """BASELINE configs[4]: K time steps (predictor, Newton with reassembly of F and J in every nonlinear iteration,
+    corrector: reference src/main.c:537-565 around SolveFlowSystem :77-283) from the reference's initial condition.
+    A "step" of the JSON line is one NEWTON ITERATION (assemble J + KrylovSolve + state update + assemble F + norms)."""
+    import torch
+    from dedflow_b200 import boxmesh
+    Eg = Eg or mesh_or_local.num_tet
+    Ng = Ng or mesh_or_local.num_node
+    state = [torch.from_numpy(localize(a)).cuda() for a in args._initial_state]
+    fs.time_step(*state)                                    # warm-up step (plans, workspaces), then restart
+    state = [torch.from_numpy(localize(a)).cuda() for a in args._initial_state]
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)))
+    if rank == 0:
+        sampler.start()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    newton, gmres, last = 0, 0, None
+    for _ in range(args.timesteps):
+        hist = fs.time_step(*state)
+        newton += len(hist) - 1
+        gmres += sum(h[1] for h in hist)
+        last = hist
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    if rank == 0:
+        clocks = sampler.stop()
+        line = {"metric": METRIC, "value": Eg * newton / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": newton, "warmup": 1,
+                "ms_per_step": ms / newton, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"BASELINE configs[4]: {args.timesteps} time steps on the Kuhn box m={args.m} ({Eg} tets, {Ng} nodes, "
+                                       f"4 live DOF/node) from the reference's initial condition, reassembly of F and J in every Newton "
+                                       f"iteration; a step = one Newton iteration", "l2": "working set exceeds the 126 MB L2"},
+                "clocks": clocks,
+                "breakdown": {"time_steps": args.timesteps, "newton_iterations": newton, "gmres_iterations": gmres,
+                              "s_per_time_step": ms * 1e-3 / args.timesteps, "setup_s": setup_s,
+                              "last_newton_norms": [[float(x) for x in h[0]] for h in last]}}
+        emit(line)
+    fs.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -425,11 +475,16 @@ def main():
     ap.add_argument("--mode", default="gather", choices=["gather", "atomic", "colored", "auto"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ref-port", action="store_true", help="--impl reference: force the host-core oracle port")
+    ap.add_argument("--timesteps", type=int, default=0,
+                    help="run BASELINE configs[4] instead: this many time steps with Newton reassembly (see run_timesteps)")
     ap.add_argument("--fixed-m", action="store_true", help="N > 1: keep --m (strong scaling) instead of growing the mesh with N")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     protect_stdout()
+    if args.timesteps > 0:
+        from dedflow_b200 import boxmesh as _bm
+        args._initial_state = _bm.state_initial(_bm.make_box(args.m))
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

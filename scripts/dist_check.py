@@ -62,6 +62,31 @@ if rank == 0:
     ok = eF <= 1e-12 and ex <= 1e-10 and eh <= 1e-10 and it == ito and ghost_err <= 1e-12 * np.abs(xo).max()
     print(f"dist_check world={world} m={args.m}: iters {it} (oracle {ito})  F rel {eF:.2e}  dx rel {ex:.2e}  hist rel {eh:.2e}  "
           f"ghost {ghost_err:.2e}  -> {'OK' if ok else 'FAIL'}", flush=True)
+# ---- two time steps (predictor, Newton with reassembly, corrector) against the single-domain oracle driver ----
+wg0 = [a.copy() for a in boxmesh.state_initial(mesh)]
+d = [torch.from_numpy(lm.localize(a)).cuda() for a in wg0]
+ok2 = True
+ctx = None
+if rank == 0:
+    ctx = O.driver_setup(mesh)
+for step in range(2):
+    gh = fs.time_step(*d)
+    gathered = []
+    for v in d:
+        g = np.zeros(6 * Ng)
+        lm.scatter_owned(v.cpu().numpy(), g)
+        t = torch.from_numpy(g).cuda()
+        dist.all_reduce(t)
+        gathered.append(t.cpu().numpy())
+    if rank == 0:
+        oh = O.time_step(ctx, *wg0)
+        same = len(gh) == len(oh) and all(gi == oi for (_, gi), (_, oi) in zip(gh, oh))
+        en = max(float(np.abs(gr - orr).max()) for (gr, _), (orr, _) in zip(gh, oh)) / oh[0][0].max() if same else float("inf")
+        es = max(float(np.abs(g[:4 * Ng] - w[:4 * Ng]).max() / max(np.abs(w[:4 * Ng]).max(), 1e-12)) for g, w in zip(gathered, wg0))
+        ok2 = ok2 and same and en <= 1e-8 and es <= 1e-8
+        print(f"dist_check time step {step + 1}: Newton its {len(gh) - 1} (oracle {len(oh) - 1})  norms rel {en:.2e}  state rel {es:.2e}  "
+              f"-> {'OK' if ok2 else 'FAIL'}", flush=True)
+ok = ok and ok2
 fs.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -205,6 +205,30 @@ def test_kernel_element_math_matches_oracle(oracle, probe):
             assert np.abs(fJ - gJ[..., :4, :4]).max() <= 1e-12 * np.abs(gJ).max()
 
 
+def test_oracle_driver_time_step(oracle):
+    """numpy restatement of main.c's driver (SolveFlowSystem + one pass of the time loop): slot rules of the alpha-level
+    states, Newton residuals decrease, phi/T residual blocks are discarded, pressure slot of wgold is never touched."""
+    mesh = boxmesh.make_box(4)
+    N = mesh.num_node
+    rng = np.random.default_rng(0)
+    wgold, dwgold, dwg = (rng.standard_normal(6 * N) for _ in range(3))
+    wga, dwga = oracle.alpha_states(N, wgold, dwgold, dwg)
+    assert np.all(wga[3 * N:4 * N] == 0) and np.array_equal(dwga[3 * N:4 * N], dwg[3 * N:4 * N])
+    am, af = oracle.K_ALPHAM, oracle.K_ALPHAF
+    assert np.allclose(dwga[:3 * N], (1 - am) * dwgold[:3 * N] + am * dwg[:3 * N], rtol=1e-14)
+    assert np.allclose(wga[4 * N:], wgold[4 * N:] + oracle.K_DT * af * ((1 - oracle.K_GAMMA) * dwgold[4 * N:] + oracle.K_GAMMA * dwg[4 * N:]), rtol=1e-13)
+    ctx = oracle.driver_setup(mesh)
+    state = [a.copy() for a in boxmesh.state_initial(mesh)]
+    p_before = state[0][3 * N:4 * N].copy()
+    hist = oracle.time_step(ctx, *state)
+    norms = np.array([h[0] for h in hist])
+    assert 2 <= len(hist) <= 5 and all(h[1] % 20 == 0 and h[1] > 0 for h in hist[1:])
+    assert norms[-1, 0] < 1e-2 * norms[0, 0]                       # Newton converges on the momentum block
+    assert np.all(norms[:, 2:] == 0)                               # phi / T residuals are zeroed (main.c:63-66)
+    assert np.array_equal(state[0][3 * N:4 * N], p_before)         # the corrector skips the pressure slot of wgold
+    assert np.array_equal(state[1], state[2])                      # dwgold = dwg
+
+
 def test_abi_library_exports_every_declared_symbol():
     """libdedflow_b200.so loads on a GPU-less host and exports exactly what include/*.h declares."""
     from dedflow_b200 import _build, lib
