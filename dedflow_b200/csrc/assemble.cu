@@ -71,7 +71,7 @@ __device__ __forceinline__ void scatter_block(f64* __restrict__ A00, f64* __rest
 // ------------------------------------------------------------------------------------------------------------
 // F: one thread per element
 // ------------------------------------------------------------------------------------------------------------
-template <int MODE>  // 0: write scratch[e*24..], 1: atomic scatter, 2: plain scatter of a color batch
+template <int MODE>  // 0: write scratch[e*24..] (64-byte padded corner slots measured slower), 1: atomic scatter, 2: plain scatter of a color batch
 __global__ void __launch_bounds__(128, 3) k_elemF(int n, const int* __restrict__ elem_ids, int N, const int* __restrict__ ien,
                                                const f64* __restrict__ xg, const f64* __restrict__ wg,
                                                const f64* __restrict__ dwg, f64* __restrict__ out) {
@@ -291,207 +291,6 @@ __global__ void __launch_bounds__(128) k_rowJ(int N, const int* __restrict__ ien
         p01[(size_t)2 * len] += acc[sg][3];
         p11[0] += acc[sg][7];
       }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// J, two-phase GATHER (DFB_J_TWOPHASE=1; measured slower than the fused kernel, kept for comparison).  Phase 1 evaluates the per-element part of the hoisted Jacobian ONCE per element
-// (geometry, c = u(q).gradN, tau, the q-sums) and parks it in a 44-double record; phase 2 is the row gather above, but a
-// lane only loads its record (L2-resident: the records of a row's elements were written moments ago by neighbouring
-// rows' sweep) and forms its four 4x4 blocks (~55 fp64 instructions each).  This removes the 4x redundant element
-// prologue of the fused variant -- the fp64 pipe, not HBM, bounds this kernel (ncu: profiles/r01_*).
-// Record: [0,12) sh[a][d] | [12] w | [13,29) c[q][a] | [29,33) tauM[q] | [33,37) P[a] | [37,41) R[a] | [41] sTM | [42] sTC | pad
-// ------------------------------------------------------------------------------------------------------------
-constexpr int JREC = 44;
-constexpr int JREC_S = 45;   // shared-memory stride of a record (odd number of doubles)
-constexpr size_t ROWJ2_SMEM = sizeof(f64) * 4 * (32 * JREC_S + 16 * 32) + sizeof(u32) * 4 * 64;
-
-__global__ void __launch_bounds__(128) k_jprep(int E, const int* __restrict__ ien, const f64* __restrict__ xg,
-                                               const f64* __restrict__ wg, f64* __restrict__ rec) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  int nodes[4];
-  load_nodes(ien, e, nodes);
-  f64 x[4][3], u[4][3];
-  load_xyz(xg, nodes, x);
-  load_xyz(wg, nodes, u);
-  Geom g;
-  geometry(x, g);
-  JPrep p;
-  jac_prep(g, u, p);
-  double2* dst = reinterpret_cast<double2*>(rec + (size_t)e * JREC);
-  dst[0] = make_double2(g.sh[0][0], g.sh[0][1]); dst[1] = make_double2(g.sh[0][2], g.sh[1][0]);
-  dst[2] = make_double2(g.sh[1][1], g.sh[1][2]); dst[3] = make_double2(g.sh[2][0], g.sh[2][1]);
-  dst[4] = make_double2(g.sh[2][2], g.sh[3][0]); dst[5] = make_double2(g.sh[3][1], g.sh[3][2]);
-  dst[6] = make_double2(p.w, p.c[0][0]);
-  dst[7] = make_double2(p.c[0][1], p.c[0][2]); dst[8] = make_double2(p.c[0][3], p.c[1][0]);
-  dst[9] = make_double2(p.c[1][1], p.c[1][2]); dst[10] = make_double2(p.c[1][3], p.c[2][0]);
-  dst[11] = make_double2(p.c[2][1], p.c[2][2]); dst[12] = make_double2(p.c[2][3], p.c[3][0]);
-  dst[13] = make_double2(p.c[3][1], p.c[3][2]); dst[14] = make_double2(p.c[3][3], p.tM[0]);
-  dst[15] = make_double2(p.tM[1], p.tM[2]); dst[16] = make_double2(p.tM[3], p.P[0]);
-  dst[17] = make_double2(p.P[1], p.P[2]); dst[18] = make_double2(p.P[3], p.R[0]);
-  dst[19] = make_double2(p.R[1], p.R[2]); dst[20] = make_double2(p.R[3], p.sTM);
-  dst[21] = make_double2(p.sTC, 0.0);
-}
-
-// block (a,b) from a record; a is a run-time value (dynamic indexing into GLOBAL memory is free), b is static
-struct RecRow {
-  const f64* r;
-  f64 ga[3], cqa[4], tqa[4], Pa, w, sTM, sTC, tM[4];
-  int a;
-};
-
-__device__ __forceinline__ void rec_row(const f64* __restrict__ r, int a, RecRow& R) {
-  R.r = r; R.a = a;
-  R.w = r[12]; R.sTM = r[41]; R.sTC = r[42];
-#pragma unroll
-  for (int q = 0; q < 4; q++) R.tM[q] = r[29 + q];
-#pragma unroll
-  for (int d = 0; d < 3; d++) R.ga[d] = r[a * 3 + d];
-#pragma unroll
-  for (int q = 0; q < 4; q++) { R.cqa[q] = r[13 + q * 4 + a]; R.tqa[q] = R.tM[q] * R.cqa[q]; }
-  R.Pa = r[33 + a];
-}
-
-__device__ __forceinline__ void rec_block(const RecRow& R, int b, f64 blk[16]) {
-  const f64* r = R.r;
-  const f64 gb[3] = {r[b * 3], r[b * 3 + 1], r[b * 3 + 2]};
-  const f64 cqb[4] = {r[13 + b], r[17 + b], r[21 + b], r[25 + b]};
-  const f64 cab = r[13 + R.a * 4 + b], Pb = r[33 + b], Rb = r[37 + b];
-  const f64* ga = R.ga;
-  const f64 eK = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
-  const f64 mab = (R.a == b) ? (SA * SA + 3.0 * SB * SB) : (2.0 * SA * SB + 2.0 * SB * SB);
-  const f64 stc = R.tqa[0] * cqb[0] + R.tqa[1] * cqb[1] + R.tqa[2] * cqb[2] + R.tqa[3] * cqb[3];
-  const f64 T = R.w * (FACT1 * RHO * mab + FACT1 * RHO * RHO * (SB * R.Pa + SD * R.tqa[b]) +
-                       FACT2 * RHO * (SB * Rb + SD * cab) + FACT2 * RHO * RHO * stc + 4.0 * FACT2 * MU * eK);
-  const f64 k1 = 4.0 * R.w * FACT2 * MU, k2 = R.w * FACT2 * RHO * R.sTC;
-#pragma unroll
-  for (int ii = 0; ii < 3; ii++)
-#pragma unroll
-    for (int jj = 0; jj < 3; jj++) blk[ii * 4 + jj] = k1 * ga[jj] * gb[ii] + k2 * ga[ii] * gb[jj] + (ii == jj ? T : 0.0);
-  const f64 k3 = R.w * SN, k4 = RHO * R.w * R.Pa;
-  const f64 k5 = R.w * RHO * (FACT1 * (SB * R.sTM + SD * R.tM[b]) + FACT2 * Pb);
-  const f64 k6 = FACT2 * R.w * SN;
-#pragma unroll
-  for (int ii = 0; ii < 3; ii++) {
-    blk[ii * 4 + 3] = -k3 * ga[ii] + k4 * gb[ii];
-    blk[12 + ii] = k5 * ga[ii] + k6 * gb[ii];
-  }
-  blk[15] = R.w * R.sTM * eK;
-}
-
-template <int NSG>
-__global__ void __launch_bounds__(128) k_rowJ2(int N, const f64* __restrict__ rec, const int* __restrict__ row_ptr,
-                                               const int* __restrict__ v2c_ptr, const int* __restrict__ v2c,
-                                               const u32* __restrict__ slot32, f64* __restrict__ A00,
-                                               f64* __restrict__ A01, f64* __restrict__ A10, f64* __restrict__ A11,
-                                               int overwrite) {
-  // per warp: 32 element records (stride 45 doubles: odd => conflict-free per-lane reads), 32 staged blocks, slot masks
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 4 + warp;
-  if (row >= N) return;
-  f64* recs = reinterpret_cast<f64*>(smem_raw) + (size_t)warp * (32 * JREC_S + 16 * 32);
-  f64* stage = recs + 32 * JREC_S;
-  u32* smask = reinterpret_cast<u32*>(reinterpret_cast<f64*>(smem_raw) + (size_t)4 * (32 * JREC_S + 16 * 32)) + warp * 64;
-  smask[lane] = 0u;
-  smask[lane + 32] = 0u;
-  const int cs = v2c_ptr[row], ce = v2c_ptr[row + 1];
-  const int start = row_ptr[row], len = row_ptr[row + 1] - start;
-  f64 acc[NSG][8];
-#pragma unroll
-  for (int sg = 0; sg < NSG; sg++)
-#pragma unroll
-    for (int v = 0; v < 8; v++) acc[sg][v] = 0.0;
-  const int myslot = lane >> 1, half = lane & 1;
-  __syncwarp();
-  for (int base = cs; base < ce; base += 32) {
-    const int nact = min(32, ce - base);
-    const bool active = lane < nact;
-    int corner = 0;
-    u32 slots = 0xffffffffu;
-    if (active) {
-      corner = __ldg(v2c + base + lane);
-      slots = __ldg(slot32 + corner);
-    }
-    // cooperative, coalesced staging of the pass's element records: the warp copies one 352-byte record per step
-    // (two 8-byte loads per lane) instead of every lane gathering its own record line by line
-#pragma unroll 4
-    for (int r = 0; r < nact; r++) {
-      const int e = __shfl_sync(FULL, corner, r) >> 2;
-      const f64* src = rec + (size_t)e * JREC;
-      const f64 v0 = __ldg(src + lane);
-      f64 v1 = 0.0;
-      if (lane < JREC - 32) v1 = __ldg(src + 32 + lane);
-      recs[r * JREC_S + lane] = v0;
-      if (lane < JREC - 32) recs[r * JREC_S + 32 + lane] = v1;
-    }
-    __syncwarp();
-    RecRow R;
-    if (active) rec_row(recs + lane * JREC_S, corner & 3, R);
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      f64 blk[16];
-      if (active) rec_block(R, b, blk);
-      const u32 tgt = active ? ((slots >> (8 * b)) & 0xffu) : 255u;
-      const u32 peers = __match_any_sync(FULL, tgt);
-      const bool leader = active && ((__ffs(peers) - 1) == lane);
-      if (leader) smask[tgt] = peers;
-      if (active) {
-#pragma unroll
-        for (int v = 0; v < 16; v++) stage[v * 32 + lane] = blk[v];
-      }
-      __syncwarp();
-#pragma unroll
-      for (int sg = 0; sg < NSG; sg++) {
-        const int s = sg * 16 + myslot;
-        if (s < len) {
-          u32 m = smask[s];
-          while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-#pragma unroll
-            for (int v = 0; v < 8; v++) acc[sg][v] += stage[(half * 8 + v) * 32 + src];
-          }
-        }
-      }
-      __syncwarp();
-      if (leader) smask[tgt] = 0u;
-      __syncwarp();
-    }
-  }
-#pragma unroll
-  for (int sg = 0; sg < NSG; sg++) {
-    const int s = sg * 16 + myslot;
-    if (s >= len) continue;
-    const size_t st = (size_t)start;
-    f64* p00 = A00 + st * 9 + (size_t)s * 3;
-    f64* p01 = A01 + st * 3 + s;
-    f64* p10 = A10 + st * 3 + (size_t)s * 3;
-    f64* p11 = A11 + st + s;
-    if (half == 0) {
-#pragma unroll
-      for (int ii = 0; ii < 2; ii++) {
-#pragma unroll
-        for (int jj = 0; jj < 3; jj++) {
-          f64* q = p00 + (size_t)ii * len * 3 + jj;
-          *q = overwrite ? acc[sg][ii * 4 + jj] : *q + acc[sg][ii * 4 + jj];
-        }
-        f64* q = p01 + (size_t)ii * len;
-        *q = overwrite ? acc[sg][ii * 4 + 3] : *q + acc[sg][ii * 4 + 3];
-      }
-    } else {
-#pragma unroll
-      for (int jj = 0; jj < 3; jj++) {
-        f64* q = p00 + (size_t)2 * len * 3 + jj;
-        *q = overwrite ? acc[sg][jj] : *q + acc[sg][jj];
-        f64* q2 = p10 + jj;
-        *q2 = overwrite ? acc[sg][4 + jj] : *q2 + acc[sg][4 + jj];
-      }
-      f64* q = p01 + (size_t)2 * len;
-      *q = overwrite ? acc[sg][3] : *q + acc[sg][3];
-      *p11 = overwrite ? acc[sg][7] : *p11 + acc[sg][7];
     }
   }
 }
@@ -781,13 +580,11 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
   if (doJ) {
     if (mode == DFB_MODE_GATHER) {
       const int grid = ceil_div(P->n_rows, 4);
-      // variants of the atomic-free assembly: pull (default), fused row gather (DFB_J_VARIANT=fused), two-phase row
-      // gather (DFB_J_VARIANT=twophase); measured on B200 at 1M tets: see DESIGN.md section 3
+      // variants of the atomic-free assembly: pull (default, 0.75 ms at 1M tets on B200) and the fused row gather
+      // (DFB_J_VARIANT=fused, 1.07 ms); see DESIGN.md section 3
       static const int variant = [] {
         const char* e = getenv("DFB_J_VARIANT");
-        if (e && !strcmp(e, "fused")) return 1;
-        if (e && !strcmp(e, "twophase")) return 2;
-        return 0;
+        return (e && !strcmp(e, "fused")) ? 1 : 0;
       }();
       if (variant == 0) {
         DFB_CHECK(build_pull(P, st));
@@ -813,34 +610,13 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
         else
           k_pullJ<0><<<ceil_div(ni, 128), 128, 0, st>>>(ni, P->item_meta, P->item_ptr, P->contrib, P->prec, P->row_ptr, d_A00, d_A01, d_A10, d_A11);
         DFB_LAUNCH_CHECK();
-      } else if (variant == 1) {
+      } else {
         if (P->max_row_len <= 16)
           k_rowJ<1><<<grid, 128, 0, st>>>(P->n_rows, P->ien, d_xg, d_wg, P->row_ptr, P->v2c_ptr, P->v2c, slot32, d_A00, d_A01, d_A10, d_A11, overwrite);
         else if (P->max_row_len <= 32)
           k_rowJ<2><<<grid, 128, 0, st>>>(P->n_rows, P->ien, d_xg, d_wg, P->row_ptr, P->v2c_ptr, P->v2c, slot32, d_A00, d_A01, d_A10, d_A11, overwrite);
         else
           k_rowJ<4><<<grid, 128, 0, st>>>(P->n_rows, P->ien, d_xg, d_wg, P->row_ptr, P->v2c_ptr, P->v2c, slot32, d_A00, d_A01, d_A10, d_A11, overwrite);
-        DFB_LAUNCH_CHECK();
-      } else {
-        if (!P->jrec) {
-          P->jrec_bytes = sizeof(f64) * JREC * (size_t)E;
-          DFB_CUDA(cudaMalloc(&P->jrec, P->jrec_bytes));
-        }
-        k_jprep<<<ceil_div(E, 128), 128, 0, st>>>(E, P->ien, d_xg, d_wg, P->jrec);
-        DFB_LAUNCH_CHECK();
-        static bool attr_set = false;
-        if (!attr_set) {
-          DFB_CUDA(cudaFuncSetAttribute(k_rowJ2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWJ2_SMEM));
-          DFB_CUDA(cudaFuncSetAttribute(k_rowJ2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWJ2_SMEM));
-          DFB_CUDA(cudaFuncSetAttribute(k_rowJ2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWJ2_SMEM));
-          attr_set = true;
-        }
-        if (P->max_row_len <= 16)
-          k_rowJ2<1><<<grid, 128, ROWJ2_SMEM, st>>>(P->n_rows, P->jrec, P->row_ptr, P->v2c_ptr, P->v2c, slot32, d_A00, d_A01, d_A10, d_A11, overwrite);
-        else if (P->max_row_len <= 32)
-          k_rowJ2<2><<<grid, 128, ROWJ2_SMEM, st>>>(P->n_rows, P->jrec, P->row_ptr, P->v2c_ptr, P->v2c, slot32, d_A00, d_A01, d_A10, d_A11, overwrite);
-        else
-          k_rowJ2<4><<<grid, 128, ROWJ2_SMEM, st>>>(P->n_rows, P->jrec, P->row_ptr, P->v2c_ptr, P->v2c, slot32, d_A00, d_A01, d_A10, d_A11, overwrite);
         DFB_LAUNCH_CHECK();
       }
     } else if (mode == DFB_MODE_ATOMIC) {

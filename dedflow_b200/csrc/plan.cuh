@@ -22,9 +22,6 @@ struct dfb_plan {
   // lazily allocated element-residual scratch for the deterministic F gather (24 doubles per element)
   mutable f64* elemF = nullptr;
   mutable size_t elemF_bytes = 0;
-  // lazily allocated per-element Jacobian records of the two-phase J gather (44 doubles per element)
-  mutable f64* jrec = nullptr;
-  mutable size_t jrec_bytes = 0;
   // lazily built work lists of the PULL Jacobian assembly (setup.cu build_pull): one work item per off-diagonal nodal
   // nonzero plus four "virtual" items per diagonal entry (its contributions dealt round-robin), rows padded to multiples
   // of four items so that the four diagonal items of a row sit in one aligned lane quad.

@@ -431,14 +431,14 @@ int dfb_plan_set_rows(dfb_plan* p, int n_rows) {
 
 void dfb_plan_destroy(dfb_plan* p) {
   if (!p) return;
-  cudaFree(p->v2c_ptr); cudaFree(p->v2c); cudaFree(p->slot); cudaFree(p->elemF); cudaFree(p->jrec);
+  cudaFree(p->v2c_ptr); cudaFree(p->v2c); cudaFree(p->slot); cudaFree(p->elemF);
   cudaFree(p->row_item); cudaFree(p->item_meta); cudaFree(p->item_ptr); cudaFree(p->contrib); cudaFree(p->prec);
   delete p;
 }
 
 size_t dfb_plan_bytes(const dfb_plan* p) {
   if (!p) return 0;
-  return sizeof(int) * ((size_t)p->N + 1) + sizeof(int) * (size_t)p->E * 4 + (size_t)p->E * 16 + p->elemF_bytes + p->jrec_bytes + p->pull_bytes;
+  return sizeof(int) * ((size_t)p->N + 1) + sizeof(int) * (size_t)p->E * 4 + (size_t)p->E * 16 + p->elemF_bytes + p->pull_bytes;
 }
 
 }  // extern "C"
