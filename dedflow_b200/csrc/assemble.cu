@@ -21,6 +21,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "elem_math.cuh"
 #include "plan.cuh"
@@ -307,6 +309,7 @@ __global__ void __launch_bounds__(128) k_rowJ(int N, const int* __restrict__ ien
 //                   tail at [40,48): w sTM | sTC pad | tM0 tM1 | tM2 tM3
 // ------------------------------------------------------------------------------------------------------------
 constexpr int PREC = 48;
+constexpr int PULL_SREC = 25;   // shared-memory stride of a staged record in 16-byte chunks (odd: bank spreading)
 
 // The 32 records of a warp are contiguous in global memory (32 x 384 B): each lane parks its record in shared memory
 // (stride 49 doubles: conflict-free), then the warp streams the 12 KB out with fully coalesced 8-byte stores.
@@ -349,58 +352,44 @@ __global__ void __launch_bounds__(128) k_jprep2(int E, const int* __restrict__ i
   }
 }
 
+// one (element, a, b) contribution from the two corner sub-records and the element tail (record layout above), added to acc
+__device__ __forceinline__ void pull_block(const double2 a0, const double2 a1, const double2 a2, const double2 a3, const double2 b0,
+                                           const double2 b1, const double2 b2, const double2 b3, const double2 b4, const double2 t0,
+                                           const double2 t1, const double2 t2, const double2 t3, int a, int b, f64 acc[16]) {
+  const f64 ga[3] = {a0.x, a0.y, a1.x}, gb[3] = {b0.x, b0.y, b1.x};
+  const f64 Pa = a1.y, Pb = b1.y, Rb = b4.x;
+  const f64 w = t0.x, sTM = t0.y, sTC = t1.x;
+  const f64 tMb = sel4(b, t2.x, t2.y, t3.x, t3.y);
+  const f64 cab = sel4(a, b2.x, b2.y, b3.x, b3.y);          // c[q=a][b]
+  const f64 cba = sel4(b, a2.x, a2.y, a3.x, a3.y);          // c[q=b][a]
+  const f64 stc = (t2.x * a2.x) * b2.x + (t2.y * a2.y) * b2.y + (t3.x * a3.x) * b3.x + (t3.y * a3.y) * b3.y;
+  const f64 eK = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
+  const f64 mab = (a == b) ? (SA * SA + 3.0 * SB * SB) : (2.0 * SA * SB + 2.0 * SB * SB);
+  const f64 T = w * (FACT1 * RHO * mab + FACT1 * RHO * RHO * (SB * Pa + SD * (tMb * cba)) + FACT2 * RHO * (SB * Rb + SD * cab) +
+                     FACT2 * RHO * RHO * stc + 4.0 * FACT2 * MU * eK);
+  const f64 k1 = 4.0 * w * FACT2 * MU, k2 = w * FACT2 * RHO * sTC;
+#pragma unroll
+  for (int ii = 0; ii < 3; ii++)
+#pragma unroll
+    for (int jj = 0; jj < 3; jj++) acc[ii * 4 + jj] += k1 * ga[jj] * gb[ii] + k2 * ga[ii] * gb[jj] + (ii == jj ? T : 0.0);
+  const f64 k3 = w * SN, k4 = RHO * w * Pa;
+  const f64 k5 = w * RHO * (FACT1 * (SB * sTM + SD * tMb) + FACT2 * Pb);
+  const f64 k6 = FACT2 * w * SN;
+#pragma unroll
+  for (int ii = 0; ii < 3; ii++) {
+    acc[ii * 4 + 3] += -k3 * ga[ii] + k4 * gb[ii];
+    acc[12 + ii] += k5 * ga[ii] + k6 * gb[ii];
+  }
+  acc[15] += w * sTM * eK;
+}
+
+// Fold the four diagonal items of a row (an aligned lane quad) -- after two exchange steps lane q of the quad holds block
+// row q -- and write the item's values.  Executed by every lane of the warp (no divergence before the shuffles); only
+// diagonal items use the folded result.
 template <int OVERWRITE>
-__global__ void __launch_bounds__(128) k_pullJ(int n_items, const uint2* __restrict__ item_meta, const int* __restrict__ item_ptr,
-                                               const u32* __restrict__ contrib, const f64* __restrict__ rec,
-                                               const int* __restrict__ row_ptr, f64* __restrict__ A00, f64* __restrict__ A01,
-                                               f64* __restrict__ A10, f64* __restrict__ A11) {
-  const int item = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = item < n_items;
-  uint2 meta = make_uint2(0xffffffffu, 0u);
-  int cs = 0, ce = 0;
-  if (valid) {
-    meta = item_meta[item];
-    cs = __ldg(item_ptr + item);
-    ce = __ldg(item_ptr + item + 1);
-  }
-  f64 acc[16];
-#pragma unroll
-  for (int v = 0; v < 16; v++) acc[v] = 0.0;
-  for (int idx = cs; idx < ce; idx++) {
-    const u32 cid = __ldg(contrib + idx);
-    const int a = (int)((cid >> 2) & 3u), b = (int)(cid & 3u);
-    const double2* R = reinterpret_cast<const double2*>(rec + (size_t)(cid >> 4) * PREC);
-    const double2 a0 = R[a * 5], a1 = R[a * 5 + 1], a2 = R[a * 5 + 2], a3 = R[a * 5 + 3];
-    const double2 b0 = R[b * 5], b1 = R[b * 5 + 1], b2 = R[b * 5 + 2], b3 = R[b * 5 + 3], b4 = R[b * 5 + 4];
-    const double2 t0 = R[20], t1 = R[21], t2 = R[22], t3 = R[23];
-    const f64 ga[3] = {a0.x, a0.y, a1.x}, gb[3] = {b0.x, b0.y, b1.x};
-    const f64 Pa = a1.y, Pb = b1.y, Rb = b4.x;
-    const f64 w = t0.x, sTM = t0.y, sTC = t1.x;
-    const f64 tMb = sel4(b, t2.x, t2.y, t3.x, t3.y);
-    const f64 cab = sel4(a, b2.x, b2.y, b3.x, b3.y);          // c[q=a][b]
-    const f64 cba = sel4(b, a2.x, a2.y, a3.x, a3.y);          // c[q=b][a]
-    const f64 stc = (t2.x * a2.x) * b2.x + (t2.y * a2.y) * b2.y + (t3.x * a3.x) * b3.x + (t3.y * a3.y) * b3.y;
-    const f64 eK = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
-    const f64 mab = (a == b) ? (SA * SA + 3.0 * SB * SB) : (2.0 * SA * SB + 2.0 * SB * SB);
-    const f64 T = w * (FACT1 * RHO * mab + FACT1 * RHO * RHO * (SB * Pa + SD * (tMb * cba)) + FACT2 * RHO * (SB * Rb + SD * cab) +
-                       FACT2 * RHO * RHO * stc + 4.0 * FACT2 * MU * eK);
-    const f64 k1 = 4.0 * w * FACT2 * MU, k2 = w * FACT2 * RHO * sTC;
-#pragma unroll
-    for (int ii = 0; ii < 3; ii++)
-#pragma unroll
-      for (int jj = 0; jj < 3; jj++) acc[ii * 4 + jj] += k1 * ga[jj] * gb[ii] + k2 * ga[ii] * gb[jj] + (ii == jj ? T : 0.0);
-    const f64 k3 = w * SN, k4 = RHO * w * Pa;
-    const f64 k5 = w * RHO * (FACT1 * (SB * sTM + SD * tMb) + FACT2 * Pb);
-    const f64 k6 = FACT2 * w * SN;
-#pragma unroll
-    for (int ii = 0; ii < 3; ii++) {
-      acc[ii * 4 + 3] += -k3 * ga[ii] + k4 * gb[ii];
-      acc[12 + ii] += k5 * ga[ii] + k6 * gb[ii];
-    }
-    acc[15] += w * sTM * eK;
-  }
-  // fold the four diagonal items of a row (an aligned lane quad): after two exchange steps lane q of the quad holds
-  // block row q.  Executed by every lane (no divergence); only diagonal items use the result.
+__device__ __forceinline__ void pull_finish(const f64 acc[16], bool valid, uint2 meta, const int* __restrict__ row_ptr,
+                                            f64* __restrict__ A00, f64* __restrict__ A01, f64* __restrict__ A10,
+                                            f64* __restrict__ A11) {
   const int lane = threadIdx.x & 31;
   const bool hi = lane & 2, odd = lane & 1;
   f64 t[2][4], u[4];
@@ -447,6 +436,98 @@ __global__ void __launch_bounds__(128) k_pullJ(int n_items, const uint2* __restr
     }
     if (OVERWRITE) { p10[0] = acc[12]; p10[1] = acc[13]; p10[2] = acc[14]; *p11 = acc[15]; }
     else { p10[0] += acc[12]; p10[1] += acc[13]; p10[2] += acc[14]; *p11 += acc[15]; }
+  }
+}
+
+template <int OVERWRITE>
+__global__ void __launch_bounds__(128) k_pullJ(int n_items, const uint2* __restrict__ item_meta, const int* __restrict__ item_ptr,
+                                               const u32* __restrict__ contrib, const f64* __restrict__ rec,
+                                               const int* __restrict__ row_ptr, f64* __restrict__ A00, f64* __restrict__ A01,
+                                               f64* __restrict__ A10, f64* __restrict__ A11) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = item < n_items;
+  uint2 meta = make_uint2(0xffffffffu, 0u);
+  int cs = 0, ce = 0;
+  if (valid) {
+    meta = item_meta[item];
+    cs = __ldg(item_ptr + item);
+    ce = __ldg(item_ptr + item + 1);
+  }
+  f64 acc[16];
+#pragma unroll
+  for (int v = 0; v < 16; v++) acc[v] = 0.0;
+  for (int idx = cs; idx < ce; idx++) {
+    const u32 cid = __ldg(contrib + idx);
+    const int a = (int)((cid >> 2) & 3u), b = (int)(cid & 3u);
+    const double2* R = reinterpret_cast<const double2*>(rec + (size_t)(cid >> 4) * PREC);
+    const double2 a0 = R[a * 5], a1 = R[a * 5 + 1], a2 = R[a * 5 + 2], a3 = R[a * 5 + 3];
+    const double2 b0 = R[b * 5], b1 = R[b * 5 + 1], b2 = R[b * 5 + 2], b3 = R[b * 5 + 3], b4 = R[b * 5 + 4];
+    const double2 t0 = R[20], t1 = R[21], t2 = R[22], t3 = R[23];
+    pull_block(a0, a1, a2, a3, b0, b1, b2, b3, b4, t0, t1, t2, t3, a, b, acc);
+  }
+  pull_finish<OVERWRITE>(acc, valid, meta, row_ptr, A00, A01, A10, A11);
+}
+
+// STAGED pull (default): one CTA per group of PULL_ROWS rows.  The group's distinct element records (plan: cta_elems) are
+// first copied into shared memory with coalesced 16-byte loads -- a record is 24 16-byte chunks at a stride of 25, so that
+// lanes reading the same chunk of different records spread over the banks -- and the work items of the group then pull their contributions from there (the plain k_pullJ above is L1-tag bound: every lane of a load touches
+// a different record line).  Groups whose records do not fit (contrib16 == 0xffff) read global memory like k_pullJ.
+template <int OVERWRITE>
+__global__ void __launch_bounds__(128) k_pullJ_staged(int N, int n_rows, const int* __restrict__ row_item,
+                                                      const uint2* __restrict__ item_meta, const int* __restrict__ item_ptr,
+                                                      const u32* __restrict__ contrib, const unsigned short* __restrict__ contrib16,
+                                                      const int* __restrict__ cta_elem_ptr, const int* __restrict__ cta_elems,
+                                                      const f64* __restrict__ rec, const int* __restrict__ row_ptr,
+                                                      f64* __restrict__ A00, f64* __restrict__ A01, f64* __restrict__ A10,
+                                                      f64* __restrict__ A11) {
+  extern __shared__ __align__(16) unsigned char pull_smem[];
+  double2* srec = reinterpret_cast<double2*>(pull_smem);
+  const int r0 = blockIdx.x * PULL_ROWS, r1 = min(N, r0 + PULL_ROWS);
+  const int it0 = __ldg(row_item + r0), it1 = __ldg(row_item + r1);
+  const int e0 = __ldg(cta_elem_ptr + blockIdx.x), ne = __ldg(cta_elem_ptr + blockIdx.x + 1) - e0;
+  const bool staged = ne > 0 && ne <= PULL_MAX_STAGED;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (staged) {
+    for (int r = warp; r < ne; r += 4) {
+      const int e = __ldg(cta_elems + e0 + r);
+      if (lane < 24) srec[r * PULL_SREC + lane] = __ldg(reinterpret_cast<const double2*>(rec + (size_t)e * PREC) + lane);
+    }
+  }
+  __syncthreads();
+  for (int base = it0; base < it1; base += 128) {   // block-uniform trip count (the fold below shuffles)
+    const int item = base + threadIdx.x;
+    const bool valid = item < it1;
+    uint2 meta = make_uint2(0xffffffffu, 0u);
+    int cs = 0, ce = 0;
+    if (valid) {
+      meta = item_meta[item];
+      cs = __ldg(item_ptr + item);
+      ce = __ldg(item_ptr + item + 1);
+    }
+    f64 acc[16];
+#pragma unroll
+    for (int v = 0; v < 16; v++) acc[v] = 0.0;
+    if (staged) {
+      unsigned nxt = cs < ce ? contrib16[cs] : 0u;   // one-ahead prefetch: the list load is off the LDS -> FP64 critical path
+      for (int idx = cs; idx < ce; idx++) {
+        const unsigned c16 = nxt;
+        if (idx + 1 < ce) nxt = contrib16[idx + 1];
+        const int li = (int)(c16 >> 4), a = (int)((c16 >> 2) & 3u), b = (int)(c16 & 3u);
+        const double2* R = srec + li * PULL_SREC;
+        const double2* Ra = R + a * 5;
+        const double2* Rb = R + b * 5;
+        pull_block(Ra[0], Ra[1], Ra[2], Ra[3], Rb[0], Rb[1], Rb[2], Rb[3], Rb[4], R[20], R[21], R[22], R[23], a, b, acc);
+      }
+    } else {
+      for (int idx = cs; idx < ce; idx++) {
+        const u32 cid = __ldg(contrib + idx);
+        const int a = (int)((cid >> 2) & 3u), b = (int)(cid & 3u);
+        const double2* R = reinterpret_cast<const double2*>(rec + (size_t)(cid >> 4) * PREC);
+        pull_block(R[a * 5], R[a * 5 + 1], R[a * 5 + 2], R[a * 5 + 3], R[b * 5], R[b * 5 + 1], R[b * 5 + 2], R[b * 5 + 3], R[b * 5 + 4],
+                   R[20], R[21], R[22], R[23], a, b, acc);
+      }
+    }
+    pull_finish<OVERWRITE>(acc, valid && (meta.x == 0xffffffffu || (int)meta.x < n_rows), meta, row_ptr, A00, A01, A10, A11);
   }
 }
 
@@ -604,11 +685,30 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
         }
         k_jprep2<<<ceil_div(E, 128), 128, sizeof(f64) * 128 * PREC_S, st>>>(E, P->ien, d_xg, d_wg, P->prec);
         DFB_LAUNCH_CHECK();
-        const int ni = P->items_active;
-        if (overwrite)
-          k_pullJ<1><<<ceil_div(ni, 128), 128, 0, st>>>(ni, P->item_meta, P->item_ptr, P->contrib, P->prec, P->row_ptr, d_A00, d_A01, d_A10, d_A11);
-        else
-          k_pullJ<0><<<ceil_div(ni, 128), 128, 0, st>>>(ni, P->item_meta, P->item_ptr, P->contrib, P->prec, P->row_ptr, d_A00, d_A01, d_A10, d_A11);
+        static const bool plain_pull = getenv("DFB_J_PULL_PLAIN") != nullptr;   // the unstaged kernel, kept for measurement
+        if (plain_pull) {
+          const int ni = P->items_active;
+          if (overwrite)
+            k_pullJ<1><<<ceil_div(ni, 128), 128, 0, st>>>(ni, P->item_meta, P->item_ptr, P->contrib, P->prec, P->row_ptr, d_A00, d_A01, d_A10, d_A11);
+          else
+            k_pullJ<0><<<ceil_div(ni, 128), 128, 0, st>>>(ni, P->item_meta, P->item_ptr, P->contrib, P->prec, P->row_ptr, d_A00, d_A01, d_A10, d_A11);
+        } else {
+          const int nst = std::min(P->max_cta_elems, PULL_MAX_STAGED);
+          const size_t smem = (size_t)std::max(1, nst) * PULL_SREC * sizeof(double2);
+          static size_t smem_set = 0;
+          if (smem > smem_set) {
+            DFB_CUDA(cudaFuncSetAttribute(k_pullJ_staged<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DFB_CUDA(cudaFuncSetAttribute(k_pullJ_staged<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set = smem;
+          }
+          const int ncta = ceil_div(P->n_rows, PULL_ROWS);
+          if (overwrite)
+            k_pullJ_staged<1><<<ncta, 128, smem, st>>>(N, P->n_rows, P->row_item, P->item_meta, P->item_ptr, P->contrib, P->contrib16,
+                                                       P->cta_elem_ptr, P->cta_elems, P->prec, P->row_ptr, d_A00, d_A01, d_A10, d_A11);
+          else
+            k_pullJ_staged<0><<<ncta, 128, smem, st>>>(N, P->n_rows, P->row_item, P->item_meta, P->item_ptr, P->contrib, P->contrib16,
+                                                       P->cta_elem_ptr, P->cta_elems, P->prec, P->row_ptr, d_A00, d_A01, d_A10, d_A11);
+        }
         DFB_LAUNCH_CHECK();
       } else {
         if (P->max_row_len <= 16)

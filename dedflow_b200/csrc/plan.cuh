@@ -31,11 +31,21 @@ struct dfb_plan {
   mutable int* item_ptr = nullptr;    // [n_items+1] offsets into contrib
   mutable u32* contrib = nullptr;     // [16E] corner*4 + b, ascending inside an item
   mutable f64* prec = nullptr;        // [48E] element records of the pull assembly (assemble.cu k_jprep2)
+  // staged pull: the rows are cut into groups of PULL_ROWS; one CTA per group stages the group's distinct element records in
+  // shared memory.  cta_elems = ascending distinct element ids per group, contrib16 = (local record index << 4 | a << 2 | b)
+  // parallel to contrib (0xffff: group too large for shared memory, the CTA reads the records from global memory instead).
+  mutable int n_cta = 0;
+  mutable int* cta_elem_ptr = nullptr;   // [n_cta+1]
+  mutable int* cta_elems = nullptr;
+  mutable unsigned short* contrib16 = nullptr;   // [16E]
+  mutable int max_cta_elems = 0;
   mutable size_t pull_bytes = 0;
   mutable int items_rows = -1, items_active = 0;  // cache: items of the first n_rows rows
 };
 
 namespace dfb {
+constexpr int PULL_ROWS = 6;         // rows per CTA of the staged pull assembly
+constexpr int PULL_MAX_STAGED = 160; // most element records a CTA stages (160 x 384 B = 60 KB)
 int build_v2c(int N, int E, const int* d_ien, int** d_ptr_out, int** d_v2c_out, cudaStream_t st);
 int build_pull(const dfb_plan* plan, cudaStream_t st);
 }

@@ -9,6 +9,8 @@
 #include <cub/cub.cuh>
 #include <stdarg.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "plan.cuh"
 
@@ -265,6 +267,72 @@ __global__ void k_sort_contrib(int n_items, const int* __restrict__ item_ptr, u3
   }
 }
 
+// distinct elements around the rows [r0, r1): the rows' corner lists are sorted, so this is a small sort + unique.
+// Returns the count (or -1 when the group has more than CAP corners); optionally writes the ascending list.
+constexpr int GROUP_CAP = 768;
+__device__ int group_elements(int r0, int r1, const int* __restrict__ v2c_ptr, const int* __restrict__ v2c, int* __restrict__ out) {
+  const int c0 = v2c_ptr[r0], c1 = v2c_ptr[r1];
+  if (c1 - c0 > GROUP_CAP) return -1;
+  int buf[GROUP_CAP];
+  int n = 0;
+  for (int c = c0; c < c1; c++) {   // insertion sort with de-duplication
+    const int e = v2c[c] >> 2;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (buf[mid] < e) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n && buf[lo] == e) continue;
+    for (int k = n; k > lo; k--) buf[k] = buf[k - 1];
+    buf[lo] = e;
+    n++;
+  }
+  if (out)
+    for (int k = 0; k < n; k++) out[k] = buf[k];
+  return n;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(64) k_group_elems(int N, int n_cta, const int* __restrict__ v2c_ptr, const int* __restrict__ v2c,
+                                                    int* __restrict__ cnt, const int* __restrict__ ptr, int* __restrict__ elems) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_cta) return;
+  const int r0 = g * PULL_ROWS, r1 = min(N, r0 + PULL_ROWS);
+  if (!FILL) {
+    const int n = group_elements(r0, r1, v2c_ptr, v2c, nullptr);
+    cnt[g] = n < 0 ? 0 : n;   // 0 = not staged
+  } else if (ptr[g + 1] > ptr[g]) {
+    group_elements(r0, r1, v2c_ptr, v2c, elems + ptr[g]);
+  }
+}
+
+__global__ void k_contrib16(int n_items, const uint2* __restrict__ meta, const int* __restrict__ item_ptr,
+                            const u32* __restrict__ contrib, const int* __restrict__ cta_elem_ptr,
+                            const int* __restrict__ cta_elems, unsigned short* __restrict__ contrib16) {
+  const int it = blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= n_items) return;
+  const u32 row = meta[it].x;
+  if (row == 0xffffffffu) return;
+  const int g = (int)(row / PULL_ROWS);
+  const int s = cta_elem_ptr[g], n = cta_elem_ptr[g + 1] - s;
+  for (int idx = item_ptr[it]; idx < item_ptr[it + 1]; idx++) {
+    const u32 cid = contrib[idx];
+    unsigned short v = 0xffffu;
+    if (n > 0 && n <= PULL_MAX_STAGED) {
+      const int li = lower_bound_dev(cta_elems + s, n, (int)(cid >> 4));
+      v = (unsigned short)((li << 4) | (cid & 15u));
+    }
+    contrib16[idx] = v;
+  }
+}
+
+__global__ void k_max_int(int n, const int* __restrict__ ptr, int* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int v = i < n ? ptr[i + 1] - ptr[i] : 0;
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
+}
+
 int build_pull(const dfb_plan* p, cudaStream_t st) {
   if (p->item_meta) return DFB_OK;
   if (!p->slot) { set_error("pull assembly needs a plan with a sparsity pattern"); return DFB_ERR_ARG; }
@@ -311,8 +379,40 @@ int build_pull(const dfb_plan* p, cudaStream_t st) {
   DFB_CUDA(cudaMalloc(&p->prec, sizeof(f64) * 48 * (size_t)E));
   DFB_CUDA(cudaStreamSynchronize(st));
   cudaFree(tmp); cudaFree(icnt);
+  // ---- row groups of the staged pull ----
+  const int n_cta = ceil_div(N, PULL_ROWS);
+  p->n_cta = n_cta;
+  int* gcnt = nullptr;
+  DFB_CUDA(cudaMalloc(&gcnt, sizeof(int) * ((size_t)n_cta + 1)));
+  DFB_CUDA(cudaMemsetAsync(gcnt, 0, sizeof(int) * ((size_t)n_cta + 1), st));
+  DFB_CUDA(cudaMalloc(&p->cta_elem_ptr, sizeof(int) * ((size_t)n_cta + 1)));
+  k_group_elems<false><<<ceil_div(n_cta, 64), 64, 0, st>>>(N, n_cta, p->v2c_ptr, p->v2c, gcnt, nullptr, nullptr);
+  DFB_LAUNCH_CHECK();
+  tmp_bytes = 0; tmp = nullptr;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, gcnt, p->cta_elem_ptr, n_cta + 1, st);
+  DFB_CUDA(cudaMalloc(&tmp, tmp_bytes));
+  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, gcnt, p->cta_elem_ptr, n_cta + 1, st);
+  DFB_LAUNCH_CHECK();
+  int total_ge = 0;
+  int* d_mx = nullptr;
+  DFB_CUDA(cudaMalloc(&d_mx, sizeof(int)));
+  DFB_CUDA(cudaMemsetAsync(d_mx, 0, sizeof(int), st));
+  k_max_int<<<ceil_div(n_cta, 256), 256, 0, st>>>(n_cta, p->cta_elem_ptr, d_mx);
+  DFB_LAUNCH_CHECK();
+  DFB_CUDA(cudaMemcpyAsync(&total_ge, p->cta_elem_ptr + n_cta, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DFB_CUDA(cudaMemcpyAsync(&p->max_cta_elems, d_mx, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DFB_CUDA(cudaStreamSynchronize(st));
+  DFB_CUDA(cudaMalloc(&p->cta_elems, sizeof(int) * (size_t)std::max(1, total_ge)));
+  k_group_elems<true><<<ceil_div(n_cta, 64), 64, 0, st>>>(N, n_cta, p->v2c_ptr, p->v2c, nullptr, p->cta_elem_ptr, p->cta_elems);
+  DFB_LAUNCH_CHECK();
+  DFB_CUDA(cudaMalloc(&p->contrib16, sizeof(unsigned short) * (size_t)E * 16));
+  k_contrib16<<<ceil_div(n_items, 128), 128, 0, st>>>(n_items, p->item_meta, p->item_ptr, p->contrib, p->cta_elem_ptr, p->cta_elems, p->contrib16);
+  DFB_LAUNCH_CHECK();
+  DFB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(tmp); cudaFree(gcnt); cudaFree(d_mx);
   p->pull_bytes = sizeof(int) * ((size_t)N + 1) + sizeof(uint2) * (size_t)n_items + sizeof(int) * ((size_t)n_items + 1) +
-                  sizeof(u32) * (size_t)E * 16 + sizeof(f64) * 48 * (size_t)E;
+                  sizeof(u32) * (size_t)E * 16 + sizeof(f64) * 48 * (size_t)E + sizeof(int) * ((size_t)n_cta + 1) +
+                  sizeof(int) * (size_t)total_ge + sizeof(unsigned short) * (size_t)E * 16;
   return DFB_OK;
 }
 
@@ -433,6 +533,7 @@ void dfb_plan_destroy(dfb_plan* p) {
   if (!p) return;
   cudaFree(p->v2c_ptr); cudaFree(p->v2c); cudaFree(p->slot); cudaFree(p->elemF);
   cudaFree(p->row_item); cudaFree(p->item_meta); cudaFree(p->item_ptr); cudaFree(p->contrib); cudaFree(p->prec);
+  cudaFree(p->cta_elem_ptr); cudaFree(p->cta_elems); cudaFree(p->contrib16);
   delete p;
 }
 
