@@ -183,6 +183,52 @@ def test_unstructured_mesh_matches_oracle(api, oracle, mode):
     fs.close()
 
 
+def test_error_behaviour(api):
+    """status codes + dfb_last_error instead of the reference's ASSERT traps: nodal row longer than 64 (csr.c:10,64),
+    too few coloring rounds (color.h:6 MAX_COLOR), Jacobian requested from a residual-only plan, bad arguments."""
+    import ctypes as C
+    from dedflow_b200 import lib as dlib
+    L = dlib.load()
+    P = lambda t: C.c_void_p(t.data_ptr())
+    # a "star": node 0 shared by 70 tets whose other nodes are all distinct -> row 0 would hold 211 entries
+    E = 70
+    ien = np.zeros((E, 4), np.int32)
+    ien[:, 1:] = 1 + np.arange(3 * E, dtype=np.int32).reshape(E, 3)
+    N = 1 + 3 * E
+    d_ien = torch.from_numpy(ien.reshape(-1)).cuda()
+    rp = torch.zeros(N + 1, dtype=torch.int32, device="cuda")
+    nnz = C.c_int(0)
+    assert L.dfb_pattern_rows(N, E, P(d_ien), P(rp), C.byref(nnz), None) == -3            # DFB_ERR_OVERFLOW
+    assert b"64" in L.dfb_last_error()
+    # coloring needs 70 rounds here (all tets share node 0); allow 8
+    w = torch.arange(E, dtype=torch.int32, device="cuda")
+    color = torch.zeros(E, dtype=torch.int32, device="cuda")
+    nc = C.c_int(0)
+    assert L.dfb_color_jpl(N, E, P(d_ien), P(w), 8, P(color), C.byref(nc), None) == -4      # DFB_ERR_COLOR
+    assert L.dfb_color_jpl(N, E, P(d_ien), P(w), 256, P(color), C.byref(nc), None) == 0 and nc.value == 70
+    assert sorted(color.cpu().tolist()) == list(range(70))                                # heaviest weight first
+    # residual-only plan: F works, J is refused
+    mesh = boxmesh.make_box(2)
+    fs = api.FlowSystem(mesh, with_colors=False)
+    plan = C.c_void_p()
+    assert L.dfb_plan_create(C.byref(plan), mesh.num_node, mesh.num_tet, P(fs.ien), None, None, 0, None, None, None) == 0
+    wg, dwg = (torch.from_numpy(a).cuda() for a in boxmesh.state_random(mesh.num_node))
+    F = torch.zeros(6 * mesh.num_node, dtype=torch.float64, device="cuda")
+    assert L.dfb_assemble_tet(plan, P(fs.xg), P(wg), P(dwg), P(F), None, None, None, None, 1, 1, None) == 0
+    assert L.dfb_assemble_tet(plan, P(fs.xg), P(wg), P(dwg), None, P(fs.A00), P(fs.A01), P(fs.A10), P(fs.A11), 1, 1, None) == -2
+    assert b"sparsity pattern" in L.dfb_last_error()
+    F2 = torch.zeros_like(F)
+    fs.assemble_system(wg, dwg, F=F2, faces=False, dirichlet=False)
+    F[4 * mesh.num_node:] = 0
+    assert torch.equal(F, F2)                                                            # same kernels, same order: bit-identical
+    L.dfb_plan_destroy(plan)
+    # bad arguments
+    assert L.dfb_spmv_fs(0, None, None, None, None, None, None, 1.0, None, 0.0, None, None) == -2
+    ws = C.c_void_p()
+    assert L.dfb_gmres_create(C.byref(ws), 10, 500) == -2 and b"127" in L.dfb_last_error()
+    fs.close()
+
+
 def test_newton_vector_kernels_match_numpy(api, oracle):
     """the fused driver kernels against the reference's axpy / copy / scal / nrm2 sequences"""
     import ctypes as C
