@@ -421,7 +421,20 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
   const double2* w2 = reinterpret_cast<const double2*>(w);
   const size_t np = nl >> 1, ld2 = ldq >> 1;
   if (nj == JT) {
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < np; i += (size_t)gridDim.x * 256) {
+    const size_t stride = (size_t)gridDim.x * 256;
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + stride < np; i += 2 * stride) {   // two row pairs per trip: 18 independent 16-byte loads in flight
+      const double2 wa = w2[i], wb = w2[i + stride];
+      double2 qa[JT], qb[JT];
+#pragma unroll
+      for (int j = 0; j < JT; j++) { qa[j] = q2[(size_t)j * ld2 + i]; qb[j] = q2[(size_t)j * ld2 + i + stride]; }
+#pragma unroll
+      for (int j = 0; j < JT; j++) {
+        acc[j] = fma(qa[j].y, wa.y, fma(qa[j].x, wa.x, acc[j]));
+        acc[j] = fma(qb[j].y, wb.y, fma(qb[j].x, wb.x, acc[j]));
+      }
+    }
+    if (i < np) {
       const double2 wi = w2[i];
       double2 qv[JT];
 #pragma unroll
