@@ -74,7 +74,7 @@ __device__ __forceinline__ void scatter_block(f64* __restrict__ A00, f64* __rest
 // F: one thread per element
 // ------------------------------------------------------------------------------------------------------------
 template <int MODE>  // 0: write scratch[e*24..] (64-byte padded corner slots measured slower), 1: atomic scatter, 2: plain scatter of a color batch
-__global__ void __launch_bounds__(128, 3) k_elemF(int n, const int* __restrict__ elem_ids, int N, const int* __restrict__ ien,
+__global__ void __launch_bounds__(128) k_elemF(int n, const int* __restrict__ elem_ids, int N, const int* __restrict__ ien,
                                                const f64* __restrict__ xg, const f64* __restrict__ wg,
                                                const f64* __restrict__ dwg, f64* __restrict__ out) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
