@@ -100,6 +100,11 @@ DFB_HD void metric(const Geom& g, f64 G[3][3]) {
 // residual.  val[comp][a]: nodal values; comp 0..2 = u (wgalpha), 3 = p (dwgalpha slot 3, defect D6),
 // 4 = phi, 5 = T (wgalpha);  dval[comp][a]: nodal rates from dwgalpha.  eF[a][ii].
 // ------------------------------------------------------------------------------------------
+// Hoisted like the Jacobian: for linear tets grad N is constant and N_a(q) = SB + SD [a == q], so
+//   sum_q N_a(q) X_q = SB sum_q X_q + SD X_a      and      sum_q (grad N_a . Y_q) = grad N_a . sum_q Y_q .
+// The quadrature loop therefore only accumulates a handful of sums (T0, T1, V, B4, B5, ...) and the SD terms of row q; the
+// 4 x 6 scatter over the shape functions happens once at the end instead of once per quadrature point (reference
+// assemble.cu:761-924 evaluates it inside the loop).  The re-association changes results at the 1e-16 level.
 DFB_HD void residual(const Geom& g, const f64 val[6][4], const f64 dval[6][4], f64 eF[4][6]) {
   f64 G[3][3];
   metric(g, G);
@@ -119,25 +124,26 @@ DFB_HD void residual(const Geom& g, const f64 val[6][4], const f64 dval[6][4], f
   const f64 divu = grad[0][0] + grad[1][1] + grad[2][2];
   const f64 t0 = 4.0 / (DT * DT);
   const f64 fb[3] = {FB0, FB1, FB2};
+  // nodal sums for the interpolation: value(q) = SB * sum_a v_a + SD * v_q.  Needed: u, p of val; du, dphi, dT of dval.
+  f64 sv[4], sd[6];
 #pragma unroll
-  for (int a = 0; a < 4; a++)
+  for (int c = 0; c < 4; c++) sv[c] = SB * (val[c][0] + val[c][1] + val[c][2] + val[c][3]);
 #pragma unroll
-    for (int i = 0; i < 6; i++) eF[a][i] = 0.0;
-  const f64 wdet = GW * g.detJ;
+  for (int c = 0; c < 6; c++) sd[c] = SB * (dval[c][0] + dval[c][1] + dval[c][2] + dval[c][3]);
+  f64 T0[3] = {0.0, 0.0, 0.0}, T1[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+  f64 V[3] = {0.0, 0.0, 0.0}, B4[3] = {0.0, 0.0, 0.0}, B5[3] = {0.0, 0.0, 0.0};
+  f64 sbp = 0.0, sbtc = 0.0;
 #pragma unroll
   for (int q = 0; q < 4; q++) {
-    f64 vq[6], dq[6];
-#pragma unroll
-    for (int c = 0; c < 6; c++) {
-      vq[c] = shl(0, q) * val[c][0] + shl(1, q) * val[c][1] + shl(2, q) * val[c][2] + shl(3, q) * val[c][3];
-      dq[c] = shl(0, q) * dval[c][0] + shl(1, q) * dval[c][1] + shl(2, q) * dval[c][2] + shl(3, q) * dval[c][3];
-    }
-    const f64 u0 = vq[0], u1 = vq[1], u2 = vq[2];
+    const f64 u0 = sv[0] + SD * val[0][q], u1 = sv[1] + SD * val[1][q], u2 = sv[2] + SD * val[2][q], pq = sv[3] + SD * val[3][q];
+    const f64 dq0 = sd[0] + SD * dval[0][q], dq1 = sd[1] + SD * dval[1][q], dq2 = sd[2] + SD * dval[2][q];
+    const f64 dq4 = sd[4] + SD * dval[4][q], dq5 = sd[5] + SD * dval[5][q];
     const f64 uadv[3] = {u0, u1, u2};
+    const f64 dqv[3] = {dq0, dq1, dq2};
     f64 rLi[3];
 #pragma unroll
     for (int i = 0; i < 3; i++)
-      rLi[i] = RHO * (dq[i] - fb[i]) + RHO * u0 * grad[i][0] + RHO * u1 * grad[i][1] + RHO * u2 * grad[i][2] + grad[3][i];
+      rLi[i] = RHO * (dqv[i] - fb[i]) + RHO * u0 * grad[i][0] + RHO * u1 * grad[i][1] + RHO * u2 * grad[i][2] + grad[3][i];
     // GetStabTau (assemble.cu:444-484)
     f64 t1 = 0.0;
 #pragma unroll
@@ -148,40 +154,39 @@ DFB_HD void residual(const Geom& g, const f64 val[6][4], const f64 dval[6][4], f
     const f64 tauC = sqrt(t1 + 3.0 * nu * nu * gg) / tr;
     const f64 tauP = rsqrt_(t0 + t1);
     const f64 tauT = rsqrt_(t0 + t1 + 3.0 * al * al * gg) / (RHO * CP);
-    f64 shconv[4];
+    const f64 pd = -pq + RHO * tauC * divu;
+    const f64 bp = dq4 + u0 * grad[4][0] + u1 * grad[4][1] + u2 * grad[4][2];
+    const f64 btc = RHO * CP * (dq5 + u0 * grad[5][0] + u1 * grad[5][1] + u2 * grad[5][2]);
 #pragma unroll
-    for (int a = 0; a < 4; a++) shconv[a] = u0 * g.sh[a][0] + u1 * g.sh[a][1] + u2 * g.sh[a][2];
-    f64 tmp0[3], tmp1[3][3];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-      tmp0[i] = RHO * (dq[i] - fb[i]) + RHO * (u0 - tauM * rLi[0]) * grad[i][0] + RHO * (u1 - tauM * rLi[1]) * grad[i][1] +
-                RHO * (u2 - tauM * rLi[2]) * grad[i][2];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 3; i++) {
+      const f64 tmp0 = RHO * (dqv[i] - fb[i]) + RHO * (u0 - tauM * rLi[0]) * grad[i][0] + RHO * (u1 - tauM * rLi[1]) * grad[i][1] +
+                       RHO * (u2 - tauM * rLi[2]) * grad[i][2];
+      T0[i] += tmp0;
+      eF[q][i] = SD * tmp0;                       // the SD * X_a term of row a = q
 #pragma unroll
       for (int j = 0; j < 3; j++)
-        tmp1[i][j] = MU * (grad[i][j] + grad[j][i]) + RHO * tauM * rLi[i] * uadv[j] - RHO * tauM * tauM * rLi[i] * rLi[j];
-    const f64 pd = -vq[3] + RHO * tauC * divu;
-    tmp1[0][0] += pd;
-    tmp1[1][1] += pd;
-    tmp1[2][2] += pd;
-    const f64 bp = dq[4] + u0 * grad[4][0] + u1 * grad[4][1] + u2 * grad[4][2];
-    const f64 btc = RHO * CP * (dq[5] + u0 * grad[5][0] + u1 * grad[5][1] + u2 * grad[5][2]);
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-      const f64 Na = shl(a, q);
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        f64 bm = Na * tmp0[i] + g.sh[a][0] * tmp1[i][0] + g.sh[a][1] * tmp1[i][1] + g.sh[a][2] * tmp1[i][2];
-        eF[a][i] += bm * wdet;
-      }
-      f64 bc = Na * divu + tauM * rLi[0] * g.sh[a][0] + tauM * rLi[1] * g.sh[a][1] + tauM * rLi[2] * g.sh[a][2];
-      eF[a][3] += bc * wdet;
-      eF[a][4] += bp * (Na + tauP * shconv[a]) * wdet;
-      f64 bt = btc * (Na + RHO * CP * tauT * shconv[a]) +
-               KAPPA * (grad[5][0] * g.sh[a][0] + grad[5][1] * g.sh[a][1] + grad[5][2] * g.sh[a][2]);
-      eF[a][5] += bt * wdet;
+        T1[i][j] += MU * (grad[i][j] + grad[j][i]) + RHO * tauM * rLi[i] * uadv[j] - RHO * tauM * tauM * rLi[i] * rLi[j] +
+                    (i == j ? pd : 0.0);
+      V[i] += tauM * rLi[i];
+      B4[i] += bp * tauP * uadv[i];
+      B5[i] += btc * (RHO * CP * tauT) * uadv[i];
     }
+    sbp += bp;
+    sbtc += btc;
+    eF[q][4] = SD * bp;
+    eF[q][5] = SD * btc;
+  }
+  const f64 wdet = GW * g.detJ;
+#pragma unroll
+  for (int d = 0; d < 3; d++) B5[d] += 4.0 * KAPPA * grad[5][d];   // kappa grad T . grad N_a at the 4 points
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const f64 s0 = g.sh[a][0], s1 = g.sh[a][1], s2 = g.sh[a][2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) eF[a][i] = (eF[a][i] + SB * T0[i] + s0 * T1[i][0] + s1 * T1[i][1] + s2 * T1[i][2]) * wdet;
+    eF[a][3] = (SN * divu + s0 * V[0] + s1 * V[1] + s2 * V[2]) * wdet;
+    eF[a][4] = (eF[a][4] + SB * sbp + s0 * B4[0] + s1 * B4[1] + s2 * B4[2]) * wdet;
+    eF[a][5] = (eF[a][5] + SB * sbtc + s0 * B5[0] + s1 * B5[1] + s2 * B5[2]) * wdet;
   }
 }
 
