@@ -43,6 +43,29 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
   } while (0)
 
 inline int ceil_div(i64 a, i64 b) { return (int)((a + b - 1) / b); }
+
+// Device scratch that is released on every return path (the DFB_CUDA / DFB_CHECK macros return early on errors).
+// release() hands the pointer over to a longer-lived owner.
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t count) {
+    if (p) { cudaFree(p); p = nullptr; }
+    const cudaError_t e = cudaMalloc(&p, sizeof(T) * (count ? count : 1));
+    if (e != cudaSuccess) {
+      p = nullptr;
+      set_error("cudaMalloc of %zu bytes failed: %s", sizeof(T) * count, cudaGetErrorString(e));
+      return DFB_ERR_CUDA;
+    }
+    return DFB_OK;
+  }
+  T* release() { T* q = p; p = nullptr; return q; }
+  operator T*() const { return p; }
+};
 inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
 
 // number of SMs of the current device (B200: 148); cached

@@ -71,18 +71,18 @@ __global__ void k_sort_corners(int N, const int* __restrict__ ptr, int* __restri
 }
 
 int build_v2c(int N, int E, const int* d_ien, int** d_ptr_out, int** d_v2c_out, cudaStream_t st) {
-  int *ptr = nullptr, *v2c = nullptr, *cnt = nullptr;
-  DFB_CUDA(cudaMalloc(&ptr, sizeof(int) * ((size_t)N + 1)));
-  DFB_CUDA(cudaMalloc(&v2c, sizeof(int) * (size_t)E * 4));
-  DFB_CUDA(cudaMalloc(&cnt, sizeof(int) * ((size_t)N + 1)));
+  DevBuf<int> ptr, v2c, cnt;
+  DevBuf<char> tmp;
+  DFB_CHECK(ptr.alloc((size_t)N + 1));
+  DFB_CHECK(v2c.alloc((size_t)E * 4));
+  DFB_CHECK(cnt.alloc((size_t)N + 1));
   DFB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)N + 1), st));
   k_count_corners<<<ceil_div(4 * (i64)E, 256), 256, 0, st>>>(E, d_ien, cnt);
   DFB_LAUNCH_CHECK();
   size_t tmp_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, ptr, N + 1, st);
-  void* tmp = nullptr;
-  DFB_CUDA(cudaMalloc(&tmp, tmp_bytes));
-  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, ptr, N + 1, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt.p, ptr.p, N + 1, st);
+  DFB_CHECK(tmp.alloc(tmp_bytes));
+  cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cnt.p, ptr.p, N + 1, st);
   DFB_LAUNCH_CHECK();
   DFB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)N + 1), st));
   k_fill_corners<<<ceil_div(4 * (i64)E, 256), 256, 0, st>>>(E, d_ien, ptr, cnt, v2c);
@@ -90,10 +90,8 @@ int build_v2c(int N, int E, const int* d_ien, int** d_ptr_out, int** d_v2c_out, 
   k_sort_corners<<<ceil_div(N, 128), 128, 0, st>>>(N, ptr, v2c);
   DFB_LAUNCH_CHECK();
   DFB_CUDA(cudaStreamSynchronize(st));
-  cudaFree(tmp);
-  cudaFree(cnt);
-  *d_ptr_out = ptr;
-  *d_v2c_out = v2c;
+  *d_ptr_out = ptr.release();
+  *d_v2c_out = v2c.release();
   return DFB_OK;
 }
 
@@ -437,25 +435,24 @@ long long dfb_launch_count(void) { return g_launches.load(); }
 int dfb_pattern_rows(int N, int E, const int* d_ien, int* d_row_ptr, int* nnz, void* stream) {
   cudaStream_t st = as_stream(stream);
   if (N <= 0 || E <= 0 || !d_ien || !d_row_ptr || !nnz) { set_error("dfb_pattern_rows: bad argument"); return DFB_ERR_ARG; }
-  int *ptr = nullptr, *v2c = nullptr, *len = nullptr, *ovf = nullptr;
-  DFB_CHECK(build_v2c(N, E, d_ien, &ptr, &v2c, st));
-  DFB_CUDA(cudaMalloc(&len, sizeof(int) * ((size_t)N + 1)));
-  DFB_CUDA(cudaMalloc(&ovf, sizeof(int)));
+  DevBuf<int> ptr, v2c, len, ovf;
+  DevBuf<char> tmp;
+  DFB_CHECK(build_v2c(N, E, d_ien, &ptr.p, &v2c.p, st));
+  DFB_CHECK(len.alloc((size_t)N + 1));
+  DFB_CHECK(ovf.alloc(1));
   DFB_CUDA(cudaMemsetAsync(len, 0, sizeof(int) * ((size_t)N + 1), st));
   DFB_CUDA(cudaMemsetAsync(ovf, 0, sizeof(int), st));
   k_pattern<false><<<ceil_div(N, 128), 128, 0, st>>>(N, d_ien, ptr, v2c, len, nullptr, nullptr, ovf);
   DFB_LAUNCH_CHECK();
   size_t tmp_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, len, d_row_ptr, N + 1, st);
-  void* tmp = nullptr;
-  DFB_CUDA(cudaMalloc(&tmp, tmp_bytes));
-  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, len, d_row_ptr, N + 1, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, len.p, d_row_ptr, N + 1, st);
+  DFB_CHECK(tmp.alloc(tmp_bytes));
+  cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, len.p, d_row_ptr, N + 1, st);
   DFB_LAUNCH_CHECK();
   int h_ovf = 0, h_nnz = 0;
   DFB_CUDA(cudaMemcpyAsync(&h_ovf, ovf, sizeof(int), cudaMemcpyDeviceToHost, st));
   DFB_CUDA(cudaMemcpyAsync(&h_nnz, d_row_ptr + N, sizeof(int), cudaMemcpyDeviceToHost, st));
   DFB_CUDA(cudaStreamSynchronize(st));
-  cudaFree(tmp); cudaFree(len); cudaFree(ovf); cudaFree(ptr); cudaFree(v2c);
   if (h_ovf) { set_error("dfb_pattern_rows: a nodal row exceeds 64 entries (reference csr.c:64 asserts)"); return DFB_ERR_OVERFLOW; }
   *nnz = h_nnz;
   return DFB_OK;
@@ -464,14 +461,13 @@ int dfb_pattern_rows(int N, int E, const int* d_ien, int* d_row_ptr, int* nnz, v
 int dfb_pattern_cols(int N, int E, const int* d_ien, const int* d_row_ptr, int* d_col_ind, void* stream) {
   cudaStream_t st = as_stream(stream);
   if (N <= 0 || E <= 0 || !d_ien || !d_row_ptr || !d_col_ind) { set_error("dfb_pattern_cols: bad argument"); return DFB_ERR_ARG; }
-  int *ptr = nullptr, *v2c = nullptr, *ovf = nullptr;
-  DFB_CHECK(build_v2c(N, E, d_ien, &ptr, &v2c, st));
-  DFB_CUDA(cudaMalloc(&ovf, sizeof(int)));
+  DevBuf<int> ptr, v2c, ovf;
+  DFB_CHECK(build_v2c(N, E, d_ien, &ptr.p, &v2c.p, st));
+  DFB_CHECK(ovf.alloc(1));
   DFB_CUDA(cudaMemsetAsync(ovf, 0, sizeof(int), st));
   k_pattern<true><<<ceil_div(N, 128), 128, 0, st>>>(N, d_ien, ptr, v2c, nullptr, d_row_ptr, d_col_ind, ovf);
   DFB_LAUNCH_CHECK();
   DFB_CUDA(cudaStreamSynchronize(st));
-  cudaFree(ovf); cudaFree(ptr); cudaFree(v2c);
   return DFB_OK;
 }
 
