@@ -532,6 +532,156 @@ __global__ void __launch_bounds__(128) k_pullJ_staged(int N, int n_rows, const i
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// J, PAIRS (default).  One CTA per group of R rows (plan.cuh pr_*), two phases, no global intermediate:
+//   A. every thread evaluates the per-element part of the hoisted Jacobian (geometry + jac_prep) of one of the group's
+//      distinct elements and parks the 368-byte record in shared memory (23 16-byte chunks: odd stride, conflict-free);
+//   B. one thread per work item.  The first 4R items are the diagonal entries (4 virtual items each, whole warps, folded by
+//      the quad butterfly); the others are the UPPER off-diagonal nonzeros (i,j), j > i: the thread walks the elements
+//      around the edge once and accumulates BOTH blocks A_ij and A_ji (elem_math.cuh jrec_pair: 13 LDS.128 and ~90 FP64
+//      instructions per element instead of 2 x (13 + ~80)), then writes A_ij into row i (coalesced across the lanes of a
+//      row) and A_ji into row j (scattered 24-byte pieces that L2 merges with the rest of row j).
+// Every CSR value is written exactly once, in a fixed order: no atomics, no colors, no memset, deterministic.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PAIR_SREC = 23;   // shared-memory stride of a staged record in 16-byte chunks (JREC = 46 doubles)
+
+__device__ __forceinline__ void fold_quad(const f64 acc[16], f64 u[4]) {
+  const int lane = threadIdx.x & 31;
+  const bool hi = lane & 2, odd = lane & 1;
+  f64 t[2][4];
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const f64 send = hi ? acc[r * 4 + j] : acc[(r + 2) * 4 + j];
+      const f64 keep = hi ? acc[(r + 2) * 4 + j] : acc[r * 4 + j];
+      t[r][j] = keep + __shfl_xor_sync(FULL, send, 2);
+    }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const f64 send = odd ? t[0][j] : t[1][j];
+    const f64 keep = odd ? t[1][j] : t[0][j];
+    u[j] = keep + __shfl_xor_sync(FULL, send, 1);
+  }
+}
+
+__device__ __forceinline__ void load_chunks5(const double2* __restrict__ p, f64 out[10]) {
+#pragma unroll
+  for (int c = 0; c < 5; c++) { const double2 v = p[c]; out[2 * c] = v.x; out[2 * c + 1] = v.y; }
+}
+
+template <int OVERWRITE>
+__global__ void __launch_bounds__(192, 2) k_pairJ(int N, int n_rows, int R, const int* __restrict__ grp_item,
+                                                  const uint2* __restrict__ item_meta, const int* __restrict__ item_ptr,
+                                                  const unsigned short* __restrict__ contrib, const int* __restrict__ elem_ptr,
+                                                  const int* __restrict__ elems, const int* __restrict__ ien,
+                                                  const f64* __restrict__ xg, const f64* __restrict__ wg,
+                                                  const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
+                                                  f64* __restrict__ A00, f64* __restrict__ A01, f64* __restrict__ A10,
+                                                  f64* __restrict__ A11) {
+  extern __shared__ __align__(16) unsigned char pair_smem[];
+  double2* srec = reinterpret_cast<double2*>(pair_smem);
+  const int g = blockIdx.x;
+  const int e0 = __ldg(elem_ptr + g), ne = __ldg(elem_ptr + g + 1) - e0;
+  // ---- phase A: element records into shared memory ----
+  for (int r = threadIdx.x; r < ne; r += blockDim.x) {
+    const int e = __ldg(elems + e0 + r);
+    int nodes[4];
+    load_nodes(ien, e, nodes);
+    f64 x[4][3], u[4][3];
+    load_xyz(xg, nodes, x);
+    load_xyz(wg, nodes, u);
+    Geom gm;
+    geometry(x, gm);
+    JPrep p;
+    jac_prep(gm, u, p);
+    f64 rec[JREC];
+    jrec_store(gm, p, rec);
+    double2* dst = srec + r * PAIR_SREC;
+#pragma unroll
+    for (int c = 0; c < PAIR_SREC; c++) dst[c] = make_double2(rec[2 * c], rec[2 * c + 1]);
+  }
+  __syncthreads();
+  // ---- phase B: work items ----
+  const int it0 = __ldg(grp_item + g), n_it = __ldg(grp_item + g + 1) - it0;
+  const int nd = 4 * R;
+  for (int base = 0; base < n_it; base += blockDim.x) {
+    const int t = base + threadIdx.x;
+    const int item = it0 + t;
+    if (base + (int)(threadIdx.x & ~31u) < nd) {
+      // a warp of diagonal items (nd is a multiple of 32 and n_it >= nd: every lane has an item)
+      const uint2 meta = item_meta[item];
+      const int cs = __ldg(item_ptr + item), ce = __ldg(item_ptr + item + 1);
+      f64 acc[16];
+#pragma unroll
+      for (int v = 0; v < 16; v++) acc[v] = 0.0;
+      unsigned nxt = cs < ce ? contrib[cs] : 0u;
+      for (int idx = cs; idx < ce; idx++) {
+        const unsigned c16 = nxt;
+        if (idx + 1 < ce) nxt = contrib[idx + 1];
+        const int li = (int)(c16 >> 4), a = (int)((c16 >> 2) & 3u);
+        const double2* Rr = srec + li * PAIR_SREC;
+        f64 A[10], T[6];
+        load_chunks5(Rr + a * 5, A);
+        const double2 t0 = Rr[20], t1 = Rr[21], t2 = Rr[22];
+        T[0] = t0.x; T[1] = t0.y; T[2] = t1.x; T[3] = t1.y; T[4] = t2.x; T[5] = t2.y;
+        jrec_diag(A, T, a, acc);
+      }
+      f64 u[4];
+      fold_quad(acc, u);
+      if (meta.x != 0xffffffffu && (int)meta.x < n_rows) {
+        const int row = (int)meta.x, k = (int)(meta.y & 0xffu);
+        const int start = __ldg(row_ptr + row), len = __ldg(row_ptr + row + 1) - start;
+        const size_t st = (size_t)start;
+        const int q = threadIdx.x & 3;
+        if (q < 3) {
+          f64* d = A00 + st * 9 + (size_t)k * 3 + (size_t)q * len * 3;
+          f64* d1 = A01 + st * 3 + k + (size_t)q * len;
+          if (OVERWRITE) { d[0] = u[0]; d[1] = u[1]; d[2] = u[2]; *d1 = u[3]; }
+          else { d[0] += u[0]; d[1] += u[1]; d[2] += u[2]; *d1 += u[3]; }
+        } else {
+          f64* p10 = A10 + st * 3 + (size_t)k * 3;
+          f64* p11 = A11 + st + k;
+          if (OVERWRITE) { p10[0] = u[0]; p10[1] = u[1]; p10[2] = u[2]; *p11 = u[3]; }
+          else { p10[0] += u[0]; p10[1] += u[1]; p10[2] += u[2]; *p11 += u[3]; }
+        }
+      }
+    } else if (t < n_it) {
+      const uint2 meta = item_meta[item];
+      const int cs = __ldg(item_ptr + item), ce = __ldg(item_ptr + item + 1);
+      f64 acc[24];
+#pragma unroll
+      for (int v = 0; v < 24; v++) acc[v] = 0.0;
+      unsigned nxt = cs < ce ? contrib[cs] : 0u;
+      for (int idx = cs; idx < ce; idx++) {
+        const unsigned c16 = nxt;
+        if (idx + 1 < ce) nxt = contrib[idx + 1];
+        const int li = (int)(c16 >> 4), a = (int)((c16 >> 2) & 3u), b = (int)(c16 & 3u);
+        const double2* Rr = srec + li * PAIR_SREC;
+        f64 A[10], B[10], T[6];
+        load_chunks5(Rr + a * 5, A);
+        load_chunks5(Rr + b * 5, B);
+        const double2 t0 = Rr[20], t1 = Rr[21], t2 = Rr[22];
+        T[0] = t0.x; T[1] = t0.y; T[2] = t1.x; T[3] = t1.y; T[4] = t2.x; T[5] = t2.y;
+        jrec_pair(A, B, T, a, b, acc);
+      }
+      const int row = (int)meta.x;
+      if (row < n_rows) {
+        f64 ab[16], ba[16];
+        jrec_pair_blocks(acc, ab, ba);
+        const int kij = (int)(meta.y & 0xffu), kji = (int)((meta.y >> 16) & 0xffu);
+        const int start = __ldg(row_ptr + row), len = __ldg(row_ptr + row + 1) - start;
+        scatter_block<OVERWRITE ? 2 : 0>(A00, A01, A10, A11, (size_t)start, len, kij, ab);
+        const int j = __ldg(col_ind + start + kij);
+        if (j < n_rows) {
+          const int sj = __ldg(row_ptr + j), lj = __ldg(row_ptr + j + 1) - sj;
+          scatter_block<OVERWRITE ? 2 : 0>(A00, A01, A10, A11, (size_t)sj, lj, kji, ba);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // boundary faces (tiny: O(N^(2/3)) faces): one thread per face, atomic scatter
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_face(int nf, const int* __restrict__ f2e, const int* __restrict__ forn, int N,
@@ -661,13 +811,43 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
   if (doJ) {
     if (mode == DFB_MODE_GATHER) {
       const int grid = ceil_div(P->n_rows, 4);
-      // variants of the atomic-free assembly: pull (default, 0.75 ms at 1M tets on B200) and the fused row gather
-      // (DFB_J_VARIANT=fused, 1.07 ms); see DESIGN.md section 3
-      static const int variant = [] {
+      // variants of the atomic-free assembly: node pairs (default), pull (DFB_J_VARIANT=pull) and the fused row gather
+      // (DFB_J_VARIANT=fused); see DESIGN.md section 3
+      const int variant = [] {   // read per call: tests switch variants inside one process
         const char* e = getenv("DFB_J_VARIANT");
-        return (e && !strcmp(e, "fused")) ? 1 : 0;
+        if (e && !strcmp(e, "fused")) return 1;
+        if (e && !strcmp(e, "pull")) return 0;
+        return 2;   // pairs
       }();
-      if (variant == 0) {
+      bool done = false;
+      if (variant == 2) {
+        const int pair_rows = [] {   // only read when the plan's pair lists are first built
+          const char* e = getenv("DFB_J_PAIR_ROWS");
+          const int r = e ? atoi(e) : 8;
+          return (r >= 8 && r <= 16 && (r & 7) == 0) ? r : 8;
+        }();
+        DFB_CHECK(build_pairs(P, pair_rows, st));
+        if (P->pr_state == 1) {
+          const size_t smem = (size_t)std::max(1, P->pr_max_elems) * PAIR_SREC * sizeof(double2);
+          static size_t pair_smem_set = 0;
+          if (smem > pair_smem_set) {
+            DFB_CUDA(cudaFuncSetAttribute(k_pairJ<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DFB_CUDA(cudaFuncSetAttribute(k_pairJ<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            pair_smem_set = smem;
+          }
+          const int R = P->pr_rows, ncta = ceil_div(P->n_rows, R), nthr = 96 * (R / 8);
+          if (overwrite)
+            k_pairJ<1><<<ncta, nthr, smem, st>>>(N, P->n_rows, R, P->pr_grp_item, P->pr_meta, P->pr_item_ptr, P->pr_contrib, P->pr_elem_ptr,
+                                                 P->pr_elems, P->ien, d_xg, d_wg, P->row_ptr, P->col_ind, d_A00, d_A01, d_A10, d_A11);
+          else
+            k_pairJ<0><<<ncta, nthr, smem, st>>>(N, P->n_rows, R, P->pr_grp_item, P->pr_meta, P->pr_item_ptr, P->pr_contrib, P->pr_elem_ptr,
+                                                 P->pr_elems, P->ien, d_xg, d_wg, P->row_ptr, P->col_ind, d_A00, d_A01, d_A10, d_A11);
+          DFB_LAUNCH_CHECK();
+          done = true;
+        }
+      }
+      if (done) {
+      } else if (variant != 1) {
         DFB_CHECK(build_pull(P, st));
         if (P->items_rows != P->n_rows) {
           if (P->n_rows == P->N) {

@@ -309,6 +309,102 @@ DFB_HD void jac_block(const Geom& g, const JPrep& p, int a, int b, f64 blk[16]) 
 }
 
 // ------------------------------------------------------------------------------------------
+// Jacobian by node PAIRS (assemble.cu k_pairJ).  The blocks (a,b) and (b,a) of one element share their inputs and most of
+// their arithmetic: the 3x3 parts are transposes of each other apart from the diagonal term T, and eK, stc, mab are
+// symmetric.  One accumulator set of 24 doubles therefore carries BOTH nodal nonzeros (i,j) and (j,i):
+//   acc[0..8]  S[ii][jj] = sum k1 ga[jj] gb[ii] + k2 ga[ii] gb[jj]      (A_ij 3x3 = S + T_ab I,  A_ji 3x3 = S^T + T_ba I)
+//   acc[9] T_ab   acc[10] T_ba   acc[11..13] col_ab   acc[14..16] row_ab   acc[17..19] col_ba   acc[20..22] row_ba
+//   acc[23] d = sum w sTM eK   (the (3,3) entry of both blocks)
+// Element record (JREC doubles): corner x at [10x, 10x+10): g0 g1 g2 P c0 c1 c2 c3 R sTC  (c_q = u(q).grad N_x),
+//                                tail at [40,46): w sTM tM0 tM1 tM2 tM3.
+// ------------------------------------------------------------------------------------------
+constexpr int JREC = 46;
+
+DFB_HD void jrec_store(const Geom& g, const JPrep& p, f64* rec) {
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    rec[a * 10 + 0] = g.sh[a][0]; rec[a * 10 + 1] = g.sh[a][1]; rec[a * 10 + 2] = g.sh[a][2]; rec[a * 10 + 3] = p.P[a];
+    rec[a * 10 + 4] = p.c[0][a]; rec[a * 10 + 5] = p.c[1][a]; rec[a * 10 + 6] = p.c[2][a]; rec[a * 10 + 7] = p.c[3][a];
+    rec[a * 10 + 8] = p.R[a]; rec[a * 10 + 9] = p.sTC;
+  }
+  rec[40] = p.w; rec[41] = p.sTM; rec[42] = p.tM[0]; rec[43] = p.tM[1]; rec[44] = p.tM[2]; rec[45] = p.tM[3];
+}
+
+// A, B: the corner sub-records of local nodes a and b (a != b), T: the tail
+DFB_HD void jrec_pair(const f64 A[10], const f64 B[10], const f64 T[6], int a, int b, f64 acc[24]) {
+  const f64 w = T[0], sTM = T[1];
+  const f64 ta0 = T[2] * A[4], ta1 = T[3] * A[5], ta2 = T[4] * A[6], ta3 = T[5] * A[7];
+  const f64 stc = ta0 * B[4] + ta1 * B[5] + ta2 * B[6] + ta3 * B[7];
+  const f64 eK = A[0] * B[0] + A[1] * B[1] + A[2] * B[2];
+  const f64 tab = sel4(b, ta0, ta1, ta2, ta3);                 // tM[b] c[b][a]
+  const f64 cab = sel4(a, B[4], B[5], B[6], B[7]);             // c[q=a][b]
+  const f64 tMa = sel4(a, T[2], T[3], T[4], T[5]), tMb = sel4(b, T[2], T[3], T[4], T[5]);
+  const f64 tba = tMa * cab;                                   // tM[a] c[a][b]
+  const f64 cba = sel4(b, A[4], A[5], A[6], A[7]);             // c[q=b][a]
+  const f64 common = FACT1 * RHO * (2.0 * SA * SB + 2.0 * SB * SB) + FACT2 * RHO * RHO * stc + 4.0 * FACT2 * MU * eK;
+  acc[9] += w * (common + FACT1 * RHO * RHO * (SB * A[3] + SD * tab) + FACT2 * RHO * (SB * B[8] + SD * cab));
+  acc[10] += w * (common + FACT1 * RHO * RHO * (SB * B[3] + SD * tba) + FACT2 * RHO * (SB * A[8] + SD * cba));
+  const f64 k1 = 4.0 * w * FACT2 * MU, k2 = w * FACT2 * RHO * A[9];
+  const f64 k1g[3] = {k1 * A[0], k1 * A[1], k1 * A[2]}, k2g[3] = {k2 * A[0], k2 * A[1], k2 * A[2]};
+#pragma unroll
+  for (int ii = 0; ii < 3; ii++)
+#pragma unroll
+    for (int jj = 0; jj < 3; jj++) acc[ii * 3 + jj] += k1g[jj] * B[ii] + k2g[ii] * B[jj];
+  const f64 k3 = w * SN, k6 = FACT2 * w * SN;
+  const f64 k4a = RHO * w * A[3], k4b = RHO * w * B[3];
+  const f64 k5b = w * RHO * (FACT1 * (SB * sTM + SD * tMb) + FACT2 * B[3]);
+  const f64 k5a = w * RHO * (FACT1 * (SB * sTM + SD * tMa) + FACT2 * A[3]);
+#pragma unroll
+  for (int ii = 0; ii < 3; ii++) {
+    acc[11 + ii] += -k3 * A[ii] + k4a * B[ii];   // block (a,b) column 3
+    acc[14 + ii] += k5b * A[ii] + k6 * B[ii];    // block (a,b) row 3
+    acc[17 + ii] += -k3 * B[ii] + k4b * A[ii];   // block (b,a) column 3
+    acc[20 + ii] += k5a * B[ii] + k6 * A[ii];    // block (b,a) row 3
+  }
+  acc[23] += w * sTM * eK;
+}
+
+// the two 4x4 blocks of a pair accumulator: ab[ii*4+jj] = A_ij, ba = A_ji
+DFB_HD void jrec_pair_blocks(const f64 acc[24], f64 ab[16], f64 ba[16]) {
+#pragma unroll
+  for (int ii = 0; ii < 3; ii++) {
+#pragma unroll
+    for (int jj = 0; jj < 3; jj++) {
+      ab[ii * 4 + jj] = acc[ii * 3 + jj] + (ii == jj ? acc[9] : 0.0);
+      ba[ii * 4 + jj] = acc[jj * 3 + ii] + (ii == jj ? acc[10] : 0.0);
+    }
+    ab[ii * 4 + 3] = acc[11 + ii]; ab[12 + ii] = acc[14 + ii];
+    ba[ii * 4 + 3] = acc[17 + ii]; ba[12 + ii] = acc[20 + ii];
+  }
+  ab[15] = acc[23];
+  ba[15] = acc[23];
+}
+
+// diagonal contribution (a,a) of one element from the corner sub-record and the tail, added to acc[ii*4+jj]
+DFB_HD void jrec_diag(const f64 A[10], const f64 T[6], int a, f64 acc[16]) {
+  const f64 w = T[0], sTM = T[1];
+  const f64 stc = (T[2] * A[4]) * A[4] + (T[3] * A[5]) * A[5] + (T[4] * A[6]) * A[6] + (T[5] * A[7]) * A[7];
+  const f64 eK = A[0] * A[0] + A[1] * A[1] + A[2] * A[2];
+  const f64 caa = sel4(a, A[4], A[5], A[6], A[7]);
+  const f64 tMa = sel4(a, T[2], T[3], T[4], T[5]);
+  const f64 Tt = w * (FACT1 * RHO * (SA * SA + 3.0 * SB * SB) + FACT1 * RHO * RHO * (SB * A[3] + SD * (tMa * caa)) +
+                      FACT2 * RHO * (SB * A[8] + SD * caa) + FACT2 * RHO * RHO * stc + 4.0 * FACT2 * MU * eK);
+  const f64 k12 = 4.0 * w * FACT2 * MU + w * FACT2 * RHO * A[9];
+#pragma unroll
+  for (int ii = 0; ii < 3; ii++)
+#pragma unroll
+    for (int jj = 0; jj < 3; jj++) acc[ii * 4 + jj] += (k12 * A[ii]) * A[jj] + (ii == jj ? Tt : 0.0);
+  const f64 kc = RHO * w * A[3] - w * SN;
+  const f64 kr = w * RHO * (FACT1 * (SB * sTM + SD * tMa) + FACT2 * A[3]) + FACT2 * w * SN;
+#pragma unroll
+  for (int ii = 0; ii < 3; ii++) {
+    acc[ii * 4 + 3] += kc * A[ii];
+    acc[12 + ii] += kr * A[ii];
+  }
+  acc[15] += w * sTM * eK;
+}
+
+// ------------------------------------------------------------------------------------------
 // boundary face (weak BC).  iorn = local index of the vertex opposite the face.
 // val[comp][a]: comp 0..2 = u (wgalpha), 3 = p (dwgalpha slot 3).
 // ------------------------------------------------------------------------------------------

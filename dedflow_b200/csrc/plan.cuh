@@ -41,6 +41,18 @@ struct dfb_plan {
   mutable int max_cta_elems = 0;
   mutable size_t pull_bytes = 0;
   mutable int items_rows = -1, items_active = 0;  // cache: items of the first n_rows rows
+  // PAIR Jacobian assembly (setup.cu build_pairs, assemble.cu k_pairJ; the default).  Rows are cut into groups of pr_rows
+  // (a multiple of 8); one CTA per group.  Work items of a group: first 4 "virtual" items per row for the diagonal entry
+  // (4*pr_rows: whole warps), then one item per UPPER off-diagonal nonzero (i,j), j > i, which also produces (j,i).
+  mutable int pr_state = 0;            // 0: not built, 1: usable, -1: a group does not fit shared memory (fall back to pull)
+  mutable int pr_rows = 0, pr_n_cta = 0, pr_n_items = 0, pr_max_elems = 0;
+  mutable int* pr_grp_item = nullptr;   // [pr_n_cta+1] first item of every group
+  mutable uint2* pr_meta = nullptr;     // [pr_n_items] {row i (0xffffffff: padding), k_ij | 0x100 diagonal | k_ji << 16}
+  mutable int* pr_item_ptr = nullptr;   // [pr_n_items+1] offsets into pr_contrib
+  mutable unsigned short* pr_contrib = nullptr;   // local record index << 4 | a << 2 | b, ascending (element, a, b) per item
+  mutable int* pr_elem_ptr = nullptr;   // [pr_n_cta+1]
+  mutable int* pr_elems = nullptr;      // ascending distinct element ids per group
+  mutable size_t pr_bytes = 0;
 };
 
 namespace dfb {
@@ -48,4 +60,6 @@ constexpr int PULL_ROWS = 6;         // rows per CTA of the staged pull assembly
 constexpr int PULL_MAX_STAGED = 160; // most element records a CTA stages (160 x 384 B = 60 KB)
 int build_v2c(int N, int E, const int* d_ien, int** d_ptr_out, int** d_v2c_out, cudaStream_t st);
 int build_pull(const dfb_plan* plan, cudaStream_t st);
+constexpr int PAIR_MAX_STAGED = 600; // most element records a CTA of the pair assembly stages (600 x 368 B = 216 KB)
+int build_pairs(const dfb_plan* plan, int rows_per_cta, cudaStream_t st);
 }

@@ -291,14 +291,16 @@ __device__ int group_elements(int r0, int r1, const int* __restrict__ v2c_ptr, c
 }
 
 template <bool FILL>
-__global__ void __launch_bounds__(64) k_group_elems(int N, int n_cta, const int* __restrict__ v2c_ptr, const int* __restrict__ v2c,
-                                                    int* __restrict__ cnt, const int* __restrict__ ptr, int* __restrict__ elems) {
+__global__ void __launch_bounds__(64) k_group_elems(int N, int n_cta, int rows, const int* __restrict__ v2c_ptr, const int* __restrict__ v2c,
+                                                    int* __restrict__ cnt, const int* __restrict__ ptr, int* __restrict__ elems,
+                                                    int* __restrict__ overflow) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_cta) return;
-  const int r0 = g * PULL_ROWS, r1 = min(N, r0 + PULL_ROWS);
+  const int r0 = g * rows, r1 = min(N, r0 + rows);
   if (!FILL) {
     const int n = group_elements(r0, r1, v2c_ptr, v2c, nullptr);
     cnt[g] = n < 0 ? 0 : n;   // 0 = not staged
+    if (n < 0 && overflow) atomicExch(overflow, 1);
   } else if (ptr[g + 1] > ptr[g]) {
     group_elements(r0, r1, v2c_ptr, v2c, elems + ptr[g]);
   }
@@ -384,7 +386,7 @@ int build_pull(const dfb_plan* p, cudaStream_t st) {
   DFB_CUDA(cudaMalloc(&gcnt, sizeof(int) * ((size_t)n_cta + 1)));
   DFB_CUDA(cudaMemsetAsync(gcnt, 0, sizeof(int) * ((size_t)n_cta + 1), st));
   DFB_CUDA(cudaMalloc(&p->cta_elem_ptr, sizeof(int) * ((size_t)n_cta + 1)));
-  k_group_elems<false><<<ceil_div(n_cta, 64), 64, 0, st>>>(N, n_cta, p->v2c_ptr, p->v2c, gcnt, nullptr, nullptr);
+  k_group_elems<false><<<ceil_div(n_cta, 64), 64, 0, st>>>(N, n_cta, PULL_ROWS, p->v2c_ptr, p->v2c, gcnt, nullptr, nullptr, nullptr);
   DFB_LAUNCH_CHECK();
   tmp_bytes = 0; tmp = nullptr;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, gcnt, p->cta_elem_ptr, n_cta + 1, st);
@@ -401,7 +403,7 @@ int build_pull(const dfb_plan* p, cudaStream_t st) {
   DFB_CUDA(cudaMemcpyAsync(&p->max_cta_elems, d_mx, sizeof(int), cudaMemcpyDeviceToHost, st));
   DFB_CUDA(cudaStreamSynchronize(st));
   DFB_CUDA(cudaMalloc(&p->cta_elems, sizeof(int) * (size_t)std::max(1, total_ge)));
-  k_group_elems<true><<<ceil_div(n_cta, 64), 64, 0, st>>>(N, n_cta, p->v2c_ptr, p->v2c, nullptr, p->cta_elem_ptr, p->cta_elems);
+  k_group_elems<true><<<ceil_div(n_cta, 64), 64, 0, st>>>(N, n_cta, PULL_ROWS, p->v2c_ptr, p->v2c, nullptr, p->cta_elem_ptr, p->cta_elems, nullptr);
   DFB_LAUNCH_CHECK();
   DFB_CUDA(cudaMalloc(&p->contrib16, sizeof(unsigned short) * (size_t)E * 16));
   k_contrib16<<<ceil_div(n_items, 128), 128, 0, st>>>(n_items, p->item_meta, p->item_ptr, p->contrib, p->cta_elem_ptr, p->cta_elems, p->contrib16);
@@ -411,6 +413,189 @@ int build_pull(const dfb_plan* p, cudaStream_t st) {
   p->pull_bytes = sizeof(int) * ((size_t)N + 1) + sizeof(uint2) * (size_t)n_items + sizeof(int) * ((size_t)n_items + 1) +
                   sizeof(u32) * (size_t)E * 16 + sizeof(f64) * 48 * (size_t)E + sizeof(int) * ((size_t)n_cta + 1) +
                   sizeof(int) * (size_t)total_ge + sizeof(unsigned short) * (size_t)E * 16;
+  return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// work lists of the PAIR Jacobian assembly (plan.cuh, assemble.cu k_pairJ)
+// ------------------------------------------------------------------------------------------
+__global__ void k_pair_group_count(int N, int n_cta, int R, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
+                                   int* __restrict__ cnt) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > n_cta) return;
+  if (g == n_cta) { cnt[g] = 0; return; }
+  int total = 4 * R;
+  for (int row = g * R; row < min(N, (g + 1) * R); row++) {
+    const int s = row_ptr[row], len = row_ptr[row + 1] - s;
+    total += len - 1 - lower_bound_dev(col_ind + s, len, row);   // entries right of the diagonal
+  }
+  cnt[g] = total;
+}
+
+__global__ void k_pair_meta(int N, int n_cta, int R, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
+                            const int* __restrict__ grp_item, uint2* __restrict__ meta, int* __restrict__ row_pair) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_cta) return;
+  const int base = grp_item[g];
+  int pos = base + 4 * R;
+  for (int r = 0; r < R; r++) {
+    const int row = g * R + r;
+    uint2 md = make_uint2(0xffffffffu, 0u);
+    if (row < N) {
+      const int s = row_ptr[row], len = row_ptr[row + 1] - s;
+      const int kd = lower_bound_dev(col_ind + s, len, row);
+      md = make_uint2((u32)row, (u32)kd | 0x100u);
+      row_pair[row] = pos;
+      for (int k = kd + 1; k < len; k++) {
+        const int j = col_ind[s + k];
+        const int sj = row_ptr[j];
+        const int kji = lower_bound_dev(col_ind + sj, row_ptr[j + 1] - sj, row);
+        meta[pos++] = make_uint2((u32)row, (u32)k | ((u32)kji << 16));
+      }
+    }
+    for (int v = 0; v < 4; v++) meta[base + r * 4 + v] = md;
+  }
+}
+
+// item of contribution (corner c = e*4+a, b): -1 for the lower half (produced by the pair item of the other node)
+__device__ __forceinline__ int pair_item_of(int c, int b, int R, const int* __restrict__ ien, const int* __restrict__ row_ptr,
+                                            const int* __restrict__ col_ind, const int* __restrict__ v2c_ptr,
+                                            const int* __restrict__ v2c, const u32* __restrict__ slot32,
+                                            const int* __restrict__ grp_item, const int* __restrict__ row_pair, int* __restrict__ bad) {
+  const int a = c & 3;
+  const int row = ien[c];
+  if (a == b) {
+    const int g = row / R;
+    const int vs = v2c_ptr[row];
+    const int r = lower_bound_dev(v2c + vs, v2c_ptr[row + 1] - vs, c);
+    return grp_item[g] + (row - g * R) * 4 + (r & 3);
+  }
+  const int col = ien[(c & ~3) + b];
+  if (col == row) { atomicExch(bad, 1); return -1; }   // degenerate element (repeated node): the pair variant is not used
+  if (col < row) return -1;
+  const int k = (int)((slot32[c] >> (8 * b)) & 0xffu);
+  const int s = row_ptr[row];
+  const int kd = lower_bound_dev(col_ind + s, row_ptr[row + 1] - s, row);
+  return row_pair[row] + (k - kd - 1);
+}
+
+template <bool FILL>
+__global__ void k_pair_contrib(int E, int R, const int* __restrict__ ien, const int* __restrict__ row_ptr,
+                               const int* __restrict__ col_ind, const int* __restrict__ v2c_ptr, const int* __restrict__ v2c,
+                               const u32* __restrict__ slot32, const int* __restrict__ grp_item, const int* __restrict__ row_pair,
+                               int* __restrict__ cnt, const int* __restrict__ item_ptr, u32* __restrict__ contrib, int* __restrict__ bad) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)16 * E) return;
+  const int c = (int)(t >> 2), b = (int)(t & 3);
+  const int it = pair_item_of(c, b, R, ien, row_ptr, col_ind, v2c_ptr, v2c, slot32, grp_item, row_pair, bad);
+  if (it < 0) return;
+  const int pos = atomicAdd(cnt + it, 1);
+  if (FILL) contrib[item_ptr[it] + pos] = (u32)t;
+}
+
+__global__ void k_pair_contrib16(int n_items, int R, const uint2* __restrict__ meta, const int* __restrict__ item_ptr,
+                                 const u32* __restrict__ contrib, const int* __restrict__ elem_ptr,
+                                 const int* __restrict__ elems, unsigned short* __restrict__ contrib16) {
+  const int it = blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= n_items) return;
+  const u32 row = meta[it].x;
+  if (row == 0xffffffffu) return;
+  const int g = (int)row / R;
+  const int s = elem_ptr[g], n = elem_ptr[g + 1] - s;
+  for (int idx = item_ptr[it]; idx < item_ptr[it + 1]; idx++) {
+    const u32 cid = contrib[idx];
+    const int li = lower_bound_dev(elems + s, n, (int)(cid >> 4));
+    contrib16[idx] = (unsigned short)((li << 4) | (cid & 15u));
+  }
+}
+
+int build_pairs(const dfb_plan* p, int R, cudaStream_t st) {
+  if (p->pr_state != 0) return DFB_OK;
+  if (!p->slot) { set_error("pair assembly needs a plan with a sparsity pattern"); return DFB_ERR_ARG; }
+  if (R < 8 || (R & 7)) { set_error("pair assembly: rows per CTA must be a multiple of 8"); return DFB_ERR_ARG; }
+  if ((i64)p->E * 16 > 0xffffffffLL) { p->pr_state = -1; return DFB_OK; }
+  const int N = p->N, E = p->E;
+  const u32* slot32 = reinterpret_cast<const u32*>(p->slot);
+  const int n_cta = ceil_div(N, R);
+  DevBuf<int> cnt, row_pair, icnt, gcnt, flags;
+  DevBuf<char> tmp;
+  DevBuf<u32> contrib32;
+  DFB_CHECK(cnt.alloc((size_t)n_cta + 1));
+  DFB_CHECK(flags.alloc(3));   // [0] degenerate element, [1] group too large, [2] max elements per group
+  DFB_CUDA(cudaMemsetAsync(flags, 0, 3 * sizeof(int), st));
+  DFB_CUDA(cudaMalloc(&p->pr_grp_item, sizeof(int) * ((size_t)n_cta + 1)));
+  k_pair_group_count<<<ceil_div((i64)n_cta + 1, 128), 128, 0, st>>>(N, n_cta, R, p->row_ptr, p->col_ind, cnt);
+  DFB_LAUNCH_CHECK();
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt.p, p->pr_grp_item, n_cta + 1, st);
+  DFB_CHECK(tmp.alloc(tmp_bytes));
+  cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cnt.p, p->pr_grp_item, n_cta + 1, st);
+  DFB_LAUNCH_CHECK();
+  int n_items = 0;
+  DFB_CUDA(cudaMemcpyAsync(&n_items, p->pr_grp_item + n_cta, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DFB_CUDA(cudaStreamSynchronize(st));
+  DFB_CUDA(cudaMalloc(&p->pr_meta, sizeof(uint2) * (size_t)n_items));
+  DFB_CUDA(cudaMalloc(&p->pr_item_ptr, sizeof(int) * ((size_t)n_items + 1)));
+  DFB_CHECK(row_pair.alloc((size_t)N));
+  DFB_CHECK(icnt.alloc((size_t)n_items + 1));
+  DFB_CUDA(cudaMemsetAsync(icnt, 0, sizeof(int) * ((size_t)n_items + 1), st));
+  k_pair_meta<<<ceil_div(n_cta, 128), 128, 0, st>>>(N, n_cta, R, p->row_ptr, p->col_ind, p->pr_grp_item, p->pr_meta, row_pair);
+  DFB_LAUNCH_CHECK();
+  const int cgrid = ceil_div((i64)E * 16, 256);
+  k_pair_contrib<false><<<cgrid, 256, 0, st>>>(E, R, p->ien, p->row_ptr, p->col_ind, p->v2c_ptr, p->v2c, slot32, p->pr_grp_item,
+                                               row_pair, icnt, nullptr, nullptr, flags);
+  DFB_LAUNCH_CHECK();
+  tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, icnt.p, p->pr_item_ptr, n_items + 1, st);
+  DFB_CHECK(tmp.alloc(tmp_bytes));
+  cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, icnt.p, p->pr_item_ptr, n_items + 1, st);
+  DFB_LAUNCH_CHECK();
+  int n_contrib = 0;
+  DFB_CUDA(cudaMemcpyAsync(&n_contrib, p->pr_item_ptr + n_items, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DFB_CUDA(cudaStreamSynchronize(st));
+  DFB_CHECK(contrib32.alloc((size_t)n_contrib));
+  DFB_CUDA(cudaMemsetAsync(icnt, 0, sizeof(int) * ((size_t)n_items + 1), st));
+  k_pair_contrib<true><<<cgrid, 256, 0, st>>>(E, R, p->ien, p->row_ptr, p->col_ind, p->v2c_ptr, p->v2c, slot32, p->pr_grp_item,
+                                              row_pair, icnt, p->pr_item_ptr, contrib32, flags);
+  DFB_LAUNCH_CHECK();
+  k_sort_contrib<<<ceil_div(n_items, 128), 128, 0, st>>>(n_items, p->pr_item_ptr, contrib32);
+  DFB_LAUNCH_CHECK();
+  // ---- distinct elements of every row group ----
+  DFB_CHECK(gcnt.alloc((size_t)n_cta + 1));
+  DFB_CUDA(cudaMemsetAsync(gcnt, 0, sizeof(int) * ((size_t)n_cta + 1), st));
+  DFB_CUDA(cudaMalloc(&p->pr_elem_ptr, sizeof(int) * ((size_t)n_cta + 1)));
+  k_group_elems<false><<<ceil_div(n_cta, 64), 64, 0, st>>>(N, n_cta, R, p->v2c_ptr, p->v2c, gcnt, nullptr, nullptr, flags.p + 1);
+  DFB_LAUNCH_CHECK();
+  tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, gcnt.p, p->pr_elem_ptr, n_cta + 1, st);
+  DFB_CHECK(tmp.alloc(tmp_bytes));
+  cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, gcnt.p, p->pr_elem_ptr, n_cta + 1, st);
+  DFB_LAUNCH_CHECK();
+  k_max_int<<<ceil_div(n_cta, 256), 256, 0, st>>>(n_cta, p->pr_elem_ptr, flags.p + 2);
+  DFB_LAUNCH_CHECK();
+  int total_ge = 0, h_flags[3] = {0, 0, 0};
+  DFB_CUDA(cudaMemcpyAsync(&total_ge, p->pr_elem_ptr + n_cta, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DFB_CUDA(cudaMemcpyAsync(h_flags, flags, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  DFB_CUDA(cudaStreamSynchronize(st));
+  p->pr_rows = R; p->pr_n_cta = n_cta; p->pr_n_items = n_items; p->pr_max_elems = h_flags[2];
+  if (h_flags[0] || h_flags[1] || h_flags[2] > PAIR_MAX_STAGED || h_flags[2] >= 4096) {
+    // degenerate elements or a row group whose element records do not fit shared memory: the caller falls back to the pull variant
+    cudaFree(p->pr_grp_item); cudaFree(p->pr_meta); cudaFree(p->pr_item_ptr); cudaFree(p->pr_elem_ptr);
+    p->pr_grp_item = nullptr; p->pr_meta = nullptr; p->pr_item_ptr = nullptr; p->pr_elem_ptr = nullptr;
+    p->pr_state = -1;
+    return DFB_OK;
+  }
+  DFB_CUDA(cudaMalloc(&p->pr_elems, sizeof(int) * (size_t)std::max(1, total_ge)));
+  k_group_elems<true><<<ceil_div(n_cta, 64), 64, 0, st>>>(N, n_cta, R, p->v2c_ptr, p->v2c, nullptr, p->pr_elem_ptr, p->pr_elems, nullptr);
+  DFB_LAUNCH_CHECK();
+  DFB_CUDA(cudaMalloc(&p->pr_contrib, sizeof(unsigned short) * (size_t)std::max(1, n_contrib)));
+  k_pair_contrib16<<<ceil_div(n_items, 128), 128, 0, st>>>(n_items, R, p->pr_meta, p->pr_item_ptr, contrib32, p->pr_elem_ptr, p->pr_elems,
+                                                           p->pr_contrib);
+  DFB_LAUNCH_CHECK();
+  DFB_CUDA(cudaStreamSynchronize(st));
+  p->pr_bytes = sizeof(int) * 2 * ((size_t)n_cta + 1) + sizeof(uint2) * (size_t)n_items + sizeof(int) * ((size_t)n_items + 1) +
+                sizeof(int) * (size_t)total_ge + sizeof(unsigned short) * (size_t)n_contrib;
+  p->pr_state = 1;
   return DFB_OK;
 }
 
@@ -530,12 +715,14 @@ void dfb_plan_destroy(dfb_plan* p) {
   cudaFree(p->v2c_ptr); cudaFree(p->v2c); cudaFree(p->slot); cudaFree(p->elemF);
   cudaFree(p->row_item); cudaFree(p->item_meta); cudaFree(p->item_ptr); cudaFree(p->contrib); cudaFree(p->prec);
   cudaFree(p->cta_elem_ptr); cudaFree(p->cta_elems); cudaFree(p->contrib16);
+  cudaFree(p->pr_grp_item); cudaFree(p->pr_meta); cudaFree(p->pr_item_ptr); cudaFree(p->pr_contrib); cudaFree(p->pr_elem_ptr);
+  cudaFree(p->pr_elems);
   delete p;
 }
 
 size_t dfb_plan_bytes(const dfb_plan* p) {
   if (!p) return 0;
-  return sizeof(int) * ((size_t)p->N + 1) + sizeof(int) * (size_t)p->E * 4 + (size_t)p->E * 16 + p->elemF_bytes + p->pull_bytes;
+  return sizeof(int) * ((size_t)p->N + 1) + sizeof(int) * (size_t)p->E * 4 + (size_t)p->E * 16 + p->elemF_bytes + p->pull_bytes + p->pr_bytes;
 }
 
 }  // extern "C"

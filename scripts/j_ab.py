@@ -1,0 +1,43 @@
+"""A/B of the Jacobian assembly variants on one GPU: kernel time (CUDA events, median of 20) and agreement with the pull variant.
+usage: python scripts/j_ab.py [m]"""
+import ctypes as C
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from dedflow_b200 import api, boxmesh  # noqa: E402
+
+m = int(sys.argv[1]) if len(sys.argv) > 1 else 55
+mesh = boxmesh.make_box(m)
+N, E = mesh.num_node, mesh.num_tet
+wg, dwg = boxmesh.state_random(N)
+d_wg, d_dwg = torch.from_numpy(wg).cuda(), torch.from_numpy(dwg).cuda()
+P = lambda t: C.c_void_p(t.data_ptr())
+ref = None
+for name, env in (("pull", {"DFB_J_VARIANT": "pull"}), ("pairs R=8", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ROWS": "8"}),
+                  ("pairs R=16", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ROWS": "16"}), ("fused", {"DFB_J_VARIANT": "fused"})):
+    os.environ.update(env)
+    fs = api.FlowSystem(mesh)
+    st = fs._stream()
+    call = lambda: fs.L.dfb_assemble_tet(fs.plan, P(fs.xg), P(d_wg), P(d_dwg), None, P(fs.A00), P(fs.A01), P(fs.A10), P(fs.A11), 1, 1, st)
+    for _ in range(3):
+        assert call() == 0, fs.L.dfb_last_error()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(20):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); call(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    vals = [x.clone() for x in fs.blocks()]
+    if ref is None:
+        ref = vals
+        d = 0.0
+    else:
+        d = max(float((x - y).abs().max() / y.abs().max()) for x, y in zip(vals, ref))
+    print(f"{name:12s} m={m} E={E}: J kernels {np.median(ts) * 1e3:8.1f} us   max rel diff vs pull {d:.2e}   plan {fs.L.dfb_plan_bytes(fs.plan) / 1e6:.0f} MB", flush=True)
+    fs.close()

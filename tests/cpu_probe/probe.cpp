@@ -31,6 +31,30 @@ extern "C" void probe_tet(int n, int N, const int32_t* ien, const double* xg, co
   }
 }
 
+// the pair formulation of the Jacobian (k_pairJ): element record -> pair accumulators -> the same [a][b][ii*4+jj] layout
+extern "C" void probe_tet_pairs(int n, int N, const int32_t* ien, const double* xg, const double* wg, const double* dwg,
+                                double* eJ /* n*16*16 */) {
+  for (int e = 0; e < n; e++) {
+    double x[4][3], val[6][4], dval[6][4], u[4][3], rec[JREC];
+    load(e, N, ien, xg, wg, dwg, x, val, dval);
+    Geom g; geometry(x, g);
+    for (int a = 0; a < 4; a++) for (int d = 0; d < 3; d++) u[a][d] = val[d][a];
+    JPrep p; jac_prep(g, u, p);
+    jrec_store(g, p, rec);
+    for (int a = 0; a < 4; a++) {
+      double* daa = eJ + ((size_t)e * 16 + a * 4 + a) * 16;
+      for (int v = 0; v < 16; v++) daa[v] = 0.0;
+      jrec_diag(rec + a * 10, rec + 40, a, daa);
+      for (int b = a + 1; b < 4; b++) {
+        double acc[24];
+        for (int v = 0; v < 24; v++) acc[v] = 0.0;
+        jrec_pair(rec + a * 10, rec + b * 10, rec + 40, a, b, acc);
+        jrec_pair_blocks(acc, eJ + ((size_t)e * 16 + a * 4 + b) * 16, eJ + ((size_t)e * 16 + b * 4 + a) * 16);
+      }
+    }
+  }
+}
+
 extern "C" void probe_face(int nf, const int32_t* f2e, const int32_t* forn, int N, const int32_t* ien, const double* xg,
                            const double* wg, const double* dwg, double* eF, double* eJ) {
   for (int f = 0; f < nf; f++) {

@@ -111,6 +111,36 @@ def test_assembly_matches_oracle(api, oracle, m, shuffle, state, mode):
     fs.close()
 
 
+@pytest.mark.parametrize("variant", ["pairs", "pull", "fused"])
+@pytest.mark.parametrize("m,shuffle", [(2, False), (7, True), (16, False)])
+def test_jacobian_variants_match_oracle(api, oracle, monkeypatch, variant, m, shuffle):
+    """The three atomic-free Jacobian assemblies (node pairs = default, pull, fused row gather; DFB_J_VARIANT is read per call),
+    overwrite and accumulate, against the oracle."""
+    monkeypatch.setenv("DFB_J_VARIANT", variant)
+    mesh = shuffled_mesh(m) if shuffle else boxmesh.make_box(m)
+    fs, wg, dwg = make_pair(api, oracle, mesh, "B")
+    ref = oracle_system(oracle, mesh, wg, dwg)
+    d_wg, d_dwg = torch.from_numpy(wg).cuda(), torch.from_numpy(dwg).cuda()
+    for a in fs.blocks():
+        a.fill_(-2.0)
+    fs.assemble_system(d_wg, d_dwg, J=True, mode="gather")
+    for got, want, name in zip(fs.blocks(), ref["blocks"], ("A00", "A01", "A10", "A11")):
+        assert rel(got.cpu().numpy(), want) <= TOL_ASM, (variant, name)
+    # accumulate (overwrite = 0) on top of zeros: the bare tet part, twice
+    import ctypes as C
+    from dedflow_b200 import lib as _lib
+    ref0 = oracle_system(oracle, mesh, wg, dwg, faces=False, dirichlet=False)
+    for a in fs.blocks():
+        a.zero_()
+    ptrs = [C.c_void_p(a.data_ptr()) for a in fs.blocks()]
+    for _ in range(2):
+        _lib.check(fs.L.dfb_assemble_tet(fs.plan, C.c_void_p(fs.xg.data_ptr()), C.c_void_p(d_wg.data_ptr()),
+                                         C.c_void_p(d_dwg.data_ptr()), None, *ptrs, 1, 0, fs._stream()))
+    for got, want, name in zip(fs.blocks(), ref0["blocks"], ("A00", "A01", "A10", "A11")):
+        assert rel(got.cpu().numpy(), 2.0 * want) <= TOL_ASM, (variant, name, "accumulate")
+    fs.close()
+
+
 def test_assembly_interior_only_and_accumulate(api, oracle):
     """F / J without faces and Dirichlet (the bare AssembleSystemTet), and phi/T residual slots before zeroing."""
     mesh = shuffled_mesh(5)

@@ -191,9 +191,12 @@ def test_kernel_element_math_matches_oracle(oracle, probe):
         probe.probe_tet(E, N, vp(m.ien), vp(m.xg), vp(wg), vp(dwg), vp(eF), vp(eJ))
         oF, oJ, _, _ = oracle.tet_elements(N, m.ien, m.xg, wg, dwg)
         assert np.abs(eF - oF).max() <= 1e-12 * np.abs(oF).max()
+        eP = np.zeros((E, 4, 4, 4, 4))     # the node-pair formulation of k_pairJ (element record -> pair accumulators)
+        probe.probe_tet_pairs(E, N, vp(m.ien), vp(m.xg), vp(wg), vp(dwg), vp(eP))
         for i0, i1, j0, j1 in ((0, 3, 0, 3), (0, 3, 3, 4), (3, 4, 0, 3), (3, 4, 3, 4)):
             a, b = eJ[..., i0:i1, j0:j1], oJ[..., i0:i1, j0:j1]
             assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max()
+            assert np.abs(eP[..., i0:i1, j0:j1] - b).max() <= 1e-12 * np.abs(b).max()
         for b in range(6):
             f2e, forn = m.bound_faces(b)
             assert set(np.unique(forn)) == {0, 1, 2, 3}
