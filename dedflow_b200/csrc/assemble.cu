@@ -73,10 +73,17 @@ __device__ __forceinline__ void scatter_block(f64* __restrict__ A00, f64* __rest
 // ------------------------------------------------------------------------------------------------------------
 // F: one thread per element
 // ------------------------------------------------------------------------------------------------------------
-template <int MODE>  // 0: write scratch[e*24..] (64-byte padded corner slots measured slower), 1: atomic scatter, 2: plain scatter of a color batch
+// position of every corner (e*4+a) inside the node-sorted corner list v2c: the element kernel writes its four 48-byte corner
+// residuals in NODE-MAJOR order, so that the node gather streams contiguous memory (every fetched sector fully used)
+__global__ void k_corner_pos(int n_corner, const int* __restrict__ v2c, int* __restrict__ cpos) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_corner) cpos[v2c[p]] = p;
+}
+
+template <int MODE>  // 0: write scratch[cpos[corner]*6..] (node-major), 1: atomic scatter, 2: plain scatter of a color batch
 __global__ void __launch_bounds__(128) k_elemF(int n, const int* __restrict__ elem_ids, int N, const int* __restrict__ ien,
                                                const f64* __restrict__ xg, const f64* __restrict__ wg,
-                                               const f64* __restrict__ dwg, f64* __restrict__ out) {
+                                               const f64* __restrict__ dwg, f64* __restrict__ out, const int* __restrict__ cpos) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   int e = elem_ids ? elem_ids[t] : t;
@@ -101,11 +108,14 @@ __global__ void __launch_bounds__(128) k_elemF(int n, const int* __restrict__ el
   f64 eF[4][6];
   residual(g, val, dval, eF);
   if (MODE == 0) {
-    f64* dst = out + (size_t)e * 24;
+    const int4 cp = __ldg(reinterpret_cast<const int4*>(cpos) + e);
+    const int pos[4] = {cp.x, cp.y, cp.z, cp.w};
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int a = 0; a < 4; a++) {
+      f64* dst = out + (size_t)pos[a] * 6;
 #pragma unroll
-      for (int i = 0; i < 6; i += 2) *reinterpret_cast<double2*>(dst + a * 6 + i) = make_double2(eF[a][i], eF[a][i + 1]);
+      for (int i = 0; i < 6; i += 2) *reinterpret_cast<double2*>(dst + i) = make_double2(eF[a][i], eF[a][i + 1]);
+    }
   } else {
 #pragma unroll
     for (int a = 0; a < 4; a++) {
@@ -121,13 +131,13 @@ __global__ void __launch_bounds__(128) k_elemF(int n, const int* __restrict__ el
 }
 
 // node gather: F[node] (+)= sum over the node's corners, ascending corner id
-__global__ void k_gatherF(int N, int n_rows, const int* __restrict__ v2c_ptr, const int* __restrict__ v2c,
-                          const f64* __restrict__ scratch, f64* __restrict__ F, int overwrite) {
+__global__ void k_gatherF(int N, int n_rows, const int* __restrict__ v2c_ptr, const f64* __restrict__ scratch,
+                          f64* __restrict__ F, int overwrite) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows) return;
   f64 s[6] = {0, 0, 0, 0, 0, 0};
   for (int p = v2c_ptr[i]; p < v2c_ptr[i + 1]; p++) {
-    const f64* src = scratch + (size_t)v2c[p] * 6;
+    const f64* src = scratch + (size_t)p * 6;
     double2 a = *reinterpret_cast<const double2*>(src), b = *reinterpret_cast<const double2*>(src + 2),
             c = *reinterpret_cast<const double2*>(src + 4);
     s[0] += a.x; s[1] += a.y; s[2] += b.x; s[3] += b.y; s[4] += c.x; s[5] += c.y;
@@ -569,52 +579,78 @@ __device__ __forceinline__ void load_chunks5(const double2* __restrict__ p, f64 
   for (int c = 0; c < 5; c++) { const double2 v = p[c]; out[2 * c] = v.x; out[2 * c + 1] = v.y; }
 }
 
+__device__ __forceinline__ void pair_prep_element(const int4 nd, const f64* __restrict__ xg, const f64* __restrict__ wg,
+                                                  double2* __restrict__ dst) {
+  const int nodes[4] = {nd.x, nd.y, nd.z, nd.w};
+  f64 x[4][3], u[4][3];
+  load_xyz(xg, nodes, x);
+  load_xyz(wg, nodes, u);
+  Geom gm;
+  geometry(x, gm);
+  JPrep p;
+  jac_prep(gm, u, p);
+  f64 rec[JREC];
+  jrec_store(gm, p, rec);
+#pragma unroll
+  for (int c = 0; c < PAIR_SREC; c++) dst[c] = make_double2(rec[2 * c], rec[2 * c + 1]);
+}
+
 template <int OVERWRITE>
-__global__ void __launch_bounds__(192, 2) k_pairJ(int N, int n_rows, int R, const int* __restrict__ grp_item,
+__global__ void __launch_bounds__(192, 2) k_pairJ(int N, int n_rows, int R, const int4* __restrict__ grp,
                                                   const uint2* __restrict__ item_meta, const int* __restrict__ item_ptr,
-                                                  const unsigned short* __restrict__ contrib, const int* __restrict__ elem_ptr,
-                                                  const int* __restrict__ elems, const int* __restrict__ ien,
+                                                  const unsigned short* __restrict__ contrib, const int4* __restrict__ enodes,
                                                   const f64* __restrict__ xg, const f64* __restrict__ wg,
                                                   const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
                                                   f64* __restrict__ A00, f64* __restrict__ A01, f64* __restrict__ A10,
                                                   f64* __restrict__ A11) {
   extern __shared__ __align__(16) unsigned char pair_smem[];
   double2* srec = reinterpret_cast<double2*>(pair_smem);
-  const int g = blockIdx.x;
-  const int e0 = __ldg(elem_ptr + g), ne = __ldg(elem_ptr + g + 1) - e0;
-  // ---- phase A: element records into shared memory ----
-  for (int r = threadIdx.x; r < ne; r += blockDim.x) {
-    const int e = __ldg(elems + e0 + r);
-    int nodes[4];
-    load_nodes(ien, e, nodes);
-    f64 x[4][3], u[4][3];
-    load_xyz(xg, nodes, x);
-    load_xyz(wg, nodes, u);
-    Geom gm;
-    geometry(x, gm);
-    JPrep p;
-    jac_prep(gm, u, p);
-    f64 rec[JREC];
-    jrec_store(gm, p, rec);
-    double2* dst = srec + r * PAIR_SREC;
-#pragma unroll
-    for (int c = 0; c < PAIR_SREC; c++) dst[c] = make_double2(rec[2 * c], rec[2 * c + 1]);
+  const int4 gd = __ldg(grp + blockIdx.x);
+  const int e0 = gd.x, ne = gd.y, it0 = gd.z, n_it = gd.w;
+  const int nd = 4 * R;
+  // The dependent-load chains of both phases start together: group -> {element nodes, item meta / list bounds} ->
+  // {coordinates + velocities, first list entry}.  (With ~12 resident warps per SM these chains, not the arithmetic, set the pace.)
+  uint2 meta0 = make_uint2(0xffffffffu, 0u);
+  int cs0 = 0, ce0 = 0;
+  if ((int)threadIdx.x < n_it) {
+    meta0 = item_meta[it0 + threadIdx.x];
+    cs0 = __ldg(item_ptr + it0 + threadIdx.x);
+    ce0 = __ldg(item_ptr + it0 + threadIdx.x + 1);
   }
+  // ---- phase A: element records into shared memory (node ids fetched one trip ahead) ----
+  int4 nd_cur = make_int4(0, 0, 0, 0);
+  if ((int)threadIdx.x < ne) nd_cur = __ldg(enodes + e0 + threadIdx.x);
+  unsigned first0 = 0u;
+  for (int r = threadIdx.x; r < ne; r += blockDim.x) {
+    int4 nd_next = nd_cur;
+    if (r + (int)blockDim.x < ne) nd_next = __ldg(enodes + e0 + r + blockDim.x);
+    pair_prep_element(nd_cur, xg, wg, srec + r * PAIR_SREC);
+    nd_cur = nd_next;
+  }
+  if (cs0 < ce0) first0 = contrib[cs0];
   __syncthreads();
   // ---- phase B: work items ----
-  const int it0 = __ldg(grp_item + g), n_it = __ldg(grp_item + g + 1) - it0;
-  const int nd = 4 * R;
   for (int base = 0; base < n_it; base += blockDim.x) {
     const int t = base + threadIdx.x;
     const int item = it0 + t;
+    uint2 meta = meta0;
+    int cs = cs0, ce = ce0;
+    unsigned nxt = first0;
+    if (base > 0) {
+      meta = make_uint2(0xffffffffu, 0u);
+      cs = ce = 0;
+      if (t < n_it) {
+        meta = item_meta[item];
+        cs = __ldg(item_ptr + item);
+        ce = __ldg(item_ptr + item + 1);
+      }
+      nxt = cs < ce ? contrib[cs] : 0u;
+    }
     if (base + (int)(threadIdx.x & ~31u) < nd) {
       // a warp of diagonal items (nd is a multiple of 32 and n_it >= nd: every lane has an item)
-      const uint2 meta = item_meta[item];
-      const int cs = __ldg(item_ptr + item), ce = __ldg(item_ptr + item + 1);
       f64 acc[16];
 #pragma unroll
       for (int v = 0; v < 16; v++) acc[v] = 0.0;
-      unsigned nxt = cs < ce ? contrib[cs] : 0u;
       for (int idx = cs; idx < ce; idx++) {
         const unsigned c16 = nxt;
         if (idx + 1 < ce) nxt = contrib[idx + 1];
@@ -646,12 +682,15 @@ __global__ void __launch_bounds__(192, 2) k_pairJ(int N, int n_rows, int R, cons
         }
       }
     } else if (t < n_it) {
-      const uint2 meta = item_meta[item];
-      const int cs = __ldg(item_ptr + item), ce = __ldg(item_ptr + item + 1);
+      // row pointers of both rows are fetched before the accumulation loop: their latency hides behind it
+      const int row = (int)meta.x;
+      const int kij = (int)(meta.y & 0xffu), kji = (int)((meta.y >> 16) & 0xffu);
+      const int start = __ldg(row_ptr + row), len = __ldg(row_ptr + row + 1) - start;
+      const int j = __ldg(col_ind + start + kij);
+      const int sj = __ldg(row_ptr + j), lj = __ldg(row_ptr + j + 1) - sj;
       f64 acc[24];
 #pragma unroll
       for (int v = 0; v < 24; v++) acc[v] = 0.0;
-      unsigned nxt = cs < ce ? contrib[cs] : 0u;
       for (int idx = cs; idx < ce; idx++) {
         const unsigned c16 = nxt;
         if (idx + 1 < ce) nxt = contrib[idx + 1];
@@ -664,18 +703,11 @@ __global__ void __launch_bounds__(192, 2) k_pairJ(int N, int n_rows, int R, cons
         T[0] = t0.x; T[1] = t0.y; T[2] = t1.x; T[3] = t1.y; T[4] = t2.x; T[5] = t2.y;
         jrec_pair(A, B, T, a, b, acc);
       }
-      const int row = (int)meta.x;
       if (row < n_rows) {
         f64 ab[16], ba[16];
         jrec_pair_blocks(acc, ab, ba);
-        const int kij = (int)(meta.y & 0xffu), kji = (int)((meta.y >> 16) & 0xffu);
-        const int start = __ldg(row_ptr + row), len = __ldg(row_ptr + row + 1) - start;
         scatter_block<OVERWRITE ? 2 : 0>(A00, A01, A10, A11, (size_t)start, len, kij, ab);
-        const int j = __ldg(col_ind + start + kij);
-        if (j < n_rows) {
-          const int sj = __ldg(row_ptr + j), lj = __ldg(row_ptr + j + 1) - sj;
-          scatter_block<OVERWRITE ? 2 : 0>(A00, A01, A10, A11, (size_t)sj, lj, kji, ba);
-        }
+        if (j < n_rows) scatter_block<OVERWRITE ? 2 : 0>(A00, A01, A10, A11, (size_t)sj, lj, kji, ba);
       }
     }
   }
@@ -789,21 +821,24 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
   if (d_F) {
     if (mode == DFB_MODE_GATHER) {
       if (!P->elemF) {
-        P->elemF_bytes = sizeof(f64) * 24 * (size_t)E;
-        DFB_CUDA(cudaMalloc(&P->elemF, P->elemF_bytes));
+        P->elemF_bytes = sizeof(f64) * 24 * (size_t)E + sizeof(int) * 4 * (size_t)E;
+        DFB_CUDA(cudaMalloc(&P->elemF, sizeof(f64) * 24 * (size_t)E));
+        DFB_CUDA(cudaMalloc(&P->cpos, sizeof(int) * 4 * (size_t)E));
+        k_corner_pos<<<ceil_div(4 * (i64)E, 256), 256, 0, st>>>(4 * E, P->v2c, P->cpos);
+        DFB_LAUNCH_CHECK();
       }
-      k_elemF<0><<<ceil_div(E, 128), 128, 0, st>>>(E, nullptr, N, P->ien, d_xg, d_wg, d_dwg, P->elemF);
+      k_elemF<0><<<ceil_div(E, 128), 128, 0, st>>>(E, nullptr, N, P->ien, d_xg, d_wg, d_dwg, P->elemF, P->cpos);
       DFB_LAUNCH_CHECK();
-      k_gatherF<<<ceil_div(P->n_rows, 128), 128, 0, st>>>(N, P->n_rows, P->v2c_ptr, P->v2c, P->elemF, d_F, overwrite);
+      k_gatherF<<<ceil_div(P->n_rows, 128), 128, 0, st>>>(N, P->n_rows, P->v2c_ptr, P->elemF, d_F, overwrite);
       DFB_LAUNCH_CHECK();
     } else if (mode == DFB_MODE_ATOMIC) {
-      k_elemF<1><<<ceil_div(E, 128), 128, 0, st>>>(E, nullptr, N, P->ien, d_xg, d_wg, d_dwg, d_F);
+      k_elemF<1><<<ceil_div(E, 128), 128, 0, st>>>(E, nullptr, N, P->ien, d_xg, d_wg, d_dwg, d_F, nullptr);
       DFB_LAUNCH_CHECK();
     } else {
       for (int b = 0; b < P->num_batch; b++) {
         int n = P->batch_offset[b + 1] - P->batch_offset[b];
         if (n == 0) break;  // reference assemble.cu:1565-1567
-        k_elemF<2><<<ceil_div(n, 128), 128, 0, st>>>(n, P->batch_ind + P->batch_offset[b], N, P->ien, d_xg, d_wg, d_dwg, d_F);
+        k_elemF<2><<<ceil_div(n, 128), 128, 0, st>>>(n, P->batch_ind + P->batch_offset[b], N, P->ien, d_xg, d_wg, d_dwg, d_F, nullptr);
         DFB_LAUNCH_CHECK();
       }
     }
@@ -837,11 +872,11 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
           }
           const int R = P->pr_rows, ncta = ceil_div(P->n_rows, R), nthr = 96 * (R / 8);
           if (overwrite)
-            k_pairJ<1><<<ncta, nthr, smem, st>>>(N, P->n_rows, R, P->pr_grp_item, P->pr_meta, P->pr_item_ptr, P->pr_contrib, P->pr_elem_ptr,
-                                                 P->pr_elems, P->ien, d_xg, d_wg, P->row_ptr, P->col_ind, d_A00, d_A01, d_A10, d_A11);
+            k_pairJ<1><<<ncta, nthr, smem, st>>>(N, P->n_rows, R, P->pr_grp, P->pr_meta, P->pr_item_ptr, P->pr_contrib, P->pr_enodes,
+                                                 d_xg, d_wg, P->row_ptr, P->col_ind, d_A00, d_A01, d_A10, d_A11);
           else
-            k_pairJ<0><<<ncta, nthr, smem, st>>>(N, P->n_rows, R, P->pr_grp_item, P->pr_meta, P->pr_item_ptr, P->pr_contrib, P->pr_elem_ptr,
-                                                 P->pr_elems, P->ien, d_xg, d_wg, P->row_ptr, P->col_ind, d_A00, d_A01, d_A10, d_A11);
+            k_pairJ<0><<<ncta, nthr, smem, st>>>(N, P->n_rows, R, P->pr_grp, P->pr_meta, P->pr_item_ptr, P->pr_contrib, P->pr_enodes,
+                                                 d_xg, d_wg, P->row_ptr, P->col_ind, d_A00, d_A01, d_A10, d_A11);
           DFB_LAUNCH_CHECK();
           done = true;
         }

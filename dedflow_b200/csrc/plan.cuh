@@ -20,7 +20,8 @@ struct dfb_plan {
   std::vector<int> batch_offset;
   const int* batch_ind = nullptr;  // borrowed
   // lazily allocated element-residual scratch for the deterministic F gather (24 doubles per element)
-  mutable f64* elemF = nullptr;
+  mutable f64* elemF = nullptr;      // corner residuals in node-major order: slot cpos[e*4+a]
+  mutable int* cpos = nullptr;       // [4E] position of corner e*4+a in v2c
   mutable size_t elemF_bytes = 0;
   // lazily built work lists of the PULL Jacobian assembly (setup.cu build_pull): one work item per off-diagonal nodal
   // nonzero plus four "virtual" items per diagonal entry (its contributions dealt round-robin), rows padded to multiples
@@ -46,6 +47,8 @@ struct dfb_plan {
   // (4*pr_rows: whole warps), then one item per UPPER off-diagonal nonzero (i,j), j > i, which also produces (j,i).
   mutable int pr_state = 0;            // 0: not built, 1: usable, -1: a group does not fit shared memory (fall back to pull)
   mutable int pr_rows = 0, pr_n_cta = 0, pr_n_items = 0, pr_max_elems = 0;
+  mutable int4* pr_grp = nullptr;       // [pr_n_cta] {first staged element, #elements, first item, #items}: one 16-byte load per CTA
+  mutable int4* pr_enodes = nullptr;    // the four node ids of every staged element (parallel to pr_elems): skips elems -> ien
   mutable int* pr_grp_item = nullptr;   // [pr_n_cta+1] first item of every group
   mutable uint2* pr_meta = nullptr;     // [pr_n_items] {row i (0xffffffff: padding), k_ij | 0x100 diagonal | k_ji << 16}
   mutable int* pr_item_ptr = nullptr;   // [pr_n_items+1] offsets into pr_contrib

@@ -509,6 +509,14 @@ __global__ void k_pair_contrib16(int n_items, int R, const uint2* __restrict__ m
   }
 }
 
+__global__ void k_pair_finalize(int n_cta, int total_ge, const int* __restrict__ grp_item, const int* __restrict__ elem_ptr,
+                                const int* __restrict__ elems, const int* __restrict__ ien, int4* __restrict__ grp,
+                                int4* __restrict__ enodes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_cta) grp[i] = make_int4(elem_ptr[i], elem_ptr[i + 1] - elem_ptr[i], grp_item[i], grp_item[i + 1] - grp_item[i]);
+  if (i < total_ge) enodes[i] = *reinterpret_cast<const int4*>(ien + (size_t)elems[i] * 4);
+}
+
 int build_pairs(const dfb_plan* p, int R, cudaStream_t st) {
   if (p->pr_state != 0) return DFB_OK;
   if (!p->slot) { set_error("pair assembly needs a plan with a sparsity pattern"); return DFB_ERR_ARG; }
@@ -592,8 +600,13 @@ int build_pairs(const dfb_plan* p, int R, cudaStream_t st) {
   k_pair_contrib16<<<ceil_div(n_items, 128), 128, 0, st>>>(n_items, R, p->pr_meta, p->pr_item_ptr, contrib32, p->pr_elem_ptr, p->pr_elems,
                                                            p->pr_contrib);
   DFB_LAUNCH_CHECK();
+  DFB_CUDA(cudaMalloc(&p->pr_grp, sizeof(int4) * (size_t)n_cta));
+  DFB_CUDA(cudaMalloc(&p->pr_enodes, sizeof(int4) * (size_t)std::max(1, total_ge)));
+  k_pair_finalize<<<ceil_div(std::max(n_cta, total_ge), 256), 256, 0, st>>>(n_cta, total_ge, p->pr_grp_item, p->pr_elem_ptr, p->pr_elems, p->ien,
+                                                                          p->pr_grp, p->pr_enodes);
+  DFB_LAUNCH_CHECK();
   DFB_CUDA(cudaStreamSynchronize(st));
-  p->pr_bytes = sizeof(int) * 2 * ((size_t)n_cta + 1) + sizeof(uint2) * (size_t)n_items + sizeof(int) * ((size_t)n_items + 1) +
+  p->pr_bytes = sizeof(int4) * ((size_t)n_cta + (size_t)total_ge) + sizeof(int) * 2 * ((size_t)n_cta + 1) + sizeof(uint2) * (size_t)n_items + sizeof(int) * ((size_t)n_items + 1) +
                 sizeof(int) * (size_t)total_ge + sizeof(unsigned short) * (size_t)n_contrib;
   p->pr_state = 1;
   return DFB_OK;
@@ -712,11 +725,11 @@ int dfb_plan_set_rows(dfb_plan* p, int n_rows) {
 
 void dfb_plan_destroy(dfb_plan* p) {
   if (!p) return;
-  cudaFree(p->v2c_ptr); cudaFree(p->v2c); cudaFree(p->slot); cudaFree(p->elemF);
+  cudaFree(p->v2c_ptr); cudaFree(p->v2c); cudaFree(p->slot); cudaFree(p->elemF); cudaFree(p->cpos);
   cudaFree(p->row_item); cudaFree(p->item_meta); cudaFree(p->item_ptr); cudaFree(p->contrib); cudaFree(p->prec);
   cudaFree(p->cta_elem_ptr); cudaFree(p->cta_elems); cudaFree(p->contrib16);
   cudaFree(p->pr_grp_item); cudaFree(p->pr_meta); cudaFree(p->pr_item_ptr); cudaFree(p->pr_contrib); cudaFree(p->pr_elem_ptr);
-  cudaFree(p->pr_elems);
+  cudaFree(p->pr_elems); cudaFree(p->pr_grp); cudaFree(p->pr_enodes);
   delete p;
 }
 

@@ -39,5 +39,15 @@ for name, env in (("pull", {"DFB_J_VARIANT": "pull"}), ("pairs R=8", {"DFB_J_VAR
         d = 0.0
     else:
         d = max(float((x - y).abs().max() / y.abs().max()) for x, y in zip(vals, ref))
+    Fv = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    callF = lambda: fs.L.dfb_assemble_tet(fs.plan, P(fs.xg), P(d_wg), P(d_dwg), P(Fv), None, None, None, None, 1, 1, st)
+    tf = []
+    for k in range(13):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); assert callF() == 0; b.record()
+        torch.cuda.synchronize()
+        if k >= 3:
+            tf.append(a.elapsed_time(b))
+    print(f"   F kernels {np.median(tf) * 1e3:8.1f} us", flush=True)
     print(f"{name:12s} m={m} E={E}: J kernels {np.median(ts) * 1e3:8.1f} us   max rel diff vs pull {d:.2e}   plan {fs.L.dfb_plan_bytes(fs.plan) / 1e6:.0f} MB", flush=True)
     fs.close()
