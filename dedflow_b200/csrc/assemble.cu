@@ -595,8 +595,8 @@ __device__ __forceinline__ void pair_prep_element(const int4 nd, const f64* __re
   for (int c = 0; c < PAIR_SREC; c++) dst[c] = make_double2(rec[2 * c], rec[2 * c + 1]);
 }
 
-template <int OVERWRITE>
-__global__ void __launch_bounds__(192, 2) k_pairJ(int N, int n_rows, int R, const int4* __restrict__ grp,
+template <int OVERWRITE, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_pairJ(int N, int n_rows, int R, const int4* __restrict__ grp,
                                                   const uint2* __restrict__ item_meta, const int* __restrict__ item_ptr,
                                                   const unsigned short* __restrict__ contrib, const int4* __restrict__ enodes,
                                                   const f64* __restrict__ xg, const f64* __restrict__ wg,
@@ -861,22 +861,30 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
           const int r = e ? atoi(e) : 8;
           return (r >= 8 && r <= 16 && (r & 7) == 0) ? r : 8;
         }();
-        DFB_CHECK(build_pairs(P, pair_rows, st));
+        DFB_CHECK(build_pairs(P, pair_rows, d_xg, st));
         if (P->pr_state == 1) {
           const size_t smem = (size_t)std::max(1, P->pr_max_elems) * PAIR_SREC * sizeof(double2);
-          static size_t pair_smem_set = 0;
-          if (smem > pair_smem_set) {
-            DFB_CUDA(cudaFuncSetAttribute(k_pairJ<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            DFB_CUDA(cudaFuncSetAttribute(k_pairJ<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            pair_smem_set = smem;
-          }
-          const int R = P->pr_rows, ncta = ceil_div(P->n_rows, R), nthr = 96 * (R / 8);
-          if (overwrite)
-            k_pairJ<1><<<ncta, nthr, smem, st>>>(N, P->n_rows, R, P->pr_grp, P->pr_meta, P->pr_item_ptr, P->pr_contrib, P->pr_enodes,
-                                                 d_xg, d_wg, P->row_ptr, P->col_ind, d_A00, d_A01, d_A10, d_A11);
-          else
-            k_pairJ<0><<<ncta, nthr, smem, st>>>(N, P->n_rows, R, P->pr_grp, P->pr_meta, P->pr_item_ptr, P->pr_contrib, P->pr_enodes,
-                                                 d_xg, d_wg, P->row_ptr, P->col_ind, d_A00, d_A01, d_A10, d_A11);
+          const int R = P->pr_rows, ncta = P->pr_n_cta;
+#define DFB_PAIR_LAUNCH(NT, MINB)                                                                                                  \
+  do {                                                                                                                             \
+    static size_t set_smem = 0;                                                                                                    \
+    if (smem > set_smem) {                                                                                                         \
+      DFB_CUDA(cudaFuncSetAttribute(k_pairJ<0, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+      DFB_CUDA(cudaFuncSetAttribute(k_pairJ<1, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+      set_smem = smem;                                                                                                             \
+    }                                                                                                                              \
+    if (overwrite)                                                                                                                 \
+      k_pairJ<1, NT, MINB><<<ncta, NT, smem, st>>>(N, P->n_rows, R, P->pr_grp, P->pr_meta, P->pr_item_ptr, P->pr_contrib,          \
+                                                   P->pr_enodes, d_xg, d_wg, P->row_ptr, P->col_ind, d_A00, d_A01, d_A10, d_A11);  \
+    else                                                                                                                           \
+      k_pairJ<0, NT, MINB><<<ncta, NT, smem, st>>>(N, P->n_rows, R, P->pr_grp, P->pr_meta, P->pr_item_ptr, P->pr_contrib,          \
+                                                   P->pr_enodes, d_xg, d_wg, P->row_ptr, P->col_ind, d_A00, d_A01, d_A10, d_A11);  \
+  } while (0)
+          // 96 threads (3 warps: one of diagonal items, two of pair items) and 4 CTAs per SM measured best on B200 at 1M tets:
+          // 96x5 (128 registers, spills) 377 us, 128x3 432 us, 128x4 403 us, 160x2 547 us, 16 rows x 192 threads 404 us vs 372 us
+          if (R == 16) DFB_PAIR_LAUNCH(192, 2);
+          else DFB_PAIR_LAUNCH(96, 4);
+#undef DFB_PAIR_LAUNCH
           DFB_LAUNCH_CHECK();
           done = true;
         }

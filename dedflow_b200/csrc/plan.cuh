@@ -46,6 +46,7 @@ struct dfb_plan {
   // (a multiple of 8); one CTA per group.  Work items of a group: first 4 "virtual" items per row for the diagonal entry
   // (4*pr_rows: whole warps), then one item per UPPER off-diagonal nonzero (i,j), j > i, which also produces (j,i).
   mutable int pr_state = 0;            // 0: not built, 1: usable, -1: a group does not fit shared memory (fall back to pull)
+  mutable int pr_built_rows = -1;     // n_rows the lists were built for (rebuilt when dfb_plan_set_rows changes it)
   mutable int pr_rows = 0, pr_n_cta = 0, pr_n_items = 0, pr_max_elems = 0;
   mutable int4* pr_grp = nullptr;       // [pr_n_cta] {first staged element, #elements, first item, #items}: one 16-byte load per CTA
   mutable int4* pr_enodes = nullptr;    // the four node ids of every staged element (parallel to pr_elems): skips elems -> ien
@@ -64,5 +65,6 @@ constexpr int PULL_MAX_STAGED = 160; // most element records a CTA stages (160 x
 int build_v2c(int N, int E, const int* d_ien, int** d_ptr_out, int** d_v2c_out, cudaStream_t st);
 int build_pull(const dfb_plan* plan, cudaStream_t st);
 constexpr int PAIR_MAX_STAGED = 600; // most element records a CTA of the pair assembly stages (600 x 368 B = 216 KB)
-int build_pairs(const dfb_plan* plan, int rows_per_cta, cudaStream_t st);
+int build_pairs(const dfb_plan* plan, int rows_per_cta, const f64* d_xg, cudaStream_t st);
+void free_pairs(const dfb_plan* plan);
 }

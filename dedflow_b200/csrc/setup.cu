@@ -8,6 +8,9 @@
 //   matrix_impl.cu:406-410 per-scatter linear search of col_ind                              -> slot map, built once
 #include <cub/cub.cuh>
 #include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -418,30 +421,115 @@ int build_pull(const dfb_plan* p, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------
 // work lists of the PAIR Jacobian assembly (plan.cuh, assemble.cu k_pairJ)
+//
+// Row groups.  The CTA of a group evaluates every element around its R rows, so a group should be a compact patch of the
+// mesh: the first n_rows (owned) rows are ordered along a Morton curve of their coordinates (cells sized for one node on
+// average) and cut into runs of R.  For the Kuhn box in natural numbering this lowers the elements per row from 18.8
+// (8 consecutive nodes of a grid line) to ~14 (a 2x2x2 block); for arbitrarily numbered meshes it is what makes staging
+// worthwhile at all.  order[pos] = row, rpos[row] = pos (-1 for rows that are not assembled here).
 // ------------------------------------------------------------------------------------------
-__global__ void k_pair_group_count(int N, int n_cta, int R, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
-                                   int* __restrict__ cnt) {
+__global__ void __launch_bounds__(256) k_bbox_part(int n, const f64* __restrict__ xg, f64* __restrict__ part) {
+  __shared__ f64 sm[8][6];
+  f64 lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      const f64 v = xg[(size_t)i * 3 + d];
+      lo[d] = fmin(lo[d], v);
+      hi[d] = fmax(hi[d], v);
+    }
+#pragma unroll
+  for (int d = 0; d < 3; d++)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fmin(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0)
+    for (int d = 0; d < 3; d++) { sm[w][d] = lo[d]; sm[w][3 + d] = hi[d]; }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    f64 r = sm[0][threadIdx.x];
+    for (int k = 1; k < 8; k++) r = threadIdx.x < 3 ? fmin(r, sm[k][threadIdx.x]) : fmax(r, sm[k][threadIdx.x]);
+    part[(size_t)blockIdx.x * 6 + threadIdx.x] = r;
+  }
+}
+
+__device__ __forceinline__ unsigned long long spread21(unsigned long long v) {   // 21 bits -> every third bit
+  v &= 0x1fffffull;
+  v = (v | (v << 32)) & 0x1f00000000ffffull;
+  v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+  v = (v | (v << 8)) & 0x100f00f00f00f00full;
+  v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+  v = (v | (v << 2)) & 0x1249249249249249ull;
+  return v;
+}
+
+__global__ void k_morton_keys(int n, int nblk, const f64* __restrict__ xg, const f64* __restrict__ part,
+                              unsigned long long* __restrict__ keys, int* __restrict__ ids) {
+  __shared__ f64 bb[6];
+  if (threadIdx.x < 6) {
+    f64 r = part[threadIdx.x];
+    for (int k = 1; k < nblk; k++) r = threadIdx.x < 3 ? fmin(r, part[(size_t)k * 6 + threadIdx.x]) : fmax(r, part[(size_t)k * 6 + threadIdx.x]);
+    bb[threadIdx.x] = r;
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // cell size: one node per cell on average over the occupied box (flat directions count as one cell)
+  f64 ext[3], vol = 1.0;
+  int nd = 0;
+  for (int d = 0; d < 3; d++) {
+    ext[d] = bb[3 + d] - bb[d];
+    if (ext[d] > 0.0) { vol *= ext[d]; nd++; }
+  }
+  const f64 h = nd ? pow(vol / (f64)n, 1.0 / nd) : 1.0;
+  unsigned long long key = 0;
+  for (int d = 0; d < 3; d++) {
+    unsigned long long c = 0;
+    if (ext[d] > 0.0) {
+      const f64 nb = fmin(2097151.0, fmax(1.0, ceil(ext[d] / h)));
+      c = (unsigned long long)fmin(nb - 1.0, floor((xg[(size_t)i * 3 + d] - bb[d]) / ext[d] * nb));
+    }
+    key |= spread21(c) << d;
+  }
+  keys[i] = key;
+  ids[i] = i;
+}
+
+__global__ void k_iota_rpos(int N, int n, const int* __restrict__ order, int* __restrict__ rpos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  if (i < n) rpos[order[i]] = i;       // order is a permutation of [0, n): every rpos[0..n) is written exactly once
+  else rpos[i] = -1;
+}
+
+__global__ void k_pair_group_count(int n_act, int n_cta, int R, const int* __restrict__ order, const int* __restrict__ row_ptr,
+                                   const int* __restrict__ col_ind, int* __restrict__ cnt) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g > n_cta) return;
   if (g == n_cta) { cnt[g] = 0; return; }
   int total = 4 * R;
-  for (int row = g * R; row < min(N, (g + 1) * R); row++) {
+  for (int pos = g * R; pos < min(n_act, (g + 1) * R); pos++) {
+    const int row = order[pos];
     const int s = row_ptr[row], len = row_ptr[row + 1] - s;
     total += len - 1 - lower_bound_dev(col_ind + s, len, row);   // entries right of the diagonal
   }
   cnt[g] = total;
 }
 
-__global__ void k_pair_meta(int N, int n_cta, int R, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
-                            const int* __restrict__ grp_item, uint2* __restrict__ meta, int* __restrict__ row_pair) {
+__global__ void k_pair_meta(int n_act, int n_cta, int R, const int* __restrict__ order, const int* __restrict__ row_ptr,
+                            const int* __restrict__ col_ind, const int* __restrict__ grp_item, uint2* __restrict__ meta,
+                            int* __restrict__ row_pair) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_cta) return;
   const int base = grp_item[g];
   int pos = base + 4 * R;
   for (int r = 0; r < R; r++) {
-    const int row = g * R + r;
     uint2 md = make_uint2(0xffffffffu, 0u);
-    if (row < N) {
+    if (g * R + r < n_act) {
+      const int row = order[g * R + r];
       const int s = row_ptr[row], len = row_ptr[row + 1] - s;
       const int kd = lower_bound_dev(col_ind + s, len, row);
       md = make_uint2((u32)row, (u32)kd | 0x100u);
@@ -457,18 +545,22 @@ __global__ void k_pair_meta(int N, int n_cta, int R, const int* __restrict__ row
   }
 }
 
-// item of contribution (corner c = e*4+a, b): -1 for the lower half (produced by the pair item of the other node)
+// item of contribution (corner c = e*4+a, b): -1 for the lower half (produced by the pair item of the other node) and for
+// rows that are not assembled here
 __device__ __forceinline__ int pair_item_of(int c, int b, int R, const int* __restrict__ ien, const int* __restrict__ row_ptr,
                                             const int* __restrict__ col_ind, const int* __restrict__ v2c_ptr,
                                             const int* __restrict__ v2c, const u32* __restrict__ slot32,
-                                            const int* __restrict__ grp_item, const int* __restrict__ row_pair, int* __restrict__ bad) {
+                                            const int* __restrict__ grp_item, const int* __restrict__ rpos,
+                                            const int* __restrict__ row_pair, int* __restrict__ bad) {
   const int a = c & 3;
   const int row = ien[c];
+  const int pos = rpos[row];
+  if (pos < 0) return -1;
   if (a == b) {
-    const int g = row / R;
+    const int g = pos / R;
     const int vs = v2c_ptr[row];
     const int r = lower_bound_dev(v2c + vs, v2c_ptr[row + 1] - vs, c);
-    return grp_item[g] + (row - g * R) * 4 + (r & 3);
+    return grp_item[g] + (pos - g * R) * 4 + (r & 3);
   }
   const int col = ien[(c & ~3) + b];
   if (col == row) { atomicExch(bad, 1); return -1; }   // degenerate element (repeated node): the pair variant is not used
@@ -482,25 +574,62 @@ __device__ __forceinline__ int pair_item_of(int c, int b, int R, const int* __re
 template <bool FILL>
 __global__ void k_pair_contrib(int E, int R, const int* __restrict__ ien, const int* __restrict__ row_ptr,
                                const int* __restrict__ col_ind, const int* __restrict__ v2c_ptr, const int* __restrict__ v2c,
-                               const u32* __restrict__ slot32, const int* __restrict__ grp_item, const int* __restrict__ row_pair,
-                               int* __restrict__ cnt, const int* __restrict__ item_ptr, u32* __restrict__ contrib, int* __restrict__ bad) {
+                               const u32* __restrict__ slot32, const int* __restrict__ grp_item, const int* __restrict__ rpos,
+                               const int* __restrict__ row_pair, int* __restrict__ cnt, const int* __restrict__ item_ptr,
+                               u32* __restrict__ contrib, int* __restrict__ bad) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)16 * E) return;
   const int c = (int)(t >> 2), b = (int)(t & 3);
-  const int it = pair_item_of(c, b, R, ien, row_ptr, col_ind, v2c_ptr, v2c, slot32, grp_item, row_pair, bad);
+  const int it = pair_item_of(c, b, R, ien, row_ptr, col_ind, v2c_ptr, v2c, slot32, grp_item, rpos, row_pair, bad);
   if (it < 0) return;
   const int pos = atomicAdd(cnt + it, 1);
   if (FILL) contrib[item_ptr[it] + pos] = (u32)t;
 }
 
+// distinct elements around the rows order[g*R .. g*R+R): sorted insert with de-duplication into a private list
+template <bool FILL>
+__global__ void __launch_bounds__(64) k_pair_group_elems(int n_act, int n_cta, int R, const int* __restrict__ order,
+                                                         const int* __restrict__ v2c_ptr, const int* __restrict__ v2c,
+                                                         int* __restrict__ cnt, const int* __restrict__ ptr, int* __restrict__ elems,
+                                                         int* __restrict__ overflow) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_cta) return;
+  if (FILL && ptr[g + 1] == ptr[g]) return;
+  int buf[GROUP_CAP];
+  int n = 0;
+  bool ovf = false;
+  for (int pos = g * R; pos < min(n_act, (g + 1) * R); pos++) {
+    const int row = order[pos];
+    for (int c = v2c_ptr[row]; c < v2c_ptr[row + 1]; c++) {
+      const int e = v2c[c] >> 2;
+      int lo = 0, hi = n;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (buf[mid] < e) lo = mid + 1; else hi = mid;
+      }
+      if (lo < n && buf[lo] == e) continue;
+      if (n >= GROUP_CAP) { ovf = true; continue; }
+      for (int k = n; k > lo; k--) buf[k] = buf[k - 1];
+      buf[lo] = e;
+      n++;
+    }
+  }
+  if (!FILL) {
+    cnt[g] = ovf ? 0 : n;
+    if (ovf) atomicExch(overflow, 1);
+  } else {
+    for (int k = 0; k < n; k++) elems[ptr[g] + k] = buf[k];
+  }
+}
+
 __global__ void k_pair_contrib16(int n_items, int R, const uint2* __restrict__ meta, const int* __restrict__ item_ptr,
-                                 const u32* __restrict__ contrib, const int* __restrict__ elem_ptr,
+                                 const u32* __restrict__ contrib, const int* __restrict__ rpos, const int* __restrict__ elem_ptr,
                                  const int* __restrict__ elems, unsigned short* __restrict__ contrib16) {
   const int it = blockIdx.x * blockDim.x + threadIdx.x;
   if (it >= n_items) return;
   const u32 row = meta[it].x;
   if (row == 0xffffffffu) return;
-  const int g = (int)row / R;
+  const int g = rpos[row] / R;
   const int s = elem_ptr[g], n = elem_ptr[g + 1] - s;
   for (int idx = item_ptr[it]; idx < item_ptr[it + 1]; idx++) {
     const u32 cid = contrib[idx];
@@ -517,24 +646,67 @@ __global__ void k_pair_finalize(int n_cta, int total_ge, const int* __restrict__
   if (i < total_ge) enodes[i] = *reinterpret_cast<const int4*>(ien + (size_t)elems[i] * 4);
 }
 
-int build_pairs(const dfb_plan* p, int R, cudaStream_t st) {
-  if (p->pr_state != 0) return DFB_OK;
+void free_pairs(const dfb_plan* p) {
+  cudaFree(p->pr_grp_item); cudaFree(p->pr_meta); cudaFree(p->pr_item_ptr); cudaFree(p->pr_contrib); cudaFree(p->pr_elem_ptr);
+  cudaFree(p->pr_elems); cudaFree(p->pr_grp); cudaFree(p->pr_enodes);
+  p->pr_grp_item = nullptr; p->pr_meta = nullptr; p->pr_item_ptr = nullptr; p->pr_contrib = nullptr; p->pr_elem_ptr = nullptr;
+  p->pr_elems = nullptr; p->pr_grp = nullptr; p->pr_enodes = nullptr;
+  p->pr_state = 0; p->pr_bytes = 0;
+}
+
+// d_xg may be NULL (or DFB_J_PAIR_ORDER=natural): the rows are then grouped in their natural order.
+int build_pairs(const dfb_plan* p, int R, const f64* d_xg, cudaStream_t st) {
+  if (p->pr_state != 0 && p->pr_built_rows == p->n_rows) return DFB_OK;
+  if (p->pr_state != 0) free_pairs(p);
+  p->pr_built_rows = p->n_rows;
   if (!p->slot) { set_error("pair assembly needs a plan with a sparsity pattern"); return DFB_ERR_ARG; }
   if (R < 8 || (R & 7)) { set_error("pair assembly: rows per CTA must be a multiple of 8"); return DFB_ERR_ARG; }
   if ((i64)p->E * 16 > 0xffffffffLL) { p->pr_state = -1; return DFB_OK; }
-  const int N = p->N, E = p->E;
+  const int N = p->N, E = p->E, n_act = p->n_rows;
   const u32* slot32 = reinterpret_cast<const u32*>(p->slot);
-  const int n_cta = ceil_div(N, R);
-  DevBuf<int> cnt, row_pair, icnt, gcnt, flags;
+  const int n_cta = ceil_div(n_act, R);
+  DevBuf<int> cnt, row_pair, icnt, gcnt, flags, order, rpos;
   DevBuf<char> tmp;
   DevBuf<u32> contrib32;
+  size_t tmp_bytes = 0;
+  // ---- row order ----
+  DFB_CHECK(order.alloc((size_t)n_act));
+  DFB_CHECK(rpos.alloc((size_t)N));
+  const char* oe = getenv("DFB_J_PAIR_ORDER");
+  if (d_xg && !(oe && !strcmp(oe, "natural"))) {
+    DevBuf<f64> part;
+    DevBuf<unsigned long long> keys, keys_out;
+    DevBuf<int> ids;
+    const int nblk = std::min(1024, ceil_div(n_act, 256));
+    DFB_CHECK(part.alloc((size_t)nblk * 6));
+    DFB_CHECK(keys.alloc((size_t)n_act));
+    DFB_CHECK(keys_out.alloc((size_t)n_act));
+    DFB_CHECK(ids.alloc((size_t)n_act));
+    k_bbox_part<<<nblk, 256, 0, st>>>(n_act, d_xg, part);
+    DFB_LAUNCH_CHECK();
+    k_morton_keys<<<ceil_div(n_act, 256), 256, 0, st>>>(n_act, nblk, d_xg, part, keys, ids);
+    DFB_LAUNCH_CHECK();
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_out.p, ids.p, order.p, n_act, 0, 63, st);
+    DFB_CHECK(tmp.alloc(tmp_bytes));
+    cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_out.p, ids.p, order.p, n_act, 0, 63, st);
+    DFB_LAUNCH_CHECK();
+    DFB_CUDA(cudaStreamSynchronize(st));   // the scratch buffers above are released at the end of this scope
+  } else {
+    std::vector<int> h(n_act);
+    for (int i = 0; i < n_act; i++) h[i] = i;
+    DFB_CUDA(cudaMemcpyAsync(order, h.data(), sizeof(int) * (size_t)n_act, cudaMemcpyHostToDevice, st));
+    DFB_CUDA(cudaStreamSynchronize(st));
+  }
+  k_iota_rpos<<<ceil_div(N, 256), 256, 0, st>>>(N, n_act, order, rpos);
+  DFB_LAUNCH_CHECK();
+  // ---- items ----
   DFB_CHECK(cnt.alloc((size_t)n_cta + 1));
   DFB_CHECK(flags.alloc(3));   // [0] degenerate element, [1] group too large, [2] max elements per group
   DFB_CUDA(cudaMemsetAsync(flags, 0, 3 * sizeof(int), st));
   DFB_CUDA(cudaMalloc(&p->pr_grp_item, sizeof(int) * ((size_t)n_cta + 1)));
-  k_pair_group_count<<<ceil_div((i64)n_cta + 1, 128), 128, 0, st>>>(N, n_cta, R, p->row_ptr, p->col_ind, cnt);
+  k_pair_group_count<<<ceil_div((i64)n_cta + 1, 128), 128, 0, st>>>(n_act, n_cta, R, order, p->row_ptr, p->col_ind, cnt);
   DFB_LAUNCH_CHECK();
-  size_t tmp_bytes = 0;
+  tmp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt.p, p->pr_grp_item, n_cta + 1, st);
   DFB_CHECK(tmp.alloc(tmp_bytes));
   cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cnt.p, p->pr_grp_item, n_cta + 1, st);
@@ -547,10 +719,10 @@ int build_pairs(const dfb_plan* p, int R, cudaStream_t st) {
   DFB_CHECK(row_pair.alloc((size_t)N));
   DFB_CHECK(icnt.alloc((size_t)n_items + 1));
   DFB_CUDA(cudaMemsetAsync(icnt, 0, sizeof(int) * ((size_t)n_items + 1), st));
-  k_pair_meta<<<ceil_div(n_cta, 128), 128, 0, st>>>(N, n_cta, R, p->row_ptr, p->col_ind, p->pr_grp_item, p->pr_meta, row_pair);
+  k_pair_meta<<<ceil_div(n_cta, 128), 128, 0, st>>>(n_act, n_cta, R, order, p->row_ptr, p->col_ind, p->pr_grp_item, p->pr_meta, row_pair);
   DFB_LAUNCH_CHECK();
   const int cgrid = ceil_div((i64)E * 16, 256);
-  k_pair_contrib<false><<<cgrid, 256, 0, st>>>(E, R, p->ien, p->row_ptr, p->col_ind, p->v2c_ptr, p->v2c, slot32, p->pr_grp_item,
+  k_pair_contrib<false><<<cgrid, 256, 0, st>>>(E, R, p->ien, p->row_ptr, p->col_ind, p->v2c_ptr, p->v2c, slot32, p->pr_grp_item, rpos,
                                                row_pair, icnt, nullptr, nullptr, flags);
   DFB_LAUNCH_CHECK();
   tmp_bytes = 0;
@@ -563,7 +735,7 @@ int build_pairs(const dfb_plan* p, int R, cudaStream_t st) {
   DFB_CUDA(cudaStreamSynchronize(st));
   DFB_CHECK(contrib32.alloc((size_t)n_contrib));
   DFB_CUDA(cudaMemsetAsync(icnt, 0, sizeof(int) * ((size_t)n_items + 1), st));
-  k_pair_contrib<true><<<cgrid, 256, 0, st>>>(E, R, p->ien, p->row_ptr, p->col_ind, p->v2c_ptr, p->v2c, slot32, p->pr_grp_item,
+  k_pair_contrib<true><<<cgrid, 256, 0, st>>>(E, R, p->ien, p->row_ptr, p->col_ind, p->v2c_ptr, p->v2c, slot32, p->pr_grp_item, rpos,
                                               row_pair, icnt, p->pr_item_ptr, contrib32, flags);
   DFB_LAUNCH_CHECK();
   k_sort_contrib<<<ceil_div(n_items, 128), 128, 0, st>>>(n_items, p->pr_item_ptr, contrib32);
@@ -572,7 +744,7 @@ int build_pairs(const dfb_plan* p, int R, cudaStream_t st) {
   DFB_CHECK(gcnt.alloc((size_t)n_cta + 1));
   DFB_CUDA(cudaMemsetAsync(gcnt, 0, sizeof(int) * ((size_t)n_cta + 1), st));
   DFB_CUDA(cudaMalloc(&p->pr_elem_ptr, sizeof(int) * ((size_t)n_cta + 1)));
-  k_group_elems<false><<<ceil_div(n_cta, 64), 64, 0, st>>>(N, n_cta, R, p->v2c_ptr, p->v2c, gcnt, nullptr, nullptr, flags.p + 1);
+  k_pair_group_elems<false><<<ceil_div(n_cta, 64), 64, 0, st>>>(n_act, n_cta, R, order, p->v2c_ptr, p->v2c, gcnt, nullptr, nullptr, flags.p + 1);
   DFB_LAUNCH_CHECK();
   tmp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, gcnt.p, p->pr_elem_ptr, n_cta + 1, st);
@@ -588,16 +760,15 @@ int build_pairs(const dfb_plan* p, int R, cudaStream_t st) {
   p->pr_rows = R; p->pr_n_cta = n_cta; p->pr_n_items = n_items; p->pr_max_elems = h_flags[2];
   if (h_flags[0] || h_flags[1] || h_flags[2] > PAIR_MAX_STAGED || h_flags[2] >= 4096) {
     // degenerate elements or a row group whose element records do not fit shared memory: the caller falls back to the pull variant
-    cudaFree(p->pr_grp_item); cudaFree(p->pr_meta); cudaFree(p->pr_item_ptr); cudaFree(p->pr_elem_ptr);
-    p->pr_grp_item = nullptr; p->pr_meta = nullptr; p->pr_item_ptr = nullptr; p->pr_elem_ptr = nullptr;
+    free_pairs(p);
     p->pr_state = -1;
     return DFB_OK;
   }
   DFB_CUDA(cudaMalloc(&p->pr_elems, sizeof(int) * (size_t)std::max(1, total_ge)));
-  k_group_elems<true><<<ceil_div(n_cta, 64), 64, 0, st>>>(N, n_cta, R, p->v2c_ptr, p->v2c, nullptr, p->pr_elem_ptr, p->pr_elems, nullptr);
+  k_pair_group_elems<true><<<ceil_div(n_cta, 64), 64, 0, st>>>(n_act, n_cta, R, order, p->v2c_ptr, p->v2c, nullptr, p->pr_elem_ptr, p->pr_elems, nullptr);
   DFB_LAUNCH_CHECK();
   DFB_CUDA(cudaMalloc(&p->pr_contrib, sizeof(unsigned short) * (size_t)std::max(1, n_contrib)));
-  k_pair_contrib16<<<ceil_div(n_items, 128), 128, 0, st>>>(n_items, R, p->pr_meta, p->pr_item_ptr, contrib32, p->pr_elem_ptr, p->pr_elems,
+  k_pair_contrib16<<<ceil_div(n_items, 128), 128, 0, st>>>(n_items, R, p->pr_meta, p->pr_item_ptr, contrib32, rpos, p->pr_elem_ptr, p->pr_elems,
                                                            p->pr_contrib);
   DFB_LAUNCH_CHECK();
   DFB_CUDA(cudaMalloc(&p->pr_grp, sizeof(int4) * (size_t)n_cta));
@@ -606,9 +777,12 @@ int build_pairs(const dfb_plan* p, int R, cudaStream_t st) {
                                                                           p->pr_grp, p->pr_enodes);
   DFB_LAUNCH_CHECK();
   DFB_CUDA(cudaStreamSynchronize(st));
-  p->pr_bytes = sizeof(int4) * ((size_t)n_cta + (size_t)total_ge) + sizeof(int) * 2 * ((size_t)n_cta + 1) + sizeof(uint2) * (size_t)n_items + sizeof(int) * ((size_t)n_items + 1) +
-                sizeof(int) * (size_t)total_ge + sizeof(unsigned short) * (size_t)n_contrib;
+  p->pr_bytes = sizeof(int4) * ((size_t)n_cta + (size_t)total_ge) + sizeof(int) * 2 * ((size_t)n_cta + 1) + sizeof(uint2) * (size_t)n_items +
+                sizeof(int) * ((size_t)n_items + 1) + sizeof(int) * (size_t)total_ge + sizeof(unsigned short) * (size_t)n_contrib;
   p->pr_state = 1;
+  if (getenv("DFB_VERBOSE"))
+    fprintf(stderr, "[dfb] pair plan: %d groups of %d rows, %.1f staged elements per group (max %d), %d items, %d contributions, %.1f MB\n",
+            n_cta, R, (double)total_ge / n_cta, h_flags[2], n_items, n_contrib, p->pr_bytes / 1e6);
   return DFB_OK;
 }
 
@@ -728,8 +902,7 @@ void dfb_plan_destroy(dfb_plan* p) {
   cudaFree(p->v2c_ptr); cudaFree(p->v2c); cudaFree(p->slot); cudaFree(p->elemF); cudaFree(p->cpos);
   cudaFree(p->row_item); cudaFree(p->item_meta); cudaFree(p->item_ptr); cudaFree(p->contrib); cudaFree(p->prec);
   cudaFree(p->cta_elem_ptr); cudaFree(p->cta_elems); cudaFree(p->contrib16);
-  cudaFree(p->pr_grp_item); cudaFree(p->pr_meta); cudaFree(p->pr_item_ptr); cudaFree(p->pr_contrib); cudaFree(p->pr_elem_ptr);
-  cudaFree(p->pr_elems); cudaFree(p->pr_grp); cudaFree(p->pr_enodes);
+  free_pairs(p);
   delete p;
 }
 

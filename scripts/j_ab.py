@@ -1,7 +1,8 @@
 """A/B of the Jacobian assembly variants on one GPU: kernel time (CUDA events, median of 20) and agreement with the pull variant.
-usage: python scripts/j_ab.py [m]"""
+usage: python scripts/j_ab.py [m] [shuffle]"""
 import ctypes as C
 import os
+os.environ["DFB_VERBOSE"] = "1"
 import sys
 from pathlib import Path
 
@@ -13,13 +14,25 @@ from dedflow_b200 import api, boxmesh  # noqa: E402
 
 m = int(sys.argv[1]) if len(sys.argv) > 1 else 55
 mesh = boxmesh.make_box(m)
+if len(sys.argv) > 2 and sys.argv[2] == "shuffle":      # random node and element numbering (timing only: boundary lists go stale)
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(mesh.num_node).astype(np.int32)
+    xg = np.empty_like(mesh.xg.reshape(-1, 3))
+    xg[perm] = mesh.xg.reshape(-1, 3)
+    mesh.xg = np.ascontiguousarray(xg.reshape(mesh.xg.shape))
+    mesh.ien = np.ascontiguousarray(perm[mesh.ien][rng.permutation(mesh.num_tet)])
 N, E = mesh.num_node, mesh.num_tet
 wg, dwg = boxmesh.state_random(N)
 d_wg, d_dwg = torch.from_numpy(wg).cuda(), torch.from_numpy(dwg).cuda()
 P = lambda t: C.c_void_p(t.data_ptr())
 ref = None
-for name, env in (("pull", {"DFB_J_VARIANT": "pull"}), ("pairs R=8", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ROWS": "8"}),
-                  ("pairs R=16", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ROWS": "16"}), ("fused", {"DFB_J_VARIANT": "fused"})):
+shuffle = len(sys.argv) > 2 and sys.argv[2] == "shuffle"
+CFGS = [("pull", {"DFB_J_VARIANT": "pull"}),
+        ("pairs morton", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "morton"}),
+        ("pairs natural", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "natural"}),
+        ("pairs R=16", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "morton", "DFB_J_PAIR_ROWS": "16"}),
+        ("fused", {"DFB_J_VARIANT": "fused"})]
+for name, env in CFGS:
     os.environ.update(env)
     fs = api.FlowSystem(mesh)
     st = fs._stream()
