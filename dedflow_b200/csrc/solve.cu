@@ -404,54 +404,64 @@ __device__ __forceinline__ bool last_block(unsigned* ctr, unsigned total) {
 }
 
 
+// Stage 1 of the multi-dot for a group of NJ columns: a thread streams 16-byte pairs of rows, U row pairs per trip, so that
+// (NJ + 1) x U independent 16-byte loads are in flight (18 for a full group).
+template <int NJ>
+__device__ __forceinline__ void md_accum(const double2* __restrict__ q2, const double2* __restrict__ w2, size_t np, size_t ld2,
+                                         f64 (&acc)[JT]) {
+  constexpr int U = NJ <= 2 ? 4 : 2;
+  const size_t stride = (size_t)gridDim.x * 256;
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  for (; i + (U - 1) * stride < np; i += U * stride) {
+    double2 wv[U], qv[U][NJ];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      wv[u] = w2[i + u * stride];
+#pragma unroll
+      for (int j = 0; j < NJ; j++) qv[u][j] = q2[(size_t)j * ld2 + i + u * stride];
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int j = 0; j < NJ; j++) acc[j] = fma(qv[u][j].y, wv[u].y, fma(qv[u][j].x, wv[u].x, acc[j]));
+  }
+  for (; i < np; i += stride) {
+    const double2 wi = w2[i];
+    double2 qv[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) qv[j] = q2[(size_t)j * ld2 + i];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) acc[j] = fma(qv[j].y, wi.y, fma(qv[j].x, wi.x, acc[j]));
+  }
+}
+
 // h[j] = sum_i Q[i, j] * w[i],  j in [0, ncol): stage 1 = per-(chunk, column) partials, stage 2 by the last block.
-// nl is a multiple of 4 and every column starts 32-byte aligned, so a thread streams 16-byte pairs of rows: up to
-// (JT + 1) x 16 B in flight per thread.
+// The columns are dealt EVENLY to the gridDim.y column groups (at most JT each: 20 columns -> 7 + 7 + 6, not 8 + 8 + 4), so
+// that every block of the single resident wave streams the same number of bytes.  nl is a multiple of 4 and every column
+// starts 32-byte aligned.
 __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restrict__ Q, size_t ldq, int ncol,
                                                   const f64* __restrict__ w, f64* part, f64* __restrict__ h,
                                                   unsigned* ctr, const P2PView* __restrict__ pv, unsigned long long seq) {
   __shared__ f64 smj[8][JT];
   __shared__ f64 hsum[P2P_ACAP];
-  const int j0 = blockIdx.y * JT;
-  const int nj = min(JT, ncol - j0);
+  const int ngrp = gridDim.y, gbase = ncol / ngrp, grem = ncol - gbase * ngrp;
+  const int j0 = blockIdx.y * gbase + min((int)blockIdx.y, grem);
+  const int nj = gbase + ((int)blockIdx.y < grem ? 1 : 0);
   f64 acc[JT];
 #pragma unroll
   for (int j = 0; j < JT; j++) acc[j] = 0.0;
   const double2* q2 = reinterpret_cast<const double2*>(Q + (size_t)j0 * ldq);
   const double2* w2 = reinterpret_cast<const double2*>(w);
   const size_t np = nl >> 1, ld2 = ldq >> 1;
-  if (nj == JT) {
-    const size_t stride = (size_t)gridDim.x * 256;
-    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    for (; i + stride < np; i += 2 * stride) {   // two row pairs per trip: 18 independent 16-byte loads in flight
-      const double2 wa = w2[i], wb = w2[i + stride];
-      double2 qa[JT], qb[JT];
-#pragma unroll
-      for (int j = 0; j < JT; j++) { qa[j] = q2[(size_t)j * ld2 + i]; qb[j] = q2[(size_t)j * ld2 + i + stride]; }
-#pragma unroll
-      for (int j = 0; j < JT; j++) {
-        acc[j] = fma(qa[j].y, wa.y, fma(qa[j].x, wa.x, acc[j]));
-        acc[j] = fma(qb[j].y, wb.y, fma(qb[j].x, wb.x, acc[j]));
-      }
-    }
-    if (i < np) {
-      const double2 wi = w2[i];
-      double2 qv[JT];
-#pragma unroll
-      for (int j = 0; j < JT; j++) qv[j] = q2[(size_t)j * ld2 + i];
-#pragma unroll
-      for (int j = 0; j < JT; j++) acc[j] = fma(qv[j].y, wi.y, fma(qv[j].x, wi.x, acc[j]));
-    }
-  } else {
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < np; i += (size_t)gridDim.x * 256) {
-      const double2 wi = w2[i];
-#pragma unroll
-      for (int j = 0; j < JT; j++)
-        if (j < nj) {
-          const double2 qv = q2[(size_t)j * ld2 + i];
-          acc[j] = fma(qv.y, wi.y, fma(qv.x, wi.x, acc[j]));
-        }
-    }
+  switch (nj) {
+    case 8: md_accum<8>(q2, w2, np, ld2, acc); break;
+    case 7: md_accum<7>(q2, w2, np, ld2, acc); break;
+    case 6: md_accum<6>(q2, w2, np, ld2, acc); break;
+    case 5: md_accum<5>(q2, w2, np, ld2, acc); break;
+    case 4: md_accum<4>(q2, w2, np, ld2, acc); break;
+    case 3: md_accum<3>(q2, w2, np, ld2, acc); break;
+    case 2: md_accum<2>(q2, w2, np, ld2, acc); break;
+    default: md_accum<1>(q2, w2, np, ld2, acc); break;
   }
   {  // block reduction of the JT accumulators with a single barrier: warp shuffles, then thread j sums the 8 warps
     const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
