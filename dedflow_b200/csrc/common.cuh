@@ -90,12 +90,16 @@ constexpr f64 kSHB = 0.1381966011250105;
 // Peer-memory view of the data-parallel communicator (dist.cu builds it, the Krylov kernels in solve.cu consume it): the
 // collectives of a GMRES iteration are FUSED into the compute kernels -- partial sums and halo values are stored straight
 // into the peers' memory over NVLink (CUDA IPC mappings), flags carry monotonically increasing sequence numbers.
-// Mailbox layout in 8-byte words, R = nranks:   A: multi-dot partials [2][R][128] + flags [2][R]
-//                                               B: norm partials      [2][R]      + flags [2][R]      H: halo flags [R]
+// The small all-reduce payloads (multi-dot coefficients, norms) travel in "LL" slots: a double is sent as two 8-byte words
+// {32 data bits | 32-bit sequence tag}.  8-byte stores are single-copy atomic, so a word validates itself: the sender needs
+// no fence and no separate flag, the receiver polls the slot until both tags match -- ONE NVLink traversal per exchange
+// instead of three (data, fence round trip, flag).  Slots are double-buffered by the parity of the sequence number.
+// Mailbox layout in 8-byte words, R = nranks:   A: multi-dot partials [2][R][128][2]     B: norm partials [2][R][2]
+//                                               H: halo flags [R] (bulk data: stores + fence + flag)
 // ------------------------------------------------------------------------------------------------------------
 constexpr int P2P_MAXR = 8;
 constexpr int P2P_ACAP = 128;
-constexpr size_t P2P_MBOX_WORDS = 4096;   // mailbox size (words); the shared z vector follows it in the same allocation
+constexpr size_t P2P_MBOX_WORDS = 8192;   // mailbox size (words); the shared z vector follows it in the same allocation
 
 struct P2PView {
   int rank, nranks;
@@ -120,15 +124,27 @@ struct P2PView {
 
 struct P2PHandle { P2PView host; const P2PView* dev; };   // what dfb_comm_p2p_view() returns
 
-__host__ __device__ inline size_t p2p_a_data(int R, int par, int r, int j) { return ((size_t)par * R + r) * P2P_ACAP + j; }
-__host__ __device__ inline size_t p2p_a_flag(int R, int par, int r) { return (size_t)2 * R * P2P_ACAP + (size_t)par * R + r; }
-__host__ __device__ inline size_t p2p_b_data(int R, int par, int r) { return (size_t)2 * R * P2P_ACAP + (size_t)2 * R + (size_t)par * R + r; }
-__host__ __device__ inline size_t p2p_b_flag(int R, int par, int r) { return (size_t)2 * R * P2P_ACAP + (size_t)4 * R + (size_t)par * R + r; }
-__host__ __device__ inline size_t p2p_h_flag(int R, int r) { return (size_t)2 * R * P2P_ACAP + (size_t)6 * R + r; }
+__host__ __device__ inline size_t p2p_a_ll(int R, int par, int r, int j) { return (((size_t)par * R + r) * P2P_ACAP + j) * 2; }
+__host__ __device__ inline size_t p2p_b_ll(int R, int par, int r) { return (size_t)4 * R * P2P_ACAP + ((size_t)par * R + r) * 2; }
+__host__ __device__ inline size_t p2p_h_flag(int R, int r) { return (size_t)4 * R * P2P_ACAP + (size_t)4 * R + r; }
+static_assert((size_t)4 * P2P_MAXR * P2P_ACAP + 5 * P2P_MAXR <= P2P_MBOX_WORDS, "mailbox too small");
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void p2p_signal(unsigned long long* flag, unsigned long long seq) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+}
+__device__ __forceinline__ void ll_store(unsigned long long* slot, f64 v, unsigned tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"((b & 0xffffffffull) | t), "l"((b >> 32) | t) : "memory");
+}
+__device__ __forceinline__ f64 ll_load(const unsigned long long* slot, unsigned tag) {
+  unsigned long long w0, w1;
+  while (true) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+    if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) break;
+    __nanosleep(20);
+  }
+  return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
 }
 __device__ __forceinline__ void p2p_wait(const unsigned long long* flag, unsigned long long seq) {
   unsigned long long v;

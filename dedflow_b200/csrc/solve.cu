@@ -309,14 +309,14 @@ __global__ void __launch_bounds__(128) k_scale_pc_apply_peer(int n, const f64* _
                                                              f64* gv, f64* beta, f64* tailc, f64* res_hist) {
   __shared__ f64 s_scale;
   __shared__ bool is_last;
+  __shared__ f64 s_part[P2P_MAXR];
   if (seq) {
     const int R = pv->nranks, par = (int)(seq & 1ull);
-    if ((int)threadIdx.x < R) p2p_wait(pv->mbox_local + p2p_b_flag(R, par, threadIdx.x), seq);
+    if ((int)threadIdx.x < R) s_part[threadIdx.x] = ll_load(pv->mbox_local + p2p_b_ll(R, par, threadIdx.x), (unsigned)seq);
     __syncthreads();
     if (threadIdx.x == 0) {
-      const f64* mb = reinterpret_cast<const f64*>(pv->mbox_local);
       f64 nrm2 = 0.0;
-      for (int r = 0; r < R; r++) nrm2 += __ldcg(mb + p2p_b_data(R, par, r));
+      for (int r = 0; r < R; r++) nrm2 += s_part[r];
       const f64 cw = S->cw;
       s_scale = 1.0 / sqrt(nrm2 + cw * cw * S->tail2);
       if (blockIdx.x == 0) {
@@ -497,11 +497,8 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
     const int R = pv->nranks, par = (int)(seq & 1ull);
     for (int t = threadIdx.x; t < R * ncol; t += 256) {
       const int r = t / ncol, j = t - r * ncol;
-      reinterpret_cast<f64*>(pv->mbox_peer[r])[p2p_a_data(R, par, pv->rank, j)] = hsum[j];
+      ll_store(pv->mbox_peer[r] + p2p_a_ll(R, par, pv->rank, j), hsum[j], (unsigned)seq);
     }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < pv->nranks) p2p_signal(pv->mbox_peer[threadIdx.x] + p2p_a_flag(pv->nranks, (int)(seq & 1ull), pv->rank), seq);
   }
   if (threadIdx.x == 0) *ctr = 0u;
 }
@@ -526,12 +523,9 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
   __shared__ f64 sm[8];
   if (pv) {   // fused all-reduce of h: wait for every rank's partial (stored into OUR mailbox), sum in rank order
     const int R = pv->nranks, par = (int)(seq & 1ull);
-    if ((int)threadIdx.x < R) p2p_wait(pv->mbox_local + p2p_a_flag(R, par, threadIdx.x), seq);
-    __syncthreads();
-    const f64* mb = reinterpret_cast<const f64*>(pv->mbox_local);
     for (int j = threadIdx.x; j < ncol; j += 256) {
       f64 s = 0.0;
-      for (int r = 0; r < R; r++) s += __ldcg(mb + p2p_a_data(R, par, r, j));
+      for (int r = 0; r < R; r++) s += ll_load(pv->mbox_local + p2p_a_ll(R, par, r, j), (unsigned)seq);
       sh[j] = s;
       if (blockIdx.x == 0) h[j] = s;
     }
@@ -601,9 +595,8 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
       f64 cw = 0.0;
       for (int j = 0; j < ncol; j++) cw -= sh[j] * tailc[j];   // same expression and order as gmres_step_dev
       S->cw = cw;
-      for (int r = 0; r < R; r++) reinterpret_cast<f64*>(pv->mbox_peer[r])[p2p_b_data(R, par, pv->rank)] = s;
-      __threadfence_system();
-      for (int r = 0; r < R; r++) p2p_signal(pv->mbox_peer[r] + p2p_b_flag(R, par, pv->rank), seq);
+      __threadfence();   // S->cw before the norm becomes visible anywhere
+      for (int r = 0; r < R; r++) ll_store(pv->mbox_peer[r] + p2p_b_ll(R, par, pv->rank), s, (unsigned)seq);
     } else {
       *nrm2 = s;
       if (do_step) gmres_step_dev(ncol - 1, S, h, gv, beta, tailc, res_hist);
@@ -753,12 +746,12 @@ __global__ void k_gmres_step(int it, GmresScalars* S, f64* hcol, f64* gv, f64* b
 __global__ void k_gmres_step_peer(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist,
                                   const P2PView* __restrict__ pv, unsigned long long seq) {
   const int R = pv->nranks, par = (int)(seq & 1ull);
-  if ((int)threadIdx.x < R) p2p_wait(pv->mbox_local + p2p_b_flag(R, par, threadIdx.x), seq);
-  __syncwarp();
+  __shared__ f64 s_part[P2P_MAXR];
+  if ((int)threadIdx.x < R) s_part[threadIdx.x] = ll_load(pv->mbox_local + p2p_b_ll(R, par, threadIdx.x), (unsigned)seq);
+  __syncthreads();
   if (threadIdx.x == 0) {
-    const f64* mb = reinterpret_cast<const f64*>(pv->mbox_local);
     f64 s = 0.0;
-    for (int r = 0; r < R; r++) s += __ldcg(mb + p2p_b_data(R, par, r));
+    for (int r = 0; r < R; r++) s += s_part[r];
     S->nrm2_live = s;
     gmres_step_dev(it, S, hcol, gv, beta, tailc, res_hist);
   }
@@ -881,6 +874,10 @@ int dfb_gmres_set_parallel(dfb_gmres* w, const dfb_parallel_ops* ops) {
   if (ops->n_own <= 0 || ops->n_own > w->N || ops->n_interior < 0 || ops->n_interior > ops->n_own || !ops->allreduce ||
       !ops->halo_begin || !ops->halo_end) { set_error("dfb_gmres_set_parallel: bad argument"); return DFB_ERR_ARG; }
   w->par = *ops; w->parallel = true; w->n_own = ops->n_own; w->n_interior = ops->n_interior;
+  // Sequence numbers tag the mailbox slots of the communicator (32 low bits).  Every workspace that is made parallel starts
+  // from its own base (same creation order on all ranks), so tags left behind by an earlier workspace never match.
+  static unsigned long long n_parallel_ws = 0;
+  if (w->seq == 0) { w->seq = w->hseq = (n_parallel_ws++ & 0x7full) << 24; }
   return DFB_OK;
 }
 
