@@ -8,16 +8,16 @@
 //   dirichlet_impl.cu:15-37, matrix_impl.cu:6-23  Dirichlet rows
 //
 // B200 design:
-//   * J, GATHER (default): one warp per nodal row.  Lanes = the row's corners (element, local node); each lane
-//     stages connectivity + nodal data in registers, evaluates the hoisted element math (elem_math.cuh) and
-//     produces the 4 blocks (b = 0..3) of its element row.  Per b the 32 blocks are staged in shared memory,
-//     lanes switch roles to (slot, half-block) owners, and sum the staged blocks that target their slot
-//     (peer masks from __match_any_sync).  Every CSR value is written exactly once, coalesced per row, in a
-//     fixed order: no atomics, no colors, no memset, no elem_J round trip, deterministic.
+//   * J, GATHER (default), three atomic-free variants that write every CSR value exactly once in a fixed order (no
+//     atomics, no colors, no memset, no elem_J round trip, deterministic):
+//       pairs (default, k_pairJ): one CTA per Morton-ordered group of 8 rows forms the records of the elements around the
+//         group in shared memory; one thread per UPPER nodal nonzero (i,j) accumulates both A_ij and A_ji in registers;
+//       pull (k_jprep2 + k_pullJ_staged): per-element records in global memory, one thread per nodal nonzero;
+//       fused (k_rowJ): one warp per nodal row, lanes = the row's corners, slot-peer reduction through shared memory.
 //   * J, ATOMIC: one thread per corner, red.global.add.f64 scatter through the precomputed slot map.
 //   * J, COLORED: same kernel without atomics, one launch per color batch (the reference's structure).
-//   * F: one thread per element evaluates the residual once; GATHER writes the 24 values to an L2-friendly
-//     scratch and a node-gather kernel sums them in fixed order; ATOMIC / COLORED scatter directly.
+//   * F: one thread per element evaluates the residual once; GATHER writes the four 48-byte corner residuals to a
+//     node-major scratch and a node-gather kernel streams and sums them in fixed order; ATOMIC / COLORED scatter directly.
 #include <stdlib.h>
 #include <string.h>
 

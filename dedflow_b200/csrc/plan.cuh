@@ -42,8 +42,8 @@ struct dfb_plan {
   mutable int max_cta_elems = 0;
   mutable size_t pull_bytes = 0;
   mutable int items_rows = -1, items_active = 0;  // cache: items of the first n_rows rows
-  // PAIR Jacobian assembly (setup.cu build_pairs, assemble.cu k_pairJ; the default).  Rows are cut into groups of pr_rows
-  // (a multiple of 8); one CTA per group.  Work items of a group: first 4 "virtual" items per row for the diagonal entry
+  // PAIR Jacobian assembly (setup.cu build_pairs, assemble.cu k_pairJ; the default).  The first n_rows rows, ordered along a
+  // Morton curve of their coordinates, are cut into groups of pr_rows (a multiple of 8); one CTA per group.  Work items of a group: first 4 "virtual" items per row for the diagonal entry
   // (4*pr_rows: whole warps), then one item per UPPER off-diagonal nonzero (i,j), j > i, which also produces (j,i).
   mutable int pr_state = 0;            // 0: not built, 1: usable, -1: a group does not fit shared memory (fall back to pull)
   mutable int pr_built_rows = -1;     // n_rows the lists were built for (rebuilt when dfb_plan_set_rows changes it)

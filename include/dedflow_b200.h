@@ -84,8 +84,9 @@ typedef struct dfb_plan dfb_plan;
 
 typedef enum dfb_assemble_mode {
   DFB_MODE_AUTO = 0,     /* fastest measured variant (gather) */
-  DFB_MODE_GATHER = 1,   /* atomic-free: one warp per nodal row gathers its corner contributions, every CSR value
-                            and F entry is written exactly once, fixed summation order (deterministic) */
+  DFB_MODE_GATHER = 1,   /* atomic-free: per row group, the element records are formed in shared memory and one thread
+                            per upper nodal nonzero (i,j) accumulates A_ij and A_ji; every CSR value and F entry is
+                            written exactly once, fixed summation order (deterministic) */
   DFB_MODE_ATOMIC = 2,   /* one launch over all elements, fp64 red.global.add scatter */
   DFB_MODE_COLORED = 3   /* one launch per color batch, plain read-modify-write in the reference's order */
 } dfb_assemble_mode;
