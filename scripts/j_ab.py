@@ -27,11 +27,9 @@ d_wg, d_dwg = torch.from_numpy(wg).cuda(), torch.from_numpy(dwg).cuda()
 P = lambda t: C.c_void_p(t.data_ptr())
 ref = None
 shuffle = len(sys.argv) > 2 and sys.argv[2] == "shuffle"
-CFGS = [("pull", {"DFB_J_VARIANT": "pull"}),
-        ("pairs morton", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "morton"}),
-        ("pairs natural", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "natural"}),
-        ("pairs R=16", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "morton", "DFB_J_PAIR_ROWS": "16"}),
-        ("fused", {"DFB_J_VARIANT": "fused"})]
+CFGS = [("pairs 96x4", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_CFG": "0"}),
+        ("pairs 64x5", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_CFG": "1"}),
+        ("pairs 64x6", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_CFG": "2"})]
 for name, env in CFGS:
     os.environ.update(env)
     fs = api.FlowSystem(mesh)
