@@ -882,12 +882,9 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
                                                    P->pr_enodes, d_xg, d_wg, P->row_ptr, P->col_ind, d_A00, d_A01, d_A10, d_A11);  \
   } while (0)
           // 96 threads (3 warps: one of diagonal items, two of pair items) and 4 CTAs per SM measured best on B200 at 1M tets:
-          // 96x5 (128 registers, spills) 377 us, 128x3 432 us, 128x4 403 us, 160x2 547 us, 16 rows x 192 threads 404 us vs 372 us
-          const char* ce = getenv("DFB_J_PAIR_CFG");
-          const int cfg = ce ? atoi(ce) : 0;
+          // 96x5 (128 registers, spills) 377 us, 128x3 432 us, 128x4 403 us, 160x2 547 us, 16 rows x 192 threads 404 us vs 372 us;
+          // after the arithmetic trim: 64x5 and 64x6 370 us vs 362 us
           if (R == 16) DFB_PAIR_LAUNCH(192, 2);
-          else if (cfg == 1) DFB_PAIR_LAUNCH(64, 5);
-          else if (cfg == 2) DFB_PAIR_LAUNCH(64, 6);
           else DFB_PAIR_LAUNCH(96, 4);
 #undef DFB_PAIR_LAUNCH
           DFB_LAUNCH_CHECK();

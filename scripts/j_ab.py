@@ -27,9 +27,11 @@ d_wg, d_dwg = torch.from_numpy(wg).cuda(), torch.from_numpy(dwg).cuda()
 P = lambda t: C.c_void_p(t.data_ptr())
 ref = None
 shuffle = len(sys.argv) > 2 and sys.argv[2] == "shuffle"
-CFGS = [("pairs 96x4", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_CFG": "0"}),
-        ("pairs 64x5", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_CFG": "1"}),
-        ("pairs 64x6", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_CFG": "2"})]
+CFGS = [("pull", {"DFB_J_VARIANT": "pull"}),
+        ("pairs morton", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "morton"}),
+        ("pairs natural", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "natural"}),
+        ("pairs R=16", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "morton", "DFB_J_PAIR_ROWS": "16"}),
+        ("fused", {"DFB_J_VARIANT": "fused"})]
 for name, env in CFGS:
     os.environ.update(env)
     fs = api.FlowSystem(mesh)
@@ -60,5 +62,5 @@ for name, env in CFGS:
         if k >= 3:
             tf.append(a.elapsed_time(b))
     print(f"   F kernels {np.median(tf) * 1e3:8.1f} us", flush=True)
-    print(f"{name:12s} m={m} E={E}: J kernels {np.median(ts) * 1e3:8.1f} us   max rel diff vs pull {d:.2e}   plan {fs.L.dfb_plan_bytes(fs.plan) / 1e6:.0f} MB", flush=True)
+    print(f"{name:12s} m={m} E={E}: J kernels {np.median(ts) * 1e3:8.1f} us   max rel diff vs first {d:.2e}   plan {fs.L.dfb_plan_bytes(fs.plan) / 1e6:.0f} MB", flush=True)
     fs.close()
