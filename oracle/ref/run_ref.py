@@ -45,6 +45,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--m", type=int, default=6)
     ap.add_argument("--shuffle", action="store_true")
+    ap.add_argument("--delaunay", action="store_true", help="unstructured mesh (tests/conftest.py::delaunay_mesh); the mesh is stored in the golden file")
     ap.add_argument("--state", default="B")
     ap.add_argument("--golden", default=None)
     ap.add_argument("--out", default=None)
@@ -53,7 +54,11 @@ def main():
     ap.add_argument("--no-d1-patch", action="store_true")
     args = ap.parse_args()
 
-    if args.shuffle:
+    if args.delaunay:
+        from conftest import delaunay_mesh
+        mesh = delaunay_mesh()
+        args.m = 0
+    elif args.shuffle:
         from conftest import shuffled_mesh
         mesh = shuffled_mesh(args.m)
     else:
@@ -211,7 +216,11 @@ def main():
             color=color, batch_offset=boff, batch_ind=bind,
             F=Fh, A00=blocks[0], A01=blocks[1], A10=blocks[2], A11=blocks[3], x=x, y=yh, dx=dxh,
             res_iters=np.array(sorted(res_true)), res_true=np.array([res_true[k] for k in sorted(res_true)]),
-            dx120=sols[120], printed=np.array(printed, dtype=np.float64).reshape(-1, 2))
+            dx120=sols[120], printed=np.array(printed, dtype=np.float64).reshape(-1, 2),
+            **({"mesh_xg": mesh.xg, "mesh_ien": mesh.ien, "mesh_bound_node_offset": mesh.bound_node_offset,
+                "mesh_bound_node": mesh.bound_node, "mesh_bound_elem_offset": mesh.bound_elem_offset,
+                "mesh_bound_f2e": mesh.bound_f2e, "mesh_bound_forn": mesh.bound_forn, "mesh_bound_ien": mesh.bound_ien}
+               if args.delaunay else {}))
 
 
 if __name__ == "__main__":

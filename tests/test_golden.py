@@ -3,20 +3,29 @@
 from pathlib import Path
 
 import numpy as np
+import pytest
 
 from conftest import shuffled_mesh
 from dedflow_b200 import boxmesh
 from oracle import pyoracle
 
-GOLDEN = Path(__file__).resolve().parent / "golden" / "ref_m6_shuffled_stateB.npz"
+GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
+GOLDEN = GOLDEN_DIR / "ref_m6_shuffled_stateB.npz"
+GOLDENS = ["ref_m6_shuffled_stateB.npz", "ref_delaunay_stateB.npz"]
 
 
-def load_golden():
-    return dict(np.load(GOLDEN))
+def load_golden(name=None):
+    return dict(np.load(GOLDEN_DIR / name if name else GOLDEN))
 
 
 def golden_mesh(g):
-    assert bool(g["shuffle"]) and str(g["state"]) == "B"
+    assert str(g["state"]) == "B"
+    if "mesh_xg" in g:      # unstructured golden: the mesh travels inside the file (qhull output is not ours to reproduce)
+        return boxmesh.BoxMesh(m=0, num_node=g["mesh_xg"].shape[0], num_tet=g["mesh_ien"].shape[0], xg=g["mesh_xg"],
+                               ien=g["mesh_ien"], bound_node_offset=g["mesh_bound_node_offset"], bound_node=g["mesh_bound_node"],
+                               bound_elem_offset=g["mesh_bound_elem_offset"], bound_f2e=g["mesh_bound_f2e"],
+                               bound_forn=g["mesh_bound_forn"], bound_ien=g["mesh_bound_ien"])
+    assert bool(g["shuffle"])
     return shuffled_mesh(int(g["m"]))
 
 
@@ -24,8 +33,9 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
-def test_oracle_integer_outputs_bit_exact_vs_reference(oracle):
-    g = load_golden()
+@pytest.mark.parametrize("golden", GOLDENS)
+def test_oracle_integer_outputs_bit_exact_vs_reference(oracle, golden):
+    g = load_golden(golden)
     mesh = golden_mesh(g)
     N = mesh.num_node
     rp, ci = oracle.nodal_pattern(N, mesh.ien)
@@ -41,8 +51,9 @@ def test_oracle_integer_outputs_bit_exact_vs_reference(oracle):
     assert np.array_equal(off, g["batch_offset"]) and np.array_equal(ind, g["batch_ind"])
 
 
-def test_oracle_assembly_and_solve_vs_reference(oracle):
-    g = load_golden()
+@pytest.mark.parametrize("golden", GOLDENS)
+def test_oracle_assembly_and_solve_vs_reference(oracle, golden):
+    g = load_golden(golden)
     mesh = golden_mesh(g)
     N = mesh.num_node
     wg, dwg = boxmesh.state_random(N)

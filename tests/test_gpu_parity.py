@@ -452,9 +452,10 @@ def test_full_size_properties(api, m, num_tet):
 # ---------------------------------------------------------------------------------------------------------------
 # golden vectors produced by the reference's OWN CUDA build on a B200 (oracle/ref/run_ref.py, tests/golden/README.md)
 # ---------------------------------------------------------------------------------------------------------------
-def test_cuda_path_matches_reference_golden(api):
+@pytest.mark.parametrize("golden", ["ref_m6_shuffled_stateB.npz", "ref_delaunay_stateB.npz"])
+def test_cuda_path_matches_reference_golden(api, golden):
     from test_golden import load_golden, golden_mesh
-    g = load_golden()
+    g = load_golden(golden)
     mesh = golden_mesh(g)
     N = mesh.num_node
     fs = api.FlowSystem(mesh)
