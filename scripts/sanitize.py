@@ -20,6 +20,11 @@ for mesh in (delaunay_mesh(120, 12), boxmesh.make_box(5)):
     for mode in ("gather", "atomic", "colored"):
         fs.assemble_system(wg, dwg, F=F, mode=mode)
         fs.assemble_system(wg, dwg, J=True, mode=mode)
+    import os
+    for variant in ("pull", "fused", "pairs"):       # the three atomic-free Jacobian kernels (read per call)
+        os.environ["DFB_J_VARIANT"] = variant
+        fs.assemble_system(wg, dwg, J=True, mode="gather")
+    os.environ.pop("DFB_J_VARIANT")
     x = torch.randn(6 * N, dtype=torch.float64, device="cuda")
     y = torch.zeros_like(x)
     fs.matrix_matvec(x, y)
