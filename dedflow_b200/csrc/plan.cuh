@@ -50,12 +50,12 @@ struct dfb_plan {
   mutable int pr_rows = 0, pr_n_cta = 0, pr_n_items = 0, pr_max_elems = 0;
   mutable int4* pr_grp = nullptr;       // [pr_n_cta] {first staged element, #elements, first item, #items}: one 16-byte load per CTA
   mutable int4* pr_enodes = nullptr;    // the four node ids of every staged element (parallel to pr_elems): skips elems -> ien
-  mutable int* pr_grp_item = nullptr;   // [pr_n_cta+1] first item of every group
+  mutable int* pr_grp_item = nullptr;   // [pr_n_cta+1] first item of every group (build time only, folded into pr_grp)
   mutable uint2* pr_meta = nullptr;     // [pr_n_items] {row i (0xffffffff: padding), k_ij | 0x100 diagonal | k_ji << 16}
   mutable int* pr_item_ptr = nullptr;   // [pr_n_items+1] offsets into pr_contrib
   mutable unsigned short* pr_contrib = nullptr;   // local record index << 4 | a << 2 | b, ascending (element, a, b) per item
-  mutable int* pr_elem_ptr = nullptr;   // [pr_n_cta+1]
-  mutable int* pr_elems = nullptr;      // ascending distinct element ids per group
+  mutable int* pr_elem_ptr = nullptr;   // [pr_n_cta+1]                              (build time only, folded into pr_grp)
+  mutable int* pr_elems = nullptr;      // ascending distinct element ids per group  (build time only, see pr_enodes)
   mutable size_t pr_bytes = 0;
 };
 

@@ -777,8 +777,11 @@ int build_pairs(const dfb_plan* p, int R, const f64* d_xg, cudaStream_t st) {
                                                                           p->pr_grp, p->pr_enodes);
   DFB_LAUNCH_CHECK();
   DFB_CUDA(cudaStreamSynchronize(st));
-  p->pr_bytes = sizeof(int4) * ((size_t)n_cta + (size_t)total_ge) + sizeof(int) * 2 * ((size_t)n_cta + 1) + sizeof(uint2) * (size_t)n_items +
-                sizeof(int) * ((size_t)n_items + 1) + sizeof(int) * (size_t)total_ge + sizeof(unsigned short) * (size_t)n_contrib;
+  // the kernel reads the group descriptors and the per-group node lists only: the intermediate lists go
+  cudaFree(p->pr_grp_item); cudaFree(p->pr_elem_ptr); cudaFree(p->pr_elems);
+  p->pr_grp_item = nullptr; p->pr_elem_ptr = nullptr; p->pr_elems = nullptr;
+  p->pr_bytes = sizeof(int4) * ((size_t)n_cta + (size_t)total_ge) + sizeof(uint2) * (size_t)n_items +
+                sizeof(int) * ((size_t)n_items + 1) + sizeof(unsigned short) * (size_t)n_contrib;
   p->pr_state = 1;
   if (getenv("DFB_VERBOSE"))
     fprintf(stderr, "[dfb] pair plan: %d groups of %d rows, %.1f staged elements per group (max %d), %d items, %d contributions, %.1f MB\n",
