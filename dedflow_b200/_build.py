@@ -29,6 +29,28 @@ def _newer(a: Path, deps) -> bool:
     return all(t >= d.stat().st_mtime for d in deps)
 
 
+def build_variant(name: str, defines) -> Path:
+    """A/B build: the same sources with extra -D flags into dedflow_b200/_obj/<name>/lib<name>.so (load it with DFB_LIB=...).
+    Example: build_variant("pdl", ["-DDFB_ENABLE_PDL"]) for the programmatic-dependent-launch experiment (then DFB_PDL=1)."""
+    out = OBJ / name
+    out.mkdir(parents=True, exist_ok=True)
+    objs = []
+    for s in SOURCES:
+        o = out / (Path(s).stem + ".o")
+        cmd = [NVCC, *ARCH, *FLAGS, *defines, "-I", str(PKG.parent / "include"), "-c", str(CSRC / s), "-o", str(o)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {s} ({name}):\n{r.stderr}")
+        objs.append(o)
+    lib = out / f"lib{name}.so"
+    cmd = [NVCC, *ARCH, "-shared", "-o", str(lib), *map(str, objs), "-Xlinker", "-Bsymbolic",
+           "-Xlinker", "--exclude-libs,ALL", "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed ({name}):\n{r.stderr}")
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
     headers = list(CSRC.glob("*.cuh")) + list((PKG.parent / "include").glob("*.h"))
@@ -64,5 +86,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(p)
+    if "--variant" in sys.argv:      # python -m dedflow_b200._build --variant pdl -DDFB_ENABLE_PDL
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+        print(p)

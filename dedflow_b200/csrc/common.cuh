@@ -146,6 +146,19 @@ __device__ __forceinline__ f64 ll_load(const unsigned long long* slot, unsigned 
   }
   return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
 }
+// Programmatic dependent launch -- EXPERIMENT, compiled only with -DDFB_ENABLE_PDL (the default build is unchanged: the
+// prologue below is empty) and switched on at run time with DFB_PDL=1.  The Krylov kernels call the prologue first: it lets
+// the NEXT kernel's blocks be scheduled as soon as every block of this grid has started, and then waits until the PREVIOUS
+// grid has completed and its writes are visible -- stream-order semantics, minus the launch latency and block-scheduling
+// ramp at each of the four kernel boundaries of a GMRES iteration.  Not measured yet.
+#ifdef DFB_ENABLE_PDL
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#else
+__device__ __forceinline__ void pdl_prologue() {}
+#endif
 __device__ __forceinline__ void p2p_wait(const unsigned long long* flag, unsigned long long seq) {
   unsigned long long v;
   do {

@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int
                                                  const f64* __restrict__ x, size_t x_poff, f64 beta, f64* __restrict__ y,
                                                  size_t y_poff, const P2PView* __restrict__ pv, unsigned long long hseq,
                                                  int n_interior) {
+  pdl_prologue();
   if (PEER) {
     const int last_row = row0 + (int)((((size_t)blockIdx.x + 1) * blockDim.x - 1) / G);
     if (last_row >= n_interior) {   // block-uniform
@@ -180,6 +181,23 @@ __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int
   }
 }
 
+#ifdef DFB_ENABLE_PDL
+static bool pdl_on() {
+  static const bool on = [] { const char* e = getenv("DFB_PDL"); return e && *e && *e != '0'; }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static int spmv_group() {
   static int g = 0;
   if (g == 0) {
@@ -196,12 +214,22 @@ int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, cons
                 const P2PView* pv = nullptr, unsigned long long hseq = 0, int n_interior = 0) {
   if (row1 <= row0) return DFB_OK;
   const i64 rows = row1 - row0;
+#ifdef DFB_ENABLE_PDL
+#define DFB_SPMV_PDL(G)                                                                                                          \
+  if (pdl_on()) {                                                                                                                \
+    auto kfn = k_spmv_fs<G, false>;                                                                                              \
+    DFB_CUDA(launch_pdl(kfn, dim3(ceil_div(rows * G, 256)), dim3(256), st, row0, row1, row_ptr, col_ind, A00, A01, A10, A11,     \
+                        alpha, x, x_poff, beta, y, y_poff, (const P2PView*)nullptr, 0ull, 0));                                   \
+  } else
+#else
+#define DFB_SPMV_PDL(G)
+#endif
 #define DFB_SPMV(G)                                                                                                              \
   do {                                                                                                                           \
     if (pv)                                                                                                                      \
       k_spmv_fs<G, true><<<ceil_div(rows * G, 256), 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x,   \
                                                                   x_poff, beta, y, y_poff, pv, hseq, n_interior);               \
-    else                                                                                                                         \
+    else DFB_SPMV_PDL(G)                                                                                                         \
       k_spmv_fs<G, false><<<ceil_div(rows * G, 256), 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x,  \
                                                                    x_poff, beta, y, y_poff, nullptr, 0ull, 0);                  \
   } while (0)
@@ -283,6 +311,7 @@ __global__ void k_pc_apply(int n, const f64* __restrict__ dinv00, const f64* __r
 __global__ void k_scale_pc_apply(int n, const f64* __restrict__ scale, const f64* __restrict__ dinv00,
                                  const f64* __restrict__ dinv11, f64* __restrict__ w, size_t w_poff, f64* __restrict__ z,
                                  size_t z_poff) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const f64 s = *scale;
@@ -444,6 +473,7 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
                                                   unsigned* ctr, const P2PView* __restrict__ pv, unsigned long long seq) {
   __shared__ f64 smj[8][JT];
   __shared__ f64 hsum[P2P_ACAP];
+  pdl_prologue();
   const int ngrp = gridDim.y, gbase = ncol / ngrp, grem = ncol - gbase * ngrp;
   const int j0 = blockIdx.y * gbase + min((int)blockIdx.y, grem);
   const int nj = gbase + ((int)blockIdx.y < grem ? 1 : 0);
@@ -521,6 +551,7 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
   constexpr int PW = 32 / USPLIT;  // row pairs per warp
   __shared__ f64 sh[128];
   __shared__ f64 sm[8];
+  pdl_prologue();
   if (pv) {   // fused all-reduce of h: wait for every rank's partial (stored into OUR mailbox), sum in rank order
     const int R = pv->nranks, par = (int)(seq & 1ull);
     for (int j = threadIdx.x; j < ncol; j += 256) {
@@ -976,6 +1007,12 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
       prof.end(st);
     } else {
       prof.begin("scale_pc_apply", st);
+#ifdef DFB_ENABLE_PDL
+      if (pdl_on())
+        DFB_CUDA(launch_pdl(k_scale_pc_apply, dim3(ceil_div(n_own, 128)), dim3(128), st, n_own, (const f64*)&W->S->inv_norm, (const f64*)dinv00,
+                            (const f64*)dinv11, QCOL(iter), poffC, zvec, poffN));
+      else
+#endif
       k_scale_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, &W->S->inv_norm, dinv00, dinv11, QCOL(iter), poffC,
                                                             zvec, poffN);
       DFB_LAUNCH_CHECK();
@@ -990,6 +1027,12 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     prof.begin("multidot", st);
     const int ny = ceil_div(ncol, JT);
     const int mg = std::max(1, std::min(mgrid, (4 * num_sms()) / ny));   // one resident wave of (row chunk, column group) blocks
+#ifdef DFB_ENABLE_PDL
+    if (pdl_on() && !pv)
+      DFB_CUDA(launch_pdl(k_multidot, dim3(mg, ny), dim3(256), st, nl, (const f64*)Q, ldq, ncol, (const f64*)w, W->part, HCOL(iter), W->ctr,
+                          pv, seq));
+    else
+#endif
     k_multidot<<<dim3(mg, ny), 256, 0, st>>>(nl, Q, ldq, ncol, w, W->part, HCOL(iter), W->ctr, pv, seq);
     DFB_LAUNCH_CHECK();
     prof.end(st);
@@ -1000,6 +1043,12 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     }
     // w -= Q h, fused with ||w||^2 and (single GPU) the scalar Givens step  (krylov.c:176-183, 229-277)
     prof.begin("update", st);
+#ifdef DFB_ENABLE_PDL
+    if (pdl_on() && !pv)
+      DFB_CUDA(launch_pdl(k_update, dim3(ugrid), dim3(256), st, nl, (const f64*)Q, ldq, ncol, HCOL(iter), w, W->part, &W->S->nrm2_live,
+                          W->ctr + 1, W->parallel ? 0 : 1, W->S, W->gv, W->beta, W->tailc, W->res_hist, pv, seq));
+    else
+#endif
     k_update<<<ugrid, 256, 0, st>>>(nl, Q, ldq, ncol, HCOL(iter), w, W->part, &W->S->nrm2_live, W->ctr + 1, W->parallel ? 0 : 1,
                                     W->S, W->gv, W->beta, W->tailc, W->res_hist, pv, seq);
     DFB_LAUNCH_CHECK();
