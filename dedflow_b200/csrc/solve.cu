@@ -433,8 +433,10 @@ __device__ __forceinline__ bool last_block(unsigned* ctr, unsigned total) {
 }
 
 
-// Stage 1 of the multi-dot for a group of NJ columns: a thread streams 16-byte pairs of rows, U row pairs per trip, so that
-// (NJ + 1) x U independent 16-byte loads are in flight (18 for a full group).
+// Stage 1 of the multi-dot for a group of NJ columns: a thread streams 16-byte pairs of rows, U row pairs per trip:
+// (NJ + 1) x U independent 16-byte loads per trip (18 for a full group).  ptxas keeps the kernel at 64 registers (4 CTAs of
+// 256 threads per SM) and issues them about five at a time; with 1024 resident threads per SM that is still several times the
+// bytes in flight the HBM latency-bandwidth product asks for.
 template <int NJ>
 __device__ __forceinline__ void md_accum(const double2* __restrict__ q2, const double2* __restrict__ w2, size_t np, size_t ld2,
                                          f64 (&acc)[JT]) {
