@@ -8,7 +8,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from conftest import ROOT, shuffled_mesh
+from conftest import ROOT, delaunay_mesh, shuffled_mesh
 from dedflow_b200 import boxmesh
 from oracle import pyoracle
 
@@ -179,10 +179,12 @@ def probe():
     return C.CDLL(str(so))
 
 
-def test_kernel_element_math_matches_oracle(oracle, probe):
+@pytest.mark.parametrize("kind", ["box", "delaunay"])
+def test_kernel_element_math_matches_oracle(oracle, probe, kind):
     """The hoisted Jacobian / residual / face arithmetic the CUDA kernels use (elem_math.cuh, evaluated on the host)
-    against the reference-ordered oracle: max|d| / max|A| <= 1e-12 per sub-block."""
-    m = shuffled_mesh(6)
+    against the reference-ordered oracle: max|d| / max|A| <= 1e-12 per sub-block.  Box: every local vertex
+    order; Delaunay: irregular geometry (slivers, element sizes over two orders of magnitude)."""
+    m = shuffled_mesh(6) if kind == "box" else delaunay_mesh(150, 15)
     N, E = m.num_node, m.num_tet
     for wg, dwg in (boxmesh.state_random(N), boxmesh.state_default(m)):
         vp = lambda a: a.ctypes.data_as(C.c_void_p)
