@@ -120,9 +120,24 @@ struct P2PView {
   const int* tgt_ptr;
   const int* tgt_q;
   const int* tgt_rid;
+  // Bounded waits: every poll loop below gives up after `timeout_ns` (a peer died or returned early from the solve) and raises
+  // *err; once *err is set every later wait of every later kernel returns at once, so the stream drains and the host sees
+  // the word at its next synchronisation point (dfb_gmres_solve_pc returns DFB_ERR_PEER).  A hung peer can therefore cost
+  // at most ~timeout per kernel in flight, never a GPU that has to be reset.
+  unsigned* err;
+  unsigned long long timeout_ns;
 };
 
-struct P2PHandle { P2PView host; const P2PView* dev; };   // what dfb_comm_p2p_view() returns
+// what dfb_comm_p2p_view() returns.  The sequence counters of the fused collectives belong to the COMMUNICATOR (one owner per
+// dfb_comm): every workspace that runs over the same mailbox draws from the same monotonically increasing counters, so a
+// mailbox tag or a halo flag left behind by an earlier solve (of this or of another workspace) can never satisfy a later wait.
+struct P2PHandle {
+  P2PView host;
+  const P2PView* dev;
+  unsigned long long* seq;    // all-reduce sequence (multi-dot / norm slots)
+  unsigned long long* hseq;   // halo sequence
+  unsigned* d_err;            // device error word (== host.err)
+};
 
 __host__ __device__ inline size_t p2p_a_ll(int R, int par, int r, int j) { return (((size_t)par * R + r) * P2P_ACAP + j) * 2; }
 __host__ __device__ inline size_t p2p_b_ll(int R, int par, int r) { return (size_t)4 * R * P2P_ACAP + ((size_t)par * R + r) * 2; }
@@ -137,11 +152,27 @@ __device__ __forceinline__ void ll_store(unsigned long long* slot, f64 v, unsign
   const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
   asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"((b & 0xffffffffull) | t), "l"((b >> 32) | t) : "memory");
 }
-__device__ __forceinline__ f64 ll_load(const unsigned long long* slot, unsigned tag) {
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// true once the wait has to be abandoned: the error word is already raised, or this wait ran out of time (then it raises it)
+__device__ __forceinline__ bool p2p_give_up(const P2PView* pv, unsigned long long t0) {
+  if (*(volatile unsigned*)pv->err) return true;
+  if (global_ns() - t0 > pv->timeout_ns) { atomicExch(pv->err, 1u); return true; }
+  return false;
+}
+__device__ __forceinline__ f64 ll_load(const P2PView* pv, const unsigned long long* slot, unsigned tag) {
   unsigned long long w0, w1;
-  while (true) {
+  unsigned long long t0 = 0;
+  for (unsigned spin = 0;; spin++) {
     asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
     if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) break;
+    if ((spin & 255u) == 0u) {          // the clock and the error word are looked at every 256th poll only
+      if (spin == 0u) t0 = global_ns();
+      else if (p2p_give_up(pv, t0)) return 0.0;
+    }
     __nanosleep(20);
   }
   return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
@@ -159,13 +190,18 @@ __device__ __forceinline__ void pdl_prologue() {
 #else
 __device__ __forceinline__ void pdl_prologue() {}
 #endif
-__device__ __forceinline__ void p2p_wait(const unsigned long long* flag, unsigned long long seq) {
+__device__ __forceinline__ void p2p_wait(const P2PView* pv, const unsigned long long* flag, unsigned long long seq) {
   unsigned long long v;
-  do {
+  unsigned long long t0 = 0;
+  for (unsigned spin = 0;; spin++) {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
     if (v >= seq) break;
+    if ((spin & 255u) == 0u) {
+      if (spin == 0u) t0 = global_ns();
+      else if (p2p_give_up(pv, t0)) return;
+    }
     __nanosleep(32);
-  } while (true);
+  }
 }
 #endif
 

@@ -11,6 +11,8 @@
 // already-loaded libnccl.so.2 is reused.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -110,6 +112,8 @@ struct dfb_comm {
   int* d_remote_nodes = nullptr;
   int *d_tgt_ptr = nullptr, *d_tgt_q = nullptr, *d_tgt_rid = nullptr;
   unsigned* d_push_ctr = nullptr;
+  unsigned* d_err = nullptr;            // raised by a kernel whose bounded wait ran out (common.cuh p2p_give_up)
+  unsigned long long seq = 0, hseq = 0; // sequence counters of the fused collectives: ONE owner per communicator
   P2PView* d_view = nullptr;
   P2PView h_view;
   P2PHandle handle;
@@ -147,7 +151,7 @@ void dfb_comm_destroy(dfb_comm* c) {
   for (int r = 0; r < c->nranks && r < P2P_MAXR; r++)
     if (c->peer_base[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_base[r]);
   cudaFree(c->d_tgt_ptr); cudaFree(c->d_tgt_q); cudaFree(c->d_tgt_rid);
-  cudaFree(c->shared); cudaFree(c->d_remote_nodes); cudaFree(c->d_push_ctr); cudaFree(c->d_view);
+  cudaFree(c->shared); cudaFree(c->d_remote_nodes); cudaFree(c->d_push_ctr); cudaFree(c->d_err); cudaFree(c->d_view);
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
   if (c->ev_done) cudaEventDestroy(c->ev_done);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
@@ -308,6 +312,16 @@ int dfb_comm_p2p_connect(dfb_comm* c, const void* handles, const int* h_remote_n
     DFB_CUDA(cudaMemset(c->d_push_ctr, 0, sizeof(unsigned)));
   }
   v.push_ctr = c->d_push_ctr;
+  if (!c->d_err) {
+    DFB_CUDA(cudaMalloc(&c->d_err, sizeof(unsigned)));
+    DFB_CUDA(cudaMemset(c->d_err, 0, sizeof(unsigned)));
+  }
+  v.err = c->d_err;
+  {   // wait budget of one poll loop (default 10 s; DFB_P2P_TIMEOUT_MS overrides, tests use a short one)
+    const char* e = getenv("DFB_P2P_TIMEOUT_MS");
+    const double ms = e ? atof(e) : 10000.0;
+    v.timeout_ns = (unsigned long long)((ms > 0.0 ? ms : 10000.0) * 1e6);
+  }
   if (!c->d_view) DFB_CUDA(cudaMalloc(&c->d_view, sizeof(P2PView)));
   DFB_CUDA(cudaMemcpy(c->d_view, &v, sizeof(P2PView), cudaMemcpyHostToDevice));
   c->p2p_ready = true;
@@ -319,6 +333,9 @@ const void* dfb_comm_p2p_view(dfb_comm* c) {
   if (!c || !c->p2p_ready) return nullptr;
   c->handle.host = c->h_view;
   c->handle.dev = c->d_view;
+  c->handle.seq = &c->seq;
+  c->handle.hseq = &c->hseq;
+  c->handle.d_err = c->d_err;
   return &c->handle;
 }
 

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int
   if (PEER) {
     const int last_row = row0 + (int)((((size_t)blockIdx.x + 1) * blockDim.x - 1) / G);
     if (last_row >= n_interior) {   // block-uniform
-      if ((int)threadIdx.x < pv->n_nbr) p2p_wait(pv->mbox_local + p2p_h_flag(pv->nranks, pv->nbr[threadIdx.x]), hseq);
+      if ((int)threadIdx.x < pv->n_nbr) p2p_wait(pv, pv->mbox_local + p2p_h_flag(pv->nranks, pv->nbr[threadIdx.x]), hseq);
       __syncthreads();
     }
   }
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(128) k_scale_pc_apply_peer(int n, const f64* _
   __shared__ f64 s_part[P2P_MAXR];
   if (seq) {
     const int R = pv->nranks, par = (int)(seq & 1ull);
-    if ((int)threadIdx.x < R) s_part[threadIdx.x] = ll_load(pv->mbox_local + p2p_b_ll(R, par, threadIdx.x), (unsigned)seq);
+    if ((int)threadIdx.x < R) s_part[threadIdx.x] = ll_load(pv, pv->mbox_local + p2p_b_ll(R, par, threadIdx.x), (unsigned)seq);
     __syncthreads();
     if (threadIdx.x == 0) {
       f64 nrm2 = 0.0;
@@ -424,6 +424,7 @@ __device__ __forceinline__ f64 block_sum_256(f64 v, f64* sm) {
 // which block is last) and re-arms the counter.
 __device__ __forceinline__ bool last_block(unsigned* ctr, unsigned total) {
   __shared__ bool is_last;
+  __syncthreads();   // every thread's partial-sum store is ordered before thread 0's fence + counter increment
   if (threadIdx.x == 0) {
     __threadfence();
     is_last = atomicAdd(ctr, 1u) == total - 1;
@@ -558,7 +559,7 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
     const int R = pv->nranks, par = (int)(seq & 1ull);
     for (int j = threadIdx.x; j < ncol; j += 256) {
       f64 s = 0.0;
-      for (int r = 0; r < R; r++) s += ll_load(pv->mbox_local + p2p_a_ll(R, par, r, j), (unsigned)seq);
+      for (int r = 0; r < R; r++) s += ll_load(pv, pv->mbox_local + p2p_a_ll(R, par, r, j), (unsigned)seq);
       sh[j] = s;
       if (blockIdx.x == 0) h[j] = s;
     }
@@ -780,7 +781,7 @@ __global__ void k_gmres_step_peer(int it, GmresScalars* S, f64* hcol, f64* gv, f
                                   const P2PView* __restrict__ pv, unsigned long long seq) {
   const int R = pv->nranks, par = (int)(seq & 1ull);
   __shared__ f64 s_part[P2P_MAXR];
-  if ((int)threadIdx.x < R) s_part[threadIdx.x] = ll_load(pv->mbox_local + p2p_b_ll(R, par, threadIdx.x), (unsigned)seq);
+  if ((int)threadIdx.x < R) s_part[threadIdx.x] = ll_load(pv, pv->mbox_local + p2p_b_ll(R, par, threadIdx.x), (unsigned)seq);
   __syncthreads();
   if (threadIdx.x == 0) {
     f64 s = 0.0;
@@ -834,7 +835,6 @@ struct dfb_gmres {
   size_t bytes = 0;
   int n_interior = 0;
   dfb_parallel_ops par = {0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
-  unsigned long long seq = 0, hseq = 0;   // sequence numbers of the fused peer-memory collectives (identical on all ranks)
   bool parallel = false;
 };
 
@@ -907,10 +907,8 @@ int dfb_gmres_set_parallel(dfb_gmres* w, const dfb_parallel_ops* ops) {
   if (ops->n_own <= 0 || ops->n_own > w->N || ops->n_interior < 0 || ops->n_interior > ops->n_own || !ops->allreduce ||
       !ops->halo_begin || !ops->halo_end) { set_error("dfb_gmres_set_parallel: bad argument"); return DFB_ERR_ARG; }
   w->par = *ops; w->parallel = true; w->n_own = ops->n_own; w->n_interior = ops->n_interior;
-  // Sequence numbers tag the mailbox slots of the communicator (32 low bits).  Every workspace that is made parallel starts
-  // from its own base (same creation order on all ranks), so tags left behind by an earlier workspace never match.
-  static unsigned long long n_parallel_ws = 0;
-  if (w->seq == 0) { w->seq = w->hseq = (n_parallel_ws++ & 0x7full) << 24; }
+  // The sequence numbers that tag the mailbox slots and halo flags live in the communicator (P2PHandle::seq / hseq), not
+  // here: every workspace over the same mailbox draws from the same monotonic counters.
   return DFB_OK;
 }
 
@@ -986,6 +984,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
 
   int iter = 0;
   bool converged = false;
+  unsigned peer_err = 0;   // peer-memory mode: raised by a kernel whose bounded wait for another rank ran out
   f64 rnrm_init = 0.0;
   std::vector<f64> hist((size_t)maxit + 1, 0.0);
   SolveProfiler prof;
@@ -996,7 +995,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     if (pv) {
       // one kernel: [norm all-reduce + Givens step of iteration iter-1] + scale + P^-1 + [halo push]; then ONE mat-vec launch
       // whose boundary-row blocks (scheduled last) wait for the neighbours' halo flags
-      const unsigned long long hseq = ++W->hseq;
+      const unsigned long long hseq = ++*ph->hseq;
       prof.begin("scale_pc_apply", st);
       k_scale_pc_apply_peer<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, dinv00, dinv11, QCOL(iter), poffC, zvec, poffN, pv, pending_seq,
                                                                   hseq, iter - 1, W->S, iter ? HCOL(iter - 1) : HCOL(0), W->gv, W->beta,
@@ -1025,7 +1024,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     }
     // h = Q^T w  (krylov.c:166-174)
     const int ncol = iter + 1;
-    const unsigned long long seq = pv ? ++W->seq : 0ull;
+    const unsigned long long seq = pv ? ++*ph->seq : 0ull;
     prof.begin("multidot", st);
     const int ny = ceil_div(ncol, JT);
     const int mg = std::max(1, std::min(mgrid, (4 * num_sms()) / ny));   // one resident wave of (row chunk, column group) blocks
@@ -1075,14 +1074,16 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     }
     if ((iter + 1) % 20 == 0) {  // the reference's only convergence test (krylov.c:281-290)
       DFB_CUDA(cudaMemcpyAsync(hist.data(), W->res_hist, sizeof(f64) * ((size_t)iter + 2), cudaMemcpyDeviceToHost, st));
+      if (ph) DFB_CUDA(cudaMemcpyAsync(&peer_err, ph->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
       DFB_CUDA(cudaStreamSynchronize(st));
+      if (peer_err) break;
       rnrm_init = hist[0];
       const f64 rnrm = hist[iter + 1];
       if (rnrm < atol || rnrm < (rnrm_init + 1e-16) * rtol) converged = true;
     }
     iter++;
   }
-  if (iter) {
+  if (iter && !peer_err) {
     prof.begin("trsv..axpy", st);
     static bool trsv_attr = false;
     if (!trsv_attr) {
@@ -1107,7 +1108,12 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     }
   }
   DFB_CUDA(cudaMemcpyAsync(hist.data(), W->res_hist, sizeof(f64) * ((size_t)iter + 1), cudaMemcpyDeviceToHost, st));
+  if (ph && !peer_err) DFB_CUDA(cudaMemcpyAsync(&peer_err, ph->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   DFB_CUDA(cudaStreamSynchronize(st));
+  if (peer_err) {
+    set_error("dfb_gmres_solve: a peer-memory wait timed out (a rank died or left the solve early); destroy the communicator");
+    return DFB_ERR_PEER;
+  }
   if (res_hist)
     for (int k = 0; k <= iter; k++) res_hist[k] = hist[k];
   *iters = iter;

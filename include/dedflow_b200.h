@@ -39,7 +39,9 @@ typedef enum dfb_status {
   DFB_ERR_ARG = -2,       /* bad argument */
   DFB_ERR_OVERFLOW = -3,  /* nodal row longer than 64 (reference csr.c:10,64 asserts) or i32 index overflow */
   DFB_ERR_COLOR = -4,     /* more than max_color rounds needed */
-  DFB_ERR_NODEVICE = -5   /* no CUDA device: there is no CPU fallback */
+  DFB_ERR_NODEVICE = -5,  /* no CUDA device: there is no CPU fallback */
+  DFB_ERR_PEER = -6       /* peer-memory collective timed out (a rank died or left the solve early); the communicator is
+                             unusable afterwards, destroy it */
 } dfb_status;
 
 const char* dfb_last_error(void);

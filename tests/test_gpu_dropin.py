@@ -199,3 +199,41 @@ def test_dropin_generic_matrix_ops(reflib, oracle):
     W01[rows] = 0.0
     assert np.array_equal(B01, W01)
     assert np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3])    # pressure rows untouched (defect D8)
+
+
+def test_dropin_vector_helpers(reflib):
+    """VecAXPY / VecPointwiseMult / VecPointwiseDiv / VecPointwiseInv (reference vec.h:7-10, vec.cu:14-70) through the exported
+    drop-in symbols: same argument order (VecAXPY(a, x, y, n): y = a*x + y; Mult/Div(x, y, z, n): z = x op y; Inv in place),
+    bit-exact against numpy (one rounding per entry), in-place aliasing, n not a multiple of the block size, n = 0."""
+    L = C.CDLL(str(reflib.HYBRID_SO.parents[2] / "dedflow_b200" / "libdedflow_b200.so"))
+    P = lambda t: C.c_void_p(t.data_ptr())
+    L.VecAXPY.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_int32]
+    L.VecPointwiseMult.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    L.VecPointwiseDiv.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    L.VecPointwiseInv.argtypes = [C.c_void_p, C.c_int32]
+    rng = np.random.default_rng(21)
+    for n in (1, 255, 256, 257, 100003):
+        x, y = rng.standard_normal(n), rng.standard_normal(n)
+        y[np.abs(y) < 1e-3] = 1.0
+        dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y.copy()).cuda()
+        dz = torch.full((n + 8,), -7.25, dtype=torch.float64, device="cuda")          # guard behind the end
+        L.VecPointwiseMult(P(dx), P(dy), P(dz), n)
+        assert np.array_equal(dz.cpu().numpy()[:n], x * y) and bool((dz[n:] == -7.25).all())
+        L.VecPointwiseDiv(P(dx), P(dy), P(dz), n)
+        assert np.array_equal(dz.cpu().numpy()[:n], x / y) and bool((dz[n:] == -7.25).all())
+        L.VecAXPY(-0.375, P(dx), P(dy), n)                                              # y = a*x + y
+        got = dy.cpu().numpy()
+        want_fma = np.array([np.float64(np.longdouble(-0.375) * np.longdouble(a) + np.longdouble(b)) for a, b in zip(x[:64], y[:64])])
+        assert np.abs(got - (-0.375 * x + y)).max() <= 2.3e-16 * np.abs(got).max()    # fused or unfused multiply-add
+        assert np.array_equal(got[:64], want_fma) or np.array_equal(got[:64], (-0.375 * x + y)[:64])
+        inv = torch.from_numpy(y.copy()).cuda()
+        L.VecPointwiseInv(P(inv), n)
+        assert np.array_equal(inv.cpu().numpy(), 1.0 / y)
+        L.VecPointwiseMult(P(dx), P(dx), P(dx), n)                                      # aliasing: x = x*x in place
+        assert np.array_equal(dx.cpu().numpy(), x * x)
+    before = dz.clone()
+    L.VecPointwiseMult(P(dx), P(dy), P(dz), 0)
+    L.VecAXPY(1.0, P(dx), P(dz), 0)
+    L.VecPointwiseInv(P(dz), 0)
+    torch.cuda.synchronize()
+    assert torch.equal(before, dz)

@@ -456,6 +456,81 @@ def test_full_size_properties(api, m, num_tet):
     fs.close()
 
 
+def test_benchmarked_mesh_matches_oracle_and_reference(api, oracle):
+    """BASELINE configs[1] -- the mesh bench.py times (m=55: 998,250 tets, 175,616 nodes), state B -- compared with BOTH
+    checkers in one test: the CPU oracle and the reference's own CUDA build (oracle/_ref/libdedflow_ref.so, main.c:31-75 and
+    main.c:215-221 driven by oracle/ref/reflib.py) run on the same GPU.  Integers bit-exact (blocked row_ptr on [0, nrows),
+    defect D1), F and the four sub-blocks <= 1e-12, the 40-iteration residual history and dx <= 1e-10."""
+    from oracle.ref import reflib
+    m = 55
+    mesh = boxmesh.make_box(m)
+    N, E = mesh.num_node, mesh.num_tet
+    assert E == 998250 and N == 175616
+    fs, wg, dwg = make_pair(api, oracle, mesh, "B")
+    ref = oracle_system(oracle, mesh, wg, dwg)
+    rp, ci = ref["pattern"]
+    # ---- integers vs the oracle
+    assert np.array_equal(fs.row_ptr.cpu().numpy(), rp) and np.array_equal(fs.col_ind.cpu().numpy(), ci)
+    assert ref["ties"] == 0 and fs.num_color == ref["nc"] and np.array_equal(fs.color.cpu().numpy(), ref["color"])
+    assert np.array_equal(fs.batch_offset, ref["off"]) and np.array_equal(fs.batch_ind.cpu().numpy(), ref["ind"])
+    # ---- assembly vs the oracle
+    d_wg, d_dwg = torch.from_numpy(wg).cuda(), torch.from_numpy(dwg).cuda()
+    F = torch.full((6 * N,), 7.0, dtype=torch.float64, device="cuda")
+    fs.assemble_system(d_wg, d_dwg, F=F)
+    for a in fs.blocks():
+        a.fill_(3.0)
+    fs.assemble_system(d_wg, d_dwg, J=True)
+    Fh = F.cpu().numpy()
+    assert rel(Fh[:3 * N], ref["F"][:3 * N]) <= TOL_ASM
+    assert np.abs(Fh[3 * N:4 * N] - ref["F"][3 * N:4 * N]).max() <= TOL_ASM * np.abs(ref["F"]).max()
+    assert np.all(Fh[4 * N:] == 0)
+    ours_blocks = [a.cpu().numpy() for a in fs.blocks()]
+    for got, want, name in zip(ours_blocks, ref["blocks"], ("A00", "A01", "A10", "A11")):
+        assert rel(got, want) <= TOL_ASM, name
+    # ---- Krylov solve on OUR assembled system vs the oracle's solve on ITS system (the whole step end to end)
+    xo, ito, histo = oracle.gmres(ref["pattern"], ref["blocks"], ref["F"])
+    dx = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    it, hist = fs.krylov_solve(dx, F)
+    assert it == ito == 40
+    assert np.abs(hist - histo).max() <= TOL_SOLVE * histo[0]
+    dxh = dx.cpu().numpy()
+    assert rel(dxh[:4 * N], xo[:4 * N]) <= TOL_SOLVE and np.all(dxh[4 * N:] == 0)
+    # ---- the reference's own CUDA build, same GPU, same inputs
+    if not reflib.available():
+        pytest.fail("oracle/_ref/libdedflow_ref.so is missing: run __graft_entry__.build() where /root/reference exists")
+    R = reflib.RefProblem(mesh, patch_d1=False)
+    pats = R.patterns()
+    assert np.array_equal(pats["1x1"][0], rp) and np.array_equal(pats["1x1"][1], ci)
+    for name, (br, bc) in {"3x3": (3, 3), "3x1": (3, 1), "1x3": (1, 3)}.items():
+        nrp, nci = fs.csr_attr_create_block(br, bc)
+        nrows = br * N
+        assert np.array_equal(nrp.cpu().numpy()[:nrows], pats[name][0][:nrows])          # last entry: defect D1 (never written)
+        assert np.array_equal(nci.cpu().numpy(), pats[name][1])
+    rcolor, roff, rind, rnc = R.color_batches()
+    assert rnc == fs.num_color and np.array_equal(rcolor, ref["color"])
+    assert np.array_equal(roff, fs.batch_offset) and np.array_equal(rind, ref["ind"])
+    for a in (R.spy1x3, R.spy3x1, R.spy3x3):            # D1 patched from outside before the reference's cuSPARSE mat-vecs read it
+        ac = a.contents
+        last = torch.tensor([ac.nnz], dtype=torch.int32, device="cuda")
+        R._copy_d2d(ac.row_ptr + 4 * ac.num_row, last.data_ptr(), 4)
+    rF = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    R.assemble(d_wg, d_dwg, F_t=rF)
+    R.assemble(d_wg, d_dwg, J=True)
+    torch.cuda.synchronize()
+    rFh = rF.cpu().numpy()
+    assert rel(Fh[:3 * N], rFh[:3 * N]) <= TOL_ASM
+    assert np.abs(Fh[3 * N:4 * N] - rFh[3 * N:4 * N]).max() <= TOL_ASM * np.abs(rFh).max()
+    for got, want, name in zip(ours_blocks, R.block_vals(), ("A00", "A01", "A10", "A11")):
+        assert rel(got, want) <= TOL_ASM, ("reference", name)
+    rdx = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    printed = R.solve(rdx, rF)
+    assert [p[0] for p in printed] == [0, 20, 40]
+    for k, v in printed:                                 # the reference prints 5 digits
+        assert abs(hist[k] - v) <= 6e-5 * v
+    assert rel(dxh[:4 * N], rdx.cpu().numpy()[:4 * N]) <= TOL_SOLVE
+    fs.close()
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # golden vectors produced by the reference's OWN CUDA build on a B200 (oracle/ref/run_ref.py, tests/golden/README.md)
 # ---------------------------------------------------------------------------------------------------------------
