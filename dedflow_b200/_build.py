@@ -31,7 +31,7 @@ def _newer(a: Path, deps) -> bool:
 
 def build_variant(name: str, defines) -> Path:
     """A/B build: the same sources with extra -D flags into dedflow_b200/_obj/<name>/lib<name>.so (load it with DFB_LIB=...).
-    Example: build_variant("pdl", ["-DDFB_ENABLE_PDL"]) for the programmatic-dependent-launch experiment (then DFB_PDL=1)."""
+    Example: build_variant("u4", ["-DUPDATE_REVERSE=0"]) for a forward-sweeping update kernel."""
     out = OBJ / name
     out.mkdir(parents=True, exist_ok=True)
     objs = []
@@ -86,7 +86,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    if "--variant" in sys.argv:      # python -m dedflow_b200._build --variant pdl -DDFB_ENABLE_PDL
+    if "--variant" in sys.argv:      # python -m dedflow_b200._build --variant NAME -DFLAG ...
         i = sys.argv.index("--variant")
         print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
     else:

@@ -154,6 +154,129 @@ __global__ void k_gatherF(int N, int n_rows, const int* __restrict__ v2c_ptr, co
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// F, PATCH variant (default of DFB_MODE_GATHER; plan.cuh fp_*, setup.cu build_fpatch).  One CTA per patch of FP_PE = 256
+// Morton-ordered elements, three phases:
+//   A. the patch's ~90-130 distinct NODES are staged once in shared memory (14 doubles each, thread t <-> node t: 14
+//      independent loads in flight per thread) instead of 56 gathers per element;
+//   B. every thread evaluates the residual of two elements out of the staged node records (no global load in the FP64 phase:
+//      the dependent-load chain ien -> node ids -> 56 values that kept the FP64 pipe at 40 % is gone) and parks the 24 results in
+//      a staging area (stride 25 doubles: conflict-free);
+//   C. one thread per (patch-node, component) sums that node's corners in ascending (element, a) order -- the patch's corners
+//      are pre-sorted by node -- and writes ONE partial per patch-node: 48 B x ~2 per mesh node instead of 24 corner records x
+//      48 B (the 2 x 192 MB scratch round trip of k_elemF + k_gatherF becomes 2 x 17 MB).
+// k_gatherF2 then adds the ~2 partials of every node in ascending patch order.  Fixed order everywhere: deterministic.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int FP_SN = em::NREC + 1;   // shared-memory stride of a node record (odd: bank spreading)
+constexpr int FP_SE = 25;             // stride of an element's 24 staged results
+
+template <int MINB>   // resident CTAs per SM the register budget is set for: 3 -> 168 registers (some spills), 2 -> 255
+__global__ void __launch_bounds__(128, MINB) k_patchF(int N, const int2* __restrict__ hdr, const int* __restrict__ pnodes,
+                                                   const ushort4* __restrict__ lnode, const unsigned short* __restrict__ corner,
+                                                   const unsigned short* __restrict__ cstart, const f64* __restrict__ xg,
+                                                   const f64* __restrict__ wg, const f64* __restrict__ dwg, f64* __restrict__ part,
+                                                   int max_nodes) {
+  extern __shared__ __align__(16) f64 fp_smem[];
+  f64* sn = fp_smem;                               // [max_nodes][FP_SN]
+  f64* se = fp_smem + (size_t)max_nodes * FP_SN;   // [FP_PE][FP_SE]
+  unsigned short* scl = reinterpret_cast<unsigned short*>(se + (size_t)FP_PE * FP_SE);   // [4 FP_PE] corners sorted by node
+  unsigned short* scs = scl + 4 * FP_PE;                                                  // [max_nodes + 1] their ranges
+  const int p = blockIdx.x;
+  const int2 h = __ldg(hdr + p);
+  const int pb = h.x, nn = h.y;
+  // element connectivity of phase B and the corner lists of phase C are fetched together with the node ids of phase A
+  // (independent chains, all coalesced)
+  const ushort4 ln0 = lnode[(size_t)p * FP_PE + threadIdx.x];
+  const ushort4 ln1 = lnode[(size_t)p * FP_PE + 128 + threadIdx.x];
+  {
+    const uint4 c8 = __ldg(reinterpret_cast<const uint4*>(corner + (size_t)p * 4 * FP_PE) + threadIdx.x);   // 8 corners per thread
+    reinterpret_cast<uint4*>(scl)[threadIdx.x] = c8;
+    const unsigned short* cs = cstart + (size_t)pb + p;
+    for (int k = threadIdx.x; k <= nn; k += 128) scs[k] = cs[k];
+  }
+  // ---- A: node records (thread t <-> nodes t and t + 128: up to 28 independent loads in flight) ----
+  for (int k0 = 0; k0 < nn; k0 += 256) {
+    f64 v[2][em::NREC];
+    int kk[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      kk[r] = k0 + r * 128 + threadIdx.x;
+      if (kk[r] < nn) {
+        const size_t nd = (size_t)__ldg(pnodes + pb + kk[r]);
+        const f64* px = xg + nd * 3;
+        const f64* pu = wg + nd * 3;
+        const f64* pd = dwg + nd * 3;
+        v[r][0] = __ldg(px); v[r][1] = __ldg(px + 1); v[r][2] = __ldg(px + 2);
+        v[r][3] = __ldg(pu); v[r][4] = __ldg(pu + 1); v[r][5] = __ldg(pu + 2);
+        v[r][6] = __ldg(pd); v[r][7] = __ldg(pd + 1); v[r][8] = __ldg(pd + 2);
+        v[r][9] = __ldg(dwg + (size_t)3 * N + nd);
+        v[r][10] = __ldg(wg + (size_t)4 * N + nd); v[r][11] = __ldg(dwg + (size_t)4 * N + nd);
+        v[r][12] = __ldg(wg + (size_t)5 * N + nd); v[r][13] = __ldg(dwg + (size_t)5 * N + nd);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+      if (kk[r] < nn) {
+        f64* rec = sn + (size_t)kk[r] * FP_SN;
+#pragma unroll
+        for (int c = 0; c < em::NREC; c++) rec[c] = v[r][c];
+      }
+  }
+  __syncthreads();
+  // ---- B: two elements per thread ----
+#pragma unroll 1
+  for (int j = 0; j < 2; j++) {
+    const ushort4 ln = j ? ln1 : ln0;
+    if (ln.x == 0xffffu) continue;   // padding of the last patch
+    const f64* n0 = sn + (size_t)ln.x * FP_SN;
+    const f64* n1 = sn + (size_t)ln.y * FP_SN;
+    const f64* n2 = sn + (size_t)ln.z * FP_SN;
+    const f64* n3 = sn + (size_t)ln.w * FP_SN;
+    f64 x[4][3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) { x[0][d] = n0[d]; x[1][d] = n1[d]; x[2][d] = n2[d]; x[3][d] = n3[d]; }
+    Geom g;
+    geometry(x, g);
+    residual_rec(g, n0, n1, n2, n3, se + (size_t)(j * 128 + threadIdx.x) * FP_SE);
+  }
+  __syncthreads();
+  // ---- C: one thread per patch-node, six independent sums over the node's corners in ascending (element, a) order ----
+  for (int k = threadIdx.x; k < nn; k += 128) {
+    const int b = scs[k], e = scs[k + 1];
+    f64 s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int i = b; i < e; i++) {
+      const int cr = scl[i];
+      const f64* src = se + (cr >> 2) * FP_SE + (cr & 3) * 6;
+#pragma unroll
+      for (int c = 0; c < 6; c++) s[c] += src[c];
+    }
+    f64* dst = part + (size_t)(pb + k) * 6;
+#pragma unroll
+    for (int c = 0; c < 6; c += 2) *reinterpret_cast<double2*>(dst + c) = make_double2(s[c], s[c + 1]);
+  }
+}
+
+// F[node] (+)= sum of the node's patch partials, ascending patch order
+__global__ void k_gatherF2(int N, int n_rows, const int* __restrict__ np_ptr, const int* __restrict__ np, const f64* __restrict__ part,
+                           f64* __restrict__ F, int overwrite) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  f64 s[6] = {0, 0, 0, 0, 0, 0};
+  for (int j = np_ptr[i]; j < np_ptr[i + 1]; j++) {
+    const double2* src = reinterpret_cast<const double2*>(part + (size_t)np[j] * 6);
+    const double2 a = src[0], b = src[1], c = src[2];
+    s[0] += a.x; s[1] += a.y; s[2] += b.x; s[3] += b.y; s[4] += c.x; s[5] += c.y;
+  }
+  f64* fu = F + (size_t)i * 3;
+  if (overwrite) {
+    fu[0] = s[0]; fu[1] = s[1]; fu[2] = s[2];
+    F[(size_t)3 * N + i] = s[3]; F[(size_t)4 * N + i] = s[4]; F[(size_t)5 * N + i] = s[5];
+  } else {
+    fu[0] += s[0]; fu[1] += s[1]; fu[2] += s[2];
+    F[(size_t)3 * N + i] += s[3]; F[(size_t)4 * N + i] += s[4]; F[(size_t)5 * N + i] += s[5];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // J: per-corner work shared by all variants
 // ------------------------------------------------------------------------------------------------------------
 struct CornerCtx {
@@ -820,7 +943,32 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
   const int N = P->N, E = P->E;
   const u32* slot32 = reinterpret_cast<const u32*>(P->slot);
   if (d_F) {
-    if (mode == DFB_MODE_GATHER) {
+    bool patch_done = false;
+    if (mode == DFB_MODE_GATHER && options().f_variant == 1) {
+      DFB_CHECK(build_fpatch(P, d_xg, st));
+      if (P->fp_state == 1) {
+        const int mn = (P->fp_max_nodes + 1) & ~1;   // even: keeps the 16-byte alignment of what follows the node records
+        const size_t smem = sizeof(f64) * ((size_t)mn * FP_SN + (size_t)FP_PE * FP_SE) + sizeof(unsigned short) * ((size_t)4 * FP_PE + mn + 8);
+        static size_t smem_set = 0;   // (monotone high-water mark of an attribute that only ever needs to grow)
+        if (smem > smem_set) {
+          DFB_CUDA(cudaFuncSetAttribute(k_patchF<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          DFB_CUDA(cudaFuncSetAttribute(k_patchF<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          smem_set = smem;
+        }
+        if (options().f_patch_ctas == 2)
+          k_patchF<2><<<P->fp_n_patch, 128, smem, st>>>(N, P->fp_hdr, P->fp_nodes, P->fp_lnode, P->fp_corner, P->fp_cstart, d_xg, d_wg,
+                                                        d_dwg, P->fp_part, mn);
+        else
+          k_patchF<3><<<P->fp_n_patch, 128, smem, st>>>(N, P->fp_hdr, P->fp_nodes, P->fp_lnode, P->fp_corner, P->fp_cstart, d_xg, d_wg,
+                                                        d_dwg, P->fp_part, mn);
+        DFB_LAUNCH_CHECK();
+        k_gatherF2<<<ceil_div(P->n_rows, 128), 128, 0, st>>>(N, P->n_rows, P->fp_np_ptr, P->fp_np, P->fp_part, d_F, overwrite);
+        DFB_LAUNCH_CHECK();
+        patch_done = true;
+      }
+    }
+    if (patch_done) {
+    } else if (mode == DFB_MODE_GATHER) {
       if (!P->elemF) {
         P->elemF_bytes = sizeof(f64) * 24 * (size_t)E + sizeof(int) * 4 * (size_t)E;
         DFB_CUDA(cudaMalloc(&P->elemF, sizeof(f64) * 24 * (size_t)E));
@@ -849,19 +997,10 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
       const int grid = ceil_div(P->n_rows, 4);
       // variants of the atomic-free assembly: node pairs (default), pull (DFB_J_VARIANT=pull) and the fused row gather
       // (DFB_J_VARIANT=fused); see DESIGN.md section 3
-      const int variant = [] {   // read per call: tests switch variants inside one process
-        const char* e = getenv("DFB_J_VARIANT");
-        if (e && !strcmp(e, "fused")) return 1;
-        if (e && !strcmp(e, "pull")) return 0;
-        return 2;   // pairs
-      }();
+      const int variant = options().j_variant;   // 0 pull, 1 fused, 2 pairs (dfb_set_option / DFB_J_VARIANT)
       bool done = false;
       if (variant == 2) {
-        const int pair_rows = [] {   // only read when the plan's pair lists are first built
-          const char* e = getenv("DFB_J_PAIR_ROWS");
-          const int r = e ? atoi(e) : 8;
-          return (r >= 8 && r <= 16 && (r & 7) == 0) ? r : 8;
-        }();
+        const int pair_rows = options().j_pair_rows;   // only looked at when the plan's pair lists are first built
         DFB_CHECK(build_pairs(P, pair_rows, d_xg, st));
         if (P->pr_state == 1) {
           const size_t smem = (size_t)std::max(1, P->pr_max_elems) * PAIR_SREC * sizeof(double2);
@@ -910,8 +1049,7 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
         }
         k_jprep2<<<ceil_div(E, 128), 128, sizeof(f64) * 128 * PREC_S, st>>>(E, P->ien, d_xg, d_wg, P->prec);
         DFB_LAUNCH_CHECK();
-        static const bool plain_pull = getenv("DFB_J_PULL_PLAIN") != nullptr;   // the unstaged kernel, kept for measurement
-        if (plain_pull) {
+        if (options().j_pull_plain) {   // the unstaged kernel, kept for measurement
           const int ni = P->items_active;
           if (overwrite)
             k_pullJ<1><<<ceil_div(ni, 128), 128, 0, st>>>(ni, P->item_meta, P->item_ptr, P->contrib, P->prec, P->row_ptr, d_A00, d_A01, d_A10, d_A11);

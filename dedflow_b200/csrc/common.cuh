@@ -71,6 +71,28 @@ inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
 // number of SMs of the current device (B200: 148); cached
 int num_sms();
 
+// Variant switches of the library.  Read ONCE from the environment (first use) and afterwards only changed through
+// dfb_set_option(): no entry point calls getenv on its launch path, and tests / A-B scripts switch variants inside one process
+// without touching the environment.  Keys are the environment names (DFB_J_VARIANT=pairs|pull|fused, DFB_J_PAIR_ROWS=8|16,
+// DFB_J_PAIR_ORDER=morton|natural, DFB_J_PULL_PLAIN=0|1, DFB_F_VARIANT=patch|scratch, DFB_F_PATCH_CTAS=2|3, DFB_SPMV_G=4|8|16|32, DFB_SPMV_TMA=0|1,
+// DFB_KRYLOV_TMA=0|1, DFB_GRAPH=0|1, DFB_PROFILE=0|1|2, DFB_ASSEMBLE_MODE=gather|atomic|colored, DFB_VERBOSE=0|1).
+struct Options {
+  int j_variant = 2;        // 0 pull, 1 fused, 2 pairs
+  int j_pair_rows = 8;
+  int j_pair_natural = 0;
+  int j_pull_plain = 0;
+  int f_variant = 1;        // 0 scratch (k_elemF + k_gatherF), 1 patch (k_patchF)
+  int f_patch_ctas = 2;     // register budget of k_patchF: resident CTAs per SM (2: 232 registers, measured faster; 3: 168 + spills)
+  int spmv_g = 8;
+  int spmv_tma = 1;
+  int krylov_tma = 1;
+  int graph = 1;
+  int profile = 0;
+  int assemble_mode = DFB_MODE_GATHER;
+  int verbose = 0;
+};
+Options& options();
+
 // physics / time-integration constants: reference src/assemble.cu:23-40, src/main.c:23-27
 constexpr f64 kRHOC = 0.5;
 constexpr f64 kDT = 5e-2;
@@ -177,19 +199,6 @@ __device__ __forceinline__ f64 ll_load(const P2PView* pv, const unsigned long lo
   }
   return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
 }
-// Programmatic dependent launch -- EXPERIMENT, compiled only with -DDFB_ENABLE_PDL (the default build is unchanged: the
-// prologue below is empty) and switched on at run time with DFB_PDL=1.  The Krylov kernels call the prologue first: it lets
-// the NEXT kernel's blocks be scheduled as soon as every block of this grid has started, and then waits until the PREVIOUS
-// grid has completed and its writes are visible -- stream-order semantics, minus the launch latency and block-scheduling
-// ramp at each of the four kernel boundaries of a GMRES iteration.  Not measured yet.
-#ifdef DFB_ENABLE_PDL
-__device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.launch_dependents;");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-#else
-__device__ __forceinline__ void pdl_prologue() {}
-#endif
 __device__ __forceinline__ void p2p_wait(const P2PView* pv, const unsigned long long* flag, unsigned long long seq) {
   unsigned long long v;
   unsigned long long t0 = 0;

@@ -254,16 +254,7 @@ struct MeshPlan {
 static std::mutex g_mu;
 static std::unordered_map<const void*, MeshPlan> g_plans;
 
-static int assemble_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("DFB_ASSEMBLE_MODE");
-    mode = DFB_MODE_GATHER;
-    if (e && !strcmp(e, "atomic")) mode = DFB_MODE_ATOMIC;
-    if (e && !strcmp(e, "colored")) mode = DFB_MODE_COLORED;
-  }
-  return mode;
-}
+static int assemble_mode() { return options().assemble_mode; }
 
 static dfb_plan* plan_for(const Mesh3D* mesh, const CSRAttr* spy) {
   std::lock_guard<std::mutex> lk(g_mu);

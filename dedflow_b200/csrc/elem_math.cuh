@@ -200,6 +200,107 @@ DFB_HD void residual(const Geom& g, const f64 val[6][4], const f64 dval[6][4], f
   }
 }
 
+// The same residual with the nodal data read from four NODE RECORDS (shared memory in k_patchF) where it is used, instead of
+// 48 values held in registers from the start.  Record layout (NREC doubles):
+//   [0..2] x   [3..5] u (wgalpha)   [6..8] du (dwgalpha)   [9] p (dwgalpha slot 3, D6)   [10] phi  [11] dphi  [12] T  [13] dT
+// Identical arithmetic, identical order of operations: bit-identical to residual().  The 24 results are written to eF as
+// they are produced (the SD * X_q terms inside the quadrature loop, completed at the end), so they never occupy registers.
+constexpr int NREC = 14;
+DFB_HD void residual_rec(const Geom& g, const f64* n0, const f64* n1, const f64* n2, const f64* n3, f64* eF /* [4*6], may be shared memory */) {
+  const f64* nr[4] = {n0, n1, n2, n3};
+  // val[c][a]: c = 0..2 -> rec[3+c], 3 -> rec[9], 4 -> rec[10], 5 -> rec[12];  dval[c][a]: c = 0..2 -> rec[6+c], 4 -> rec[11], 5 -> rec[13]
+  const int vo[6] = {3, 4, 5, 9, 10, 12};
+  const int dvo[6] = {6, 7, 8, 9, 11, 13};
+  f64 G[3][3];
+  metric(g, G);
+  f64 grad[6][3];
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    const f64 v0 = nr[0][vo[c]], v1 = nr[1][vo[c]], v2 = nr[2][vo[c]], v3 = nr[3][vo[c]];
+#pragma unroll
+    for (int d = 0; d < 3; d++) grad[c][d] = g.sh[0][d] * v0 + g.sh[1][d] * v1 + g.sh[2][d] * v2 + g.sh[3][d] * v3;
+  }
+  f64 gg = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) gg += G[i][j] * G[i][j];
+  const f64 itr = 1.0 / (G[0][0] + G[1][1] + G[2][2]);
+  const f64 nu = MU / RHO, al = KAPPA / (RHO * CP);
+  const f64 divu = grad[0][0] + grad[1][1] + grad[2][2];
+  const f64 t0 = 4.0 / (DT * DT);
+  const f64 fb[3] = {FB0, FB1, FB2};
+  f64 sv[4], sd[6];
+#pragma unroll
+  for (int c = 0; c < 4; c++) sv[c] = SB * (nr[0][vo[c]] + nr[1][vo[c]] + nr[2][vo[c]] + nr[3][vo[c]]);
+#pragma unroll
+  for (int c = 0; c < 6; c++) sd[c] = SB * (nr[0][dvo[c]] + nr[1][dvo[c]] + nr[2][dvo[c]] + nr[3][dvo[c]]);
+  f64 T0[3] = {0.0, 0.0, 0.0}, T1[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+  f64 V[3] = {0.0, 0.0, 0.0}, B4[3] = {0.0, 0.0, 0.0}, B5[3] = {0.0, 0.0, 0.0};
+  f64 sbp = 0.0, sbtc = 0.0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const f64* rq = nr[q];
+    const f64 u0 = sv[0] + SD * rq[3], u1 = sv[1] + SD * rq[4], u2 = sv[2] + SD * rq[5], pq = sv[3] + SD * rq[9];
+    const f64 dq0 = sd[0] + SD * rq[6], dq1 = sd[1] + SD * rq[7], dq2 = sd[2] + SD * rq[8];
+    const f64 dq4 = sd[4] + SD * rq[11], dq5 = sd[5] + SD * rq[13];
+    const f64 uadv[3] = {u0, u1, u2};
+    const f64 dqv[3] = {dq0, dq1, dq2};
+    f64 rLi[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      rLi[i] = RHO * (dqv[i] - fb[i]) + RHO * u0 * grad[i][0] + RHO * u1 * grad[i][1] + RHO * u2 * grad[i][2] + grad[3][i];
+    f64 t1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) t1 += G[i][j] * uadv[i] * uadv[j];
+    const f64 sC = t1 + 3.0 * nu * nu * gg;
+    const f64 tauM = rsqrt_(t0 + sC) * (1.0 / RHO);
+    const f64 tauC = sC * rsqrt_(sC) * itr;
+    const f64 tauP = rsqrt_(t0 + t1);
+    const f64 tauT = rsqrt_(t0 + t1 + 3.0 * al * al * gg) * (1.0 / (RHO * CP));
+    const f64 pd = -pq + RHO * tauC * divu;
+    const f64 bp = dq4 + u0 * grad[4][0] + u1 * grad[4][1] + u2 * grad[4][2];
+    const f64 btc = RHO * CP * (dq5 + u0 * grad[5][0] + u1 * grad[5][1] + u2 * grad[5][2]);
+    f64 tr_[3], ub[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { tr_[i] = tauM * rLi[i]; ub[i] = uadv[i] - tr_[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const f64 tmp0 = RHO * (dqv[i] - fb[i]) + RHO * ub[0] * grad[i][0] + RHO * ub[1] * grad[i][1] + RHO * ub[2] * grad[i][2];
+      T0[i] += tmp0;
+      eF[q * 6 + i] = SD * tmp0;
+      const f64 ai = RHO * tr_[i];
+#pragma unroll
+      for (int j = 0; j < 3; j++) T1[i][j] += ai * ub[j] + (i == j ? pd : 0.0);
+      V[i] += tr_[i];
+      B4[i] += bp * tauP * uadv[i];
+      B5[i] += btc * (RHO * CP * tauT) * uadv[i];
+    }
+    sbp += bp;
+    sbtc += btc;
+    eF[q * 6 + 4] = SD * bp;
+    eF[q * 6 + 5] = SD * btc;
+  }
+  const f64 wdet = GW * g.detJ;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) T1[i][j] += 4.0 * MU * (grad[i][j] + grad[j][i]);
+#pragma unroll
+  for (int d = 0; d < 3; d++) B5[d] += 4.0 * KAPPA * grad[5][d];
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const f64 s0 = g.sh[a][0], s1 = g.sh[a][1], s2 = g.sh[a][2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) eF[a * 6 + i] = (eF[a * 6 + i] + SB * T0[i] + s0 * T1[i][0] + s1 * T1[i][1] + s2 * T1[i][2]) * wdet;
+    eF[a * 6 + 3] = (SN * divu + s0 * V[0] + s1 * V[1] + s2 * V[2]) * wdet;
+    eF[a * 6 + 4] = (eF[a * 6 + 4] + SB * sbp + s0 * B4[0] + s1 * B4[1] + s2 * B4[2]) * wdet;
+    eF[a * 6 + 5] = (eF[a * 6 + 5] + SB * sbtc + s0 * B5[0] + s1 * B5[1] + s2 * B5[2]) * wdet;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Jacobian, hoisted form.
 // ------------------------------------------------------------------------------------------

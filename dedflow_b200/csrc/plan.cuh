@@ -57,6 +57,22 @@ struct dfb_plan {
   mutable int* pr_elem_ptr = nullptr;   // [pr_n_cta+1]                              (build time only, folded into pr_grp)
   mutable int* pr_elems = nullptr;      // ascending distinct element ids per group  (build time only, see pr_enodes)
   mutable size_t pr_bytes = 0;
+  // PATCH residual assembly (setup.cu build_fpatch, assemble.cu k_patchF; the F path of DFB_MODE_GATHER).  The elements,
+  // ordered along a Morton curve of their centroids, are cut into patches of FP_PE; one CTA per patch.  A patch knows its
+  // distinct nodes ("patch-nodes", numbered pn = fp_hdr[p].x + k), the local node indices of its elements, and its corners
+  // sorted by node; it writes ONE 48-byte partial residual per patch-node (about 2 per mesh node instead of 24 corner records),
+  // which k_gatherF2 sums per node in ascending pn order.
+  mutable int fp_state = 0;             // 0: not built, 1: usable, -1: a patch touches too many nodes (scratch variant is used)
+  mutable int fp_n_patch = 0, fp_n_pn = 0, fp_max_nodes = 0;
+  mutable int2* fp_hdr = nullptr;       // [n_patch] {first patch-node, number of nodes}
+  mutable int* fp_nodes = nullptr;      // [n_pn] global node of every patch-node (ascending inside a patch)
+  mutable ushort4* fp_lnode = nullptr;  // [n_patch * FP_PE] local node indices of every element, patch order (0xffff: padding)
+  mutable unsigned short* fp_corner = nullptr;   // [n_patch * 4 FP_PE] local corners (element * 4 + a) sorted by (node, corner)
+  mutable unsigned short* fp_cstart = nullptr;   // [n_pn + n_patch] first sorted corner of every patch-node (+ one end entry per patch)
+  mutable f64* fp_part = nullptr;       // [6 n_pn] partial residuals
+  mutable int* fp_np_ptr = nullptr;     // [N+1] patch-nodes of every mesh node ...
+  mutable int* fp_np = nullptr;         // [n_pn] ... ascending
+  mutable size_t fp_bytes = 0;
 };
 
 namespace dfb {
@@ -67,4 +83,8 @@ int build_pull(const dfb_plan* plan, cudaStream_t st);
 constexpr int PAIR_MAX_STAGED = 600; // most element records a CTA of the pair assembly stages (600 x 368 B = 216 KB)
 int build_pairs(const dfb_plan* plan, int rows_per_cta, const f64* d_xg, cudaStream_t st);
 void free_pairs(const dfb_plan* plan);
+constexpr int FP_PE = 256;          // elements per patch of the residual assembly
+constexpr int FP_MAX_NODES = 448;   // most distinct nodes a patch may touch (448 x 15 doubles + 256 x 25 doubles of staging = 105 KB)
+int build_fpatch(const dfb_plan* plan, const f64* d_xg, cudaStream_t st);
+void free_fpatch(const dfb_plan* plan);
 }

@@ -29,6 +29,42 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static bool apply_option(Options& o, const char* key, const char* v) {
+  if (!key || !v) return false;
+  auto is = [&](const char* k) { return !strcmp(key, k); };
+  if (is("DFB_J_VARIANT")) { o.j_variant = !strcmp(v, "pull") ? 0 : (!strcmp(v, "fused") ? 1 : 2); return true; }
+  if (is("DFB_J_PAIR_ROWS")) { const int r = atoi(v); o.j_pair_rows = (r >= 8 && r <= 16 && (r & 7) == 0) ? r : 8; return true; }
+  if (is("DFB_J_PAIR_ORDER")) { o.j_pair_natural = !strcmp(v, "natural"); return true; }
+  if (is("DFB_J_PULL_PLAIN")) { o.j_pull_plain = atoi(v) != 0; return true; }
+  if (is("DFB_F_VARIANT")) { o.f_variant = !strcmp(v, "scratch") ? 0 : 1; return true; }
+  if (is("DFB_F_PATCH_CTAS")) { o.f_patch_ctas = atoi(v) == 3 ? 3 : 2; return true; }
+  if (is("DFB_SPMV_G")) { const int g = atoi(v); o.spmv_g = (g == 4 || g == 8 || g == 16 || g == 32) ? g : 8; return true; }
+  if (is("DFB_SPMV_TMA")) { o.spmv_tma = atoi(v); return true; }
+  if (is("DFB_KRYLOV_TMA")) { o.krylov_tma = atoi(v) != 0; return true; }
+  if (is("DFB_GRAPH")) { o.graph = atoi(v) != 0; return true; }
+  if (is("DFB_PROFILE")) { o.profile = atoi(v); return true; }
+  if (is("DFB_VERBOSE")) { o.verbose = atoi(v) != 0; return true; }
+  if (is("DFB_ASSEMBLE_MODE")) {
+    o.assemble_mode = !strcmp(v, "atomic") ? DFB_MODE_ATOMIC : (!strcmp(v, "colored") ? DFB_MODE_COLORED : DFB_MODE_GATHER);
+    return true;
+  }
+  return false;
+}
+
+Options& options() {
+  static Options o = [] {
+    Options t;
+    static const char* keys[] = {"DFB_J_VARIANT", "DFB_J_PAIR_ROWS", "DFB_J_PAIR_ORDER", "DFB_J_PULL_PLAIN", "DFB_F_VARIANT", "DFB_F_PATCH_CTAS", "DFB_SPMV_G",
+                                 "DFB_SPMV_TMA", "DFB_KRYLOV_TMA", "DFB_GRAPH", "DFB_PROFILE", "DFB_VERBOSE", "DFB_ASSEMBLE_MODE"};
+    for (const char* k : keys) {
+      const char* v = getenv(k);
+      if (v && *v) apply_option(t, k, v);
+    }
+    return t;
+  }();
+  return o;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -466,8 +502,10 @@ __device__ __forceinline__ unsigned long long spread21(unsigned long long v) {  
   return v;
 }
 
+// ien == nullptr: key of node i (n nodes); else key of the centroid of element i (n elements, cell size from n_cells_ref nodes)
 __global__ void k_morton_keys(int n, int nblk, const f64* __restrict__ xg, const f64* __restrict__ part,
-                              unsigned long long* __restrict__ keys, int* __restrict__ ids) {
+                              unsigned long long* __restrict__ keys, int* __restrict__ ids, const int* __restrict__ ien = nullptr,
+                              int n_cells_ref = 0) {
   __shared__ f64 bb[6];
   if (threadIdx.x < 6) {
     f64 r = part[threadIdx.x];
@@ -484,13 +522,20 @@ __global__ void k_morton_keys(int n, int nblk, const f64* __restrict__ xg, const
     ext[d] = bb[3 + d] - bb[d];
     if (ext[d] > 0.0) { vol *= ext[d]; nd++; }
   }
-  const f64 h = nd ? pow(vol / (f64)n, 1.0 / nd) : 1.0;
+  const f64 h = nd ? pow(vol / (f64)(ien ? n_cells_ref : n), 1.0 / nd) : 1.0;
   unsigned long long key = 0;
   for (int d = 0; d < 3; d++) {
     unsigned long long c = 0;
     if (ext[d] > 0.0) {
       const f64 nb = fmin(2097151.0, fmax(1.0, ceil(ext[d] / h)));
-      c = (unsigned long long)fmin(nb - 1.0, floor((xg[(size_t)i * 3 + d] - bb[d]) / ext[d] * nb));
+      f64 xv;
+      if (ien) {
+        const int4 nd4 = *reinterpret_cast<const int4*>(ien + (size_t)i * 4);
+        xv = 0.25 * (xg[(size_t)nd4.x * 3 + d] + xg[(size_t)nd4.y * 3 + d] + xg[(size_t)nd4.z * 3 + d] + xg[(size_t)nd4.w * 3 + d]);
+      } else {
+        xv = xg[(size_t)i * 3 + d];
+      }
+      c = (unsigned long long)fmin(nb - 1.0, floor((xv - bb[d]) / ext[d] * nb));
     }
     key |= spread21(c) << d;
   }
@@ -646,6 +691,188 @@ __global__ void k_pair_finalize(int n_cta, int total_ge, const int* __restrict__
   if (i < total_ge) enodes[i] = *reinterpret_cast<const int4*>(ien + (size_t)elems[i] * 4);
 }
 
+// ------------------------------------------------------------------------------------------
+// PATCH residual assembly lists (plan.cuh fp_*).  One CTA per patch sorts the patch's (node, corner) pairs once
+// (cub::BlockRadixSort over composite 64-bit keys: the order is fixed by the keys alone), numbers the distinct nodes and writes
+// the local connectivity; pass 0 only counts the nodes (their exclusive scan numbers the patch-nodes).
+// ------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(FP_PE) k_fpatch_build(int E, const int* __restrict__ order, const int* __restrict__ ien,
+                                                        int* __restrict__ nn_out, const int* __restrict__ pn_base,
+                                                        int2* __restrict__ hdr, int* __restrict__ nodes, ushort4* __restrict__ lnode,
+                                                        unsigned short* __restrict__ corner, unsigned short* __restrict__ cstart) {
+  typedef cub::BlockRadixSort<unsigned long long, FP_PE, 4> Sort;
+  typedef cub::BlockScan<int, FP_PE> Scan;
+  __shared__ union { typename Sort::TempStorage sort; typename Scan::TempStorage scan; } tmp;
+  __shared__ unsigned long long skey[4 * FP_PE + 1];
+  __shared__ unsigned short srank[4 * FP_PE];
+  const int p = blockIdx.x, t = threadIdx.x;
+  const int el = p * FP_PE + t;
+  unsigned long long key[4];
+  if (el < E) {
+    const int4 nd = *reinterpret_cast<const int4*>(ien + (size_t)order[el] * 4);
+    key[0] = ((unsigned long long)(unsigned)nd.x << 10) | (unsigned)(4 * t + 0);
+    key[1] = ((unsigned long long)(unsigned)nd.y << 10) | (unsigned)(4 * t + 1);
+    key[2] = ((unsigned long long)(unsigned)nd.z << 10) | (unsigned)(4 * t + 2);
+    key[3] = ((unsigned long long)(unsigned)nd.w << 10) | (unsigned)(4 * t + 3);
+  } else {
+    key[0] = key[1] = key[2] = key[3] = ~0ull;   // padding of the last patch: sorts behind every real corner
+  }
+  Sort(tmp.sort).Sort(key, 0, 42);
+  __syncthreads();
+  if (t == 0) skey[0] = ~0ull - 1ull;   // sentinel in front: its node differs from every real node and from the padding
+#pragma unroll
+  for (int k = 0; k < 4; k++) skey[1 + 4 * t + k] = key[k];
+  __syncthreads();
+  int head[4], rank[4], nhead = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const bool valid = key[k] != ~0ull;
+    head[k] = (valid && (key[k] >> 10) != (skey[4 * t + k] >> 10)) ? 1 : 0;
+    nhead += head[k];
+  }
+  int base, total;
+  Scan(tmp.scan).ExclusiveSum(nhead, base, total);
+  if (!FILL) {
+    if (t == 0) nn_out[p] = total;
+    return;
+  }
+  const int pb = pn_base[p];
+  if (t == 0) hdr[p] = make_int2(pb, total);
+  int run = base;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const bool valid = key[k] != ~0ull;
+    run += head[k];
+    rank[k] = run - 1;                      // local index of this corner's node
+    const int i = 4 * t + k;                // position in the sorted corner list
+    if (valid) {
+      const int cl = (int)(key[k] & 1023u);
+      srank[cl] = (unsigned short)rank[k];
+      corner[(size_t)p * 4 * FP_PE + i] = (unsigned short)cl;
+      if (head[k]) {
+        nodes[pb + rank[k]] = (int)(key[k] >> 10);
+        cstart[(size_t)pb + p + rank[k]] = (unsigned short)i;
+      }
+    } else {
+      corner[(size_t)p * 4 * FP_PE + i] = 0xffffu;
+      // the first padding item (or the end of the list) closes the last node's corner range
+      if (skey[i] != ~0ull) cstart[(size_t)pb + p + total] = (unsigned short)i;
+    }
+  }
+  if (t == FP_PE - 1 && key[3] != ~0ull) cstart[(size_t)pb + p + total] = (unsigned short)(4 * FP_PE);
+  __syncthreads();
+  lnode[(size_t)p * FP_PE + t] = el < E ? make_ushort4(srank[4 * t], srank[4 * t + 1], srank[4 * t + 2], srank[4 * t + 3])
+                                         : make_ushort4(0xffffu, 0xffffu, 0xffffu, 0xffffu);
+}
+
+__global__ void k_count_nodes(int n, const int* __restrict__ nodes, int* __restrict__ cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(cnt + nodes[i], 1);
+}
+static __global__ void k_iota_seq(int n, int* __restrict__ v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
+}
+
+void free_fpatch(const dfb_plan* p) {
+  cudaFree(p->fp_hdr); cudaFree(p->fp_nodes); cudaFree(p->fp_lnode); cudaFree(p->fp_corner); cudaFree(p->fp_cstart);
+  cudaFree(p->fp_part); cudaFree(p->fp_np_ptr); cudaFree(p->fp_np);
+  p->fp_hdr = nullptr; p->fp_nodes = nullptr; p->fp_lnode = nullptr; p->fp_corner = nullptr; p->fp_cstart = nullptr;
+  p->fp_part = nullptr; p->fp_np_ptr = nullptr; p->fp_np = nullptr;
+  p->fp_state = 0; p->fp_bytes = 0;
+}
+
+int build_fpatch(const dfb_plan* p, const f64* d_xg, cudaStream_t st) {
+  if (p->fp_state != 0) return DFB_OK;
+  const int N = p->N, E = p->E;
+  const int n_patch = ceil_div(E, FP_PE);
+  DevBuf<int> order, nn, base, ids, pn_iota, nodes_sorted, cnt;
+  DevBuf<char> tmp;
+  size_t tmp_bytes = 0;
+  DFB_CHECK(order.alloc((size_t)E));
+  {   // elements along a Morton curve of their centroids
+    DevBuf<f64> part;
+    DevBuf<unsigned long long> keys, keys_out;
+    const int nblk = std::min(1024, ceil_div(N, 256));
+    DFB_CHECK(part.alloc((size_t)nblk * 6));
+    DFB_CHECK(keys.alloc((size_t)E));
+    DFB_CHECK(keys_out.alloc((size_t)E));
+    DFB_CHECK(ids.alloc((size_t)E));
+    k_bbox_part<<<nblk, 256, 0, st>>>(N, d_xg, part);
+    DFB_LAUNCH_CHECK();
+    k_morton_keys<<<ceil_div(E, 256), 256, 0, st>>>(E, nblk, d_xg, part, keys, ids, p->ien, N);
+    DFB_LAUNCH_CHECK();
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_out.p, ids.p, order.p, E, 0, 63, st);
+    DFB_CHECK(tmp.alloc(tmp_bytes));
+    cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_out.p, ids.p, order.p, E, 0, 63, st);
+    DFB_LAUNCH_CHECK();
+    DFB_CUDA(cudaStreamSynchronize(st));
+  }
+  DFB_CHECK(nn.alloc((size_t)n_patch + 1));
+  DFB_CHECK(base.alloc((size_t)n_patch + 1));
+  DFB_CUDA(cudaMemsetAsync(nn, 0, sizeof(int) * ((size_t)n_patch + 1), st));
+  k_fpatch_build<false><<<n_patch, FP_PE, 0, st>>>(E, order, p->ien, nn, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  DFB_LAUNCH_CHECK();
+  tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, nn.p, base.p, n_patch + 1, st);
+  DFB_CHECK(tmp.alloc(tmp_bytes));
+  cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, nn.p, base.p, n_patch + 1, st);
+  DFB_LAUNCH_CHECK();
+  DevBuf<int> d_max;
+  DFB_CHECK(d_max.alloc(1));
+  DFB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
+  k_max_int<<<ceil_div(n_patch, 256), 256, 0, st>>>(n_patch, base, d_max);   // base[i+1] - base[i] = nodes of patch i
+  DFB_LAUNCH_CHECK();
+  int n_pn = 0, max_nodes = 0;
+  DFB_CUDA(cudaMemcpyAsync(&n_pn, base.p + n_patch, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DFB_CUDA(cudaMemcpyAsync(&max_nodes, d_max.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DFB_CUDA(cudaStreamSynchronize(st));
+  if (max_nodes > FP_MAX_NODES) { p->fp_state = -1; return DFB_OK; }
+  p->fp_n_patch = n_patch; p->fp_n_pn = n_pn; p->fp_max_nodes = max_nodes;
+  DFB_CUDA(cudaMalloc(&p->fp_hdr, sizeof(int2) * (size_t)n_patch));
+  DFB_CUDA(cudaMalloc(&p->fp_nodes, sizeof(int) * (size_t)n_pn));
+  DFB_CUDA(cudaMalloc(&p->fp_lnode, sizeof(ushort4) * (size_t)n_patch * FP_PE));
+  DFB_CUDA(cudaMalloc(&p->fp_corner, sizeof(unsigned short) * (size_t)n_patch * 4 * FP_PE));
+  DFB_CUDA(cudaMalloc(&p->fp_cstart, sizeof(unsigned short) * ((size_t)n_pn + n_patch)));
+  DFB_CUDA(cudaMalloc(&p->fp_part, sizeof(f64) * 6 * (size_t)n_pn));
+  DFB_CUDA(cudaMalloc(&p->fp_np_ptr, sizeof(int) * ((size_t)N + 1)));
+  DFB_CUDA(cudaMalloc(&p->fp_np, sizeof(int) * (size_t)n_pn));
+  p->fp_bytes = sizeof(int2) * (size_t)n_patch + sizeof(int) * 2 * (size_t)n_pn + sizeof(ushort4) * (size_t)n_patch * FP_PE +
+                sizeof(unsigned short) * ((size_t)n_patch * 4 * FP_PE + n_pn + n_patch) + sizeof(f64) * 6 * (size_t)n_pn +
+                sizeof(int) * ((size_t)N + 1);
+  k_fpatch_build<true><<<n_patch, FP_PE, 0, st>>>(E, order, p->ien, nullptr, base, p->fp_hdr, p->fp_nodes, p->fp_lnode, p->fp_corner,
+                                                 p->fp_cstart);
+  DFB_LAUNCH_CHECK();
+  // node -> its patch-nodes, ascending: stable sort of (node, pn)
+  DFB_CHECK(pn_iota.alloc((size_t)n_pn));
+  DFB_CHECK(nodes_sorted.alloc((size_t)n_pn));
+  DFB_CHECK(cnt.alloc((size_t)N + 1));
+  k_iota_seq<<<ceil_div(n_pn, 256), 256, 0, st>>>(n_pn, pn_iota);
+  DFB_LAUNCH_CHECK();
+  int bits = 1;
+  while ((1ll << bits) < (long long)N) bits++;
+  tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, p->fp_nodes, nodes_sorted.p, pn_iota.p, p->fp_np, n_pn, 0, bits, st);
+  DFB_CHECK(tmp.alloc(tmp_bytes));
+  cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, p->fp_nodes, nodes_sorted.p, pn_iota.p, p->fp_np, n_pn, 0, bits, st);
+  DFB_LAUNCH_CHECK();
+  DFB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)N + 1), st));
+  k_count_nodes<<<ceil_div(n_pn, 256), 256, 0, st>>>(n_pn, p->fp_nodes, cnt);
+  DFB_LAUNCH_CHECK();
+  tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt.p, p->fp_np_ptr, N + 1, st);
+  DFB_CHECK(tmp.alloc(tmp_bytes));
+  cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cnt.p, p->fp_np_ptr, N + 1, st);
+  DFB_LAUNCH_CHECK();
+  DFB_CUDA(cudaStreamSynchronize(st));
+  p->fp_state = 1;
+  if (options().verbose)
+    fprintf(stderr, "[dfb] residual patches: %d patches of %d elements, %d patch-nodes (%.2f per node), at most %d nodes per patch, %.1f MB\n",
+            n_patch, FP_PE, n_pn, (double)n_pn / N, max_nodes, p->fp_bytes / 1e6);
+  return DFB_OK;
+}
+
 void free_pairs(const dfb_plan* p) {
   cudaFree(p->pr_grp_item); cudaFree(p->pr_meta); cudaFree(p->pr_item_ptr); cudaFree(p->pr_contrib); cudaFree(p->pr_elem_ptr);
   cudaFree(p->pr_elems); cudaFree(p->pr_grp); cudaFree(p->pr_enodes);
@@ -672,8 +899,7 @@ int build_pairs(const dfb_plan* p, int R, const f64* d_xg, cudaStream_t st) {
   // ---- row order ----
   DFB_CHECK(order.alloc((size_t)n_act));
   DFB_CHECK(rpos.alloc((size_t)N));
-  const char* oe = getenv("DFB_J_PAIR_ORDER");
-  if (d_xg && !(oe && !strcmp(oe, "natural"))) {
+  if (d_xg && !options().j_pair_natural) {
     DevBuf<f64> part;
     DevBuf<unsigned long long> keys, keys_out;
     DevBuf<int> ids;
@@ -783,7 +1009,7 @@ int build_pairs(const dfb_plan* p, int R, const f64* d_xg, cudaStream_t st) {
   p->pr_bytes = sizeof(int4) * ((size_t)n_cta + (size_t)total_ge) + sizeof(uint2) * (size_t)n_items +
                 sizeof(int) * ((size_t)n_items + 1) + sizeof(unsigned short) * (size_t)n_contrib;
   p->pr_state = 1;
-  if (getenv("DFB_VERBOSE"))
+  if (options().verbose)
     fprintf(stderr, "[dfb] pair plan: %d groups of %d rows, %.1f staged elements per group (max %d), %d items, %d contributions, %.1f MB\n",
             n_cta, R, (double)total_ge / n_cta, h_flags[2], n_items, n_contrib, p->pr_bytes / 1e6);
   return DFB_OK;
@@ -806,6 +1032,11 @@ extern "C" {
 const char* dfb_last_error(void) { return g_err; }
 int dfb_version(void) { return 100; }
 long long dfb_launch_count(void) { return g_launches.load(); }
+
+int dfb_set_option(const char* key, const char* value) {
+  if (!apply_option(options(), key, value)) { set_error("dfb_set_option: unknown option %s", key ? key : "(null)"); return DFB_ERR_ARG; }
+  return DFB_OK;
+}
 
 int dfb_pattern_rows(int N, int E, const int* d_ien, int* d_row_ptr, int* nnz, void* stream) {
   cudaStream_t st = as_stream(stream);
@@ -906,12 +1137,13 @@ void dfb_plan_destroy(dfb_plan* p) {
   cudaFree(p->row_item); cudaFree(p->item_meta); cudaFree(p->item_ptr); cudaFree(p->contrib); cudaFree(p->prec);
   cudaFree(p->cta_elem_ptr); cudaFree(p->cta_elems); cudaFree(p->contrib16);
   free_pairs(p);
+  free_fpatch(p);
   delete p;
 }
 
 size_t dfb_plan_bytes(const dfb_plan* p) {
   if (!p) return 0;
-  return sizeof(int) * ((size_t)p->N + 1) + sizeof(int) * (size_t)p->E * 4 + (size_t)p->E * 16 + p->elemF_bytes + p->pull_bytes + p->pr_bytes;
+  return sizeof(int) * ((size_t)p->N + 1) + sizeof(int) * (size_t)p->E * 4 + (size_t)p->E * 16 + p->elemF_bytes + p->pull_bytes + p->pr_bytes + p->fp_bytes;
 }
 
 }  // extern "C"

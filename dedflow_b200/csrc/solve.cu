@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace dfb {
 
@@ -39,7 +40,8 @@ struct SolveProfiler {
   struct Rec { const char* name; cudaEvent_t a, b; };
   std::vector<Rec> recs;
   bool on;
-  SolveProfiler() { const char* e = getenv("DFB_PROFILE"); on = e && *e && *e != '0'; }
+  int level;
+  SolveProfiler() { level = options().profile; on = level > 0; }
   void begin(const char* name, cudaStream_t st) {
     if (!on) return;
     Rec r; r.name = name;
@@ -59,6 +61,7 @@ struct SolveProfiler {
       cudaEventElapsedTime(&ms, r.a, r.b);
       cudaEventDestroy(r.a); cudaEventDestroy(r.b);
       total += ms;
+      if (level >= 2) fprintf(stderr, "[dfb profile] launch %-18s %8.2f us\n", r.name, 1e3 * ms);
       bool found = false;
       for (auto& g : agg) if (!strcmp(g.name, r.name)) { g.n++; g.ms += ms; found = true; break; }
       if (!found) agg.push_back({r.name, 1, (double)ms});
@@ -93,35 +96,15 @@ __device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64*
 template <bool PEER>
 __device__ __forceinline__ f64 ld_x(const f64* p, bool ghost) { return (PEER && ghost) ? __ldcg(p) : __ldg(p); }
 
-template <int G, bool PEER>
-__global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
-                                                 const f64* __restrict__ A00, const f64* __restrict__ A01,
-                                                 const f64* __restrict__ A10, const f64* __restrict__ A11, f64 alpha,
-                                                 const f64* __restrict__ x, size_t x_poff, f64 beta, f64* __restrict__ y,
-                                                 size_t y_poff, const P2PView* __restrict__ pv, unsigned long long hseq,
-                                                 int n_interior) {
-  pdl_prologue();
-  if (PEER) {
-    const int last_row = row0 + (int)((((size_t)blockIdx.x + 1) * blockDim.x - 1) / G);
-    if (last_row >= n_interior) {   // block-uniform
-      if ((int)threadIdx.x < pv->n_nbr) p2p_wait(pv, pv->mbox_local + p2p_h_flag(pv->nranks, pv->nbr[threadIdx.x]), hseq);
-      __syncthreads();
-    }
-  }
-  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int row = row0 + (int)(gt / G);
-  const int lane = (int)(threadIdx.x & (G - 1));
-  const bool live = row < n_rows;
-  // the lanes of THIS group (the groups of a warp may run different trip counts)
-  const unsigned gmask = G == 32 ? FULLM : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
-  int start = 0, len = 0;
-  if (live) {
-    start = __ldg(row_ptr + row);
-    len = __ldg(row_ptr + row + 1) - start;
-  }
-  const size_t s9 = (size_t)start * 9, s3 = (size_t)start * 3;
+// One nodal row by the G lanes of a group.  p00/p01/p10/p11/pcol point at the row's value / column streams (global memory, or
+// a shared-memory stage filled by the TMA unit: SMEM), len = nodal nonzeros of the row.  Returns the group-reduced
+// (y0, y1, y2, yp) in every lane of the group.
+template <int G, bool PEER, bool SMEM>
+__device__ __forceinline__ void spmv_row(const f64* __restrict__ p00, const f64* __restrict__ p01, const f64* __restrict__ p10,
+                                         const f64* __restrict__ p11, const int* __restrict__ pcol, int len, int lane, unsigned gmask,
+                                         const f64* __restrict__ x, size_t x_poff, int n_rows, f64& y0, f64& y1, f64& y2, f64& yp) {
   const int len3 = 3 * len;
-  f64 y0 = 0.0, y1 = 0.0, y2 = 0.0, yp = 0.0;
+  y0 = 0.0; y1 = 0.0; y2 = 0.0; yp = 0.0;
   for (int c0 = 0; c0 < len; c0 += G) {   // group-uniform trip count (one trip for rows of up to G nonzeros)
     const int k = c0 + lane;
     const bool okk = k < len;
@@ -133,14 +116,24 @@ __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int
       const int t = 3 * c0 + u * G + lane;
       oku[u] = t < len3;
       const int tt = oku[u] ? t : 0;
-      a0[u] = __ldcs(A00 + s9 + tt);
-      a1[u] = __ldcs(A00 + s9 + len3 + tt);
-      a2[u] = __ldcs(A00 + s9 + 2 * len3 + tt);
-      ap[u] = __ldcs(A10 + s3 + tt);
+      if (SMEM) {
+        a0[u] = p00[tt]; a1[u] = p00[len3 + tt]; a2[u] = p00[2 * len3 + tt]; ap[u] = p10[tt];
+      } else {
+        a0[u] = __ldcs(p00 + tt);
+        a1[u] = __ldcs(p00 + len3 + tt);
+        a2[u] = __ldcs(p00 + 2 * len3 + tt);
+        ap[u] = __ldcs(p10 + tt);
+      }
     }
-    const f64 b0 = __ldcs(A01 + s3 + kk), b1 = __ldcs(A01 + s3 + len + kk), b2 = __ldcs(A01 + s3 + 2 * len + kk);
-    const f64 bp = __ldcs(A11 + start + kk);
-    const int col = __ldg(col_ind + start + kk);
+    f64 b0, b1, b2, bp;
+    int col;
+    if (SMEM) {
+      b0 = p01[kk]; b1 = p01[len + kk]; b2 = p01[2 * len + kk]; bp = p11[kk]; col = pcol[kk];
+    } else {
+      b0 = __ldcs(p01 + kk); b1 = __ldcs(p01 + len + kk); b2 = __ldcs(p01 + 2 * len + kk);
+      bp = __ldcs(p11 + kk);
+      col = __ldg(pcol + kk);
+    }
     const f64 xp = okk ? ld_x<PEER>(x + x_poff + col, col >= n_rows) : 0.0;
     f64 xv[3];
 #pragma unroll
@@ -164,49 +157,275 @@ __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int
   }
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) {
-    y0 += __shfl_xor_sync(FULLM, y0, o);
-    y1 += __shfl_xor_sync(FULLM, y1, o);
-    y2 += __shfl_xor_sync(FULLM, y2, o);
-    yp += __shfl_xor_sync(FULLM, yp, o);
+    y0 += __shfl_xor_sync(gmask, y0, o);
+    y1 += __shfl_xor_sync(gmask, y1, o);
+    y2 += __shfl_xor_sync(gmask, y2, o);
+    yp += __shfl_xor_sync(gmask, yp, o);
   }
-  if (live && lane == 0) {
-    f64* yu = y + (size_t)row * 3;
-    f64* ypp = y + y_poff + row;
-    if (beta == 0.0) {
-      yu[0] = alpha * y0; yu[1] = alpha * y1; yu[2] = alpha * y2; *ypp = alpha * yp;
-    } else {
-      yu[0] = beta * yu[0] + alpha * y0; yu[1] = beta * yu[1] + alpha * y1; yu[2] = beta * yu[2] + alpha * y2;
-      *ypp = beta * *ypp + alpha * yp;
+}
+
+__device__ __forceinline__ void spmv_store(f64* __restrict__ y, size_t y_poff, int row, f64 alpha, f64 beta, f64 y0, f64 y1, f64 y2,
+                                           f64 yp) {
+  f64* yu = y + (size_t)row * 3;
+  f64* ypp = y + y_poff + row;
+  if (beta == 0.0) {
+    yu[0] = alpha * y0; yu[1] = alpha * y1; yu[2] = alpha * y2; *ypp = alpha * yp;
+  } else {
+    yu[0] = beta * yu[0] + alpha * y0; yu[1] = beta * yu[1] + alpha * y1; yu[2] = beta * yu[2] + alpha * y2;
+    *ypp = beta * *ypp + alpha * yp;
+  }
+}
+
+// The same row out of a shared-memory stage, two chunks of G nonzeros per trip: the values cost nothing to fetch, the only
+// long latency left is the x gather through L2, so all 8 gathers of a lane (rows of up to 2G nonzeros: ONE trip) are issued
+// before the first FMA.  Same summation order as spmv_row (chunk by chunk), hence bit-identical results.
+template <int G, bool PEER>
+__device__ __forceinline__ void spmv_row_smem(const f64* __restrict__ p00, const f64* __restrict__ p01, const f64* __restrict__ p10,
+                                              const f64* __restrict__ p11, const int* __restrict__ pcol, int len, int lane,
+                                              unsigned gmask, const f64* __restrict__ x, size_t x_poff, int n_rows, f64& y0, f64& y1,
+                                              f64& y2, f64& yp) {
+  const int len3 = 3 * len;
+  y0 = 0.0; y1 = 0.0; y2 = 0.0; yp = 0.0;
+  for (int c0 = 0; c0 < len; c0 += 2 * G) {   // group-uniform trip count
+    f64 xp[2], xv[2][3];
+    int tt[2][3], kk[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int cb = c0 + h * G;
+      const int k = cb + lane;
+      const bool okk = k < len;
+      kk[h] = okk ? k : -1;
+      const int col = okk ? pcol[k] : 0;
+      xp[h] = okk ? ld_x<PEER>(x + x_poff + col, col >= n_rows) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        const int q = u * G + lane;
+        const int kl = q / 3, l = q - 3 * kl;
+        const int cu = __shfl_sync(gmask, col, kl, G);
+        const int t = 3 * cb + q;
+        const bool ok = t < len3;
+        tt[h][u] = ok ? t : -1;
+        xv[h][u] = ok ? ld_x<PEER>(x + (size_t)cu * 3 + l, cu >= n_rows) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        const int t = tt[h][u] < 0 ? 0 : tt[h][u];   // xv is 0 there
+        y0 = fma(p00[t], xv[h][u], y0);
+        y1 = fma(p00[len3 + t], xv[h][u], y1);
+        y2 = fma(p00[2 * len3 + t], xv[h][u], y2);
+        yp = fma(p10[t], xv[h][u], yp);
+      }
+      const int k = kk[h] < 0 ? 0 : kk[h];
+      y0 = fma(p01[k], xp[h], y0);
+      y1 = fma(p01[len + k], xp[h], y1);
+      y2 = fma(p01[2 * len + k], xp[h], y2);
+      yp = fma(p11[k], xp[h], yp);
     }
   }
-}
-
-#ifdef DFB_ENABLE_PDL
-static bool pdl_on() {
-  static const bool on = [] { const char* e = getenv("DFB_PDL"); return e && *e && *e != '0'; }();
-  return on;
-}
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-#endif
-
-static int spmv_group() {
-  static int g = 0;
-  if (g == 0) {
-    const char* e = getenv("DFB_SPMV_G");
-    g = e ? atoi(e) : 8;   // measured in-solve on B200 (1M tets): G=8 67.8 us, G=16 71.8 us, G=32 122 us per mat-vec
-    if (g != 4 && g != 8 && g != 16 && g != 32) g = 8;
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    y0 += __shfl_xor_sync(gmask, y0, o);
+    y1 += __shfl_xor_sync(gmask, y1, o);
+    y2 += __shfl_xor_sync(gmask, y2, o);
+    yp += __shfl_xor_sync(gmask, yp, o);
   }
-  return g;
 }
+
+template <int G, bool PEER>
+__global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
+                                                 const f64* __restrict__ A00, const f64* __restrict__ A01,
+                                                 const f64* __restrict__ A10, const f64* __restrict__ A11, f64 alpha,
+                                                 const f64* __restrict__ x, size_t x_poff, f64 beta, f64* __restrict__ y,
+                                                 size_t y_poff, const P2PView* __restrict__ pv, unsigned long long hseq,
+                                                 int n_interior) {
+  if (PEER) {
+    const int last_row = row0 + (int)((((size_t)blockIdx.x + 1) * blockDim.x - 1) / G);
+    if (last_row >= n_interior) {   // block-uniform
+      if ((int)threadIdx.x < pv->n_nbr) p2p_wait(pv, pv->mbox_local + p2p_h_flag(pv->nranks, pv->nbr[threadIdx.x]), hseq);
+      __syncthreads();
+    }
+  }
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = row0 + (int)(gt / G);
+  const int lane = (int)(threadIdx.x & (G - 1));
+  const bool live = row < n_rows;
+  // the lanes of THIS group (the groups of a warp may run different trip counts)
+  const unsigned gmask = G == 32 ? FULLM : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+  int start = 0, len = 0;
+  if (live) {
+    start = __ldg(row_ptr + row);
+    len = __ldg(row_ptr + row + 1) - start;
+  }
+  f64 y0, y1, y2, yp;
+  spmv_row<G, PEER, false>(A00 + (size_t)start * 9, A01 + (size_t)start * 3, A10 + (size_t)start * 3, A11 + start, col_ind + start, len,
+                           lane, gmask, x, x_poff, n_rows, y0, y1, y2, yp);
+  if (live && lane == 0) spmv_store(y, y_poff, row, alpha, beta, y0, y1, y2, yp);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// SpMV, TMA ring (default when the arrays are 16-byte aligned).  The value streams of CONSECUTIVE rows are contiguous in all
+// five arrays (A00: 9 doubles per nodal nonzero, A01/A10: 3, A11: 1, col_ind: 1 int), so a tile of TS_TR rows is five
+// contiguous byte ranges + its TS_TR + 1 row pointers: one elected producer thread hands them to the TMA unit as 1-D bulk
+// copies (cp.async.bulk -> SASS UBLKCP) into a ring of TS_STAGES shared-memory stages, each guarded by a full / empty
+// mbarrier pair; eight consumer warps run the row arithmetic out of shared memory and only gather x through L2.  The bytes
+// in flight (up to 3 x 66 KB per SM) no longer depend on the register budget -- the register-staged kernel above keeps
+// 24 warps x 17 loads per SM in flight and exposes the value-load and x-gather latencies in series.
+// Persistent: one CTA per SM walks the tiles round-robin.  Bulk copies need 16-byte aligned addresses and sizes: a range is
+// widened to the enclosing 16-byte window (its first element then sits 0..12 bytes into the stage) and never leaves the
+// array: the few bytes past the last full window of the LAST tile are copied by hand.  A tile with more nonzeros than a
+// stage holds (very long rows) is computed straight from global memory by the same row routine.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TS_TR = 32;       // rows per tile
+constexpr int TS_CAP = 512;     // nodal nonzeros a stage holds
+constexpr int TS_STAGES = 3;
+constexpr int TS_CWARPS = 8;    // consumer warps per stage (4 rows each per tile)
+// consumer groups: group g takes the tiles j = g, g + GROUPS, ... of its CTA, so GROUPS tiles are in the row arithmetic at once
+// (template parameter of the kernel: 3 -> 25 warps at 72 registers, 2 -> 17 warps at up to 96)
+struct __align__(16) SpmvStage {
+  f64 a00[9 * TS_CAP + 2];
+  f64 a01[3 * TS_CAP + 2];
+  f64 a10[3 * TS_CAP + 2];
+  f64 a11[TS_CAP + 2];
+  int col[TS_CAP + 8];
+  int rowp[TS_TR + 4];
+  int direct, pad_[3];
+};
+static_assert(sizeof(SpmvStage) % 16 == 0, "stage size");
+static_assert(TS_TR == 4 * TS_CWARPS, "eight lanes per row, four rows per consumer warp");
+
+// elements [lo_b, hi_b) (byte offsets) of a global array whose last byte is end_b - 1 -> dst, element lo at dst + (lo_b & 15).
+// Returns the bytes handed to the TMA unit (to be expected on the barrier).
+__device__ __forceinline__ unsigned stage_copy(void* dst, const void* src, size_t lo_b, size_t hi_b, size_t end_b, uint64_t* bar) {
+  const size_t b0 = lo_b & ~(size_t)15;
+  size_t b1 = (hi_b + 15) & ~(size_t)15;
+  const size_t lim = end_b & ~(size_t)15;
+  if (b1 > lim) {   // last tile of the array: the tail beyond the last full 16-byte window by hand (4-byte words)
+    for (size_t b = lim; b < hi_b; b += 4)
+      *reinterpret_cast<int*>(static_cast<char*>(dst) + (b - b0)) = *reinterpret_cast<const int*>(static_cast<const char*>(src) + b);
+    b1 = lim;
+  }
+  if (b1 <= b0) return 0u;
+  tma::bulk_g2s(dst, static_cast<const char*>(src) + b0, (unsigned)(b1 - b0), bar);
+  return (unsigned)(b1 - b0);
+}
+__device__ __forceinline__ unsigned stage_bytes(size_t lo_b, size_t hi_b, size_t end_b) {
+  const size_t b0 = lo_b & ~(size_t)15, lim = end_b & ~(size_t)15;
+  size_t b1 = (hi_b + 15) & ~(size_t)15;
+  if (b1 > lim) b1 = lim;
+  return b1 > b0 ? (unsigned)(b1 - b0) : 0u;
+}
+
+// oversized tile: the register-staged row routine straight from global memory (kept out of line: it must not set the register
+// budget of the streaming path)
+__device__ __noinline__ void spmv_row_direct(const f64* p00, const f64* p01, const f64* p10, const f64* p11, const int* pcol, int len,
+                                             int lane, unsigned gmask, const f64* x, size_t x_poff, int n_rows, f64& y0, f64& y1,
+                                             f64& y2, f64& yp) {
+  spmv_row<8, false, false>(p00, p01, p10, p11, pcol, len, lane, gmask, x, x_poff, n_rows, y0, y1, y2, yp);
+}
+
+template <int TS_GROUPS>
+__global__ void __launch_bounds__(32 * (TS_CWARPS * TS_GROUPS + 1), 1)
+k_spmv_tma(int row0, int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_ind, const f64* __restrict__ A00,
+           const f64* __restrict__ A01, const f64* __restrict__ A10, const f64* __restrict__ A11, f64 alpha,
+           const f64* __restrict__ x, size_t x_poff, f64 beta, f64* __restrict__ y, size_t y_poff) {
+  extern __shared__ __align__(16) unsigned char ts_smem[];
+  SpmvStage* stages = reinterpret_cast<SpmvStage*>(ts_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ts_smem + sizeof(SpmvStage) * TS_STAGES);
+  uint64_t* empty = full + TS_STAGES;
+  const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TS_STAGES; s++) { tma::mbar_init(full + s, 1); tma::mbar_init(empty + s, TS_CWARPS); }
+    tma::fence_barrier_init();
+  }
+  __syncthreads();
+  const int ntile = (n_rows - row0 + TS_TR - 1) / TS_TR;
+  if (warp == TS_CWARPS * TS_GROUPS) {
+    // ------------------------------ producer: one elected lane ------------------------------
+    if (lane32 != 0) return;
+    const size_t nnz_end = (size_t)__ldg(row_ptr + n_rows);
+    int t = blockIdx.x;
+    int s_nz = 0, e_nz = 0;
+    if (t < ntile) {
+      s_nz = __ldg(row_ptr + row0 + t * TS_TR);
+      e_nz = __ldg(row_ptr + min(n_rows, row0 + (t + 1) * TS_TR));
+    }
+    for (int j = 0; t < ntile; j++, t += gridDim.x) {
+      const int stg = j % TS_STAGES;
+      const unsigned ph = (unsigned)((j / TS_STAGES) & 1);
+      const int r0 = row0 + t * TS_TR, r1 = min(n_rows, r0 + TS_TR);
+      const size_t s = (size_t)s_nz, e = (size_t)e_nz;
+      const int tn = t + gridDim.x;        // row pointers of the next tile: one iteration ahead of their use
+      if (tn < ntile) {
+        s_nz = __ldg(row_ptr + row0 + tn * TS_TR);
+        e_nz = __ldg(row_ptr + min(n_rows, row0 + (tn + 1) * TS_TR));
+      }
+      SpmvStage* st = stages + stg;
+      tma::mbar_wait(empty + stg, ph ^ 1u);   // passes at once on the first lap
+      if (e - s > (size_t)TS_CAP) {
+        st->direct = 1;
+        tma::mbar_arrive(full + stg);
+        continue;
+      }
+      st->direct = 0;
+      const size_t rlo = (size_t)4 * r0, rhi = (size_t)4 * (r1 + 1), rend = (size_t)4 * ((size_t)n_rows + 1);
+      const unsigned total = stage_bytes(72 * s, 72 * e, 72 * nnz_end) + 2u * stage_bytes(24 * s, 24 * e, 24 * nnz_end) +
+                             stage_bytes(8 * s, 8 * e, 8 * nnz_end) + stage_bytes(4 * s, 4 * e, 4 * nnz_end) +
+                             stage_bytes(rlo, rhi, rend);
+      // hand-copied tails (inside stage_copy) are ordinary stores: they must precede the arrive below, so the copies are
+      // issued first and the barrier is armed afterwards (a transaction count may complete before it is expected)
+      stage_copy(st->a00, A00, 72 * s, 72 * e, 72 * nnz_end, full + stg);
+      stage_copy(st->a01, A01, 24 * s, 24 * e, 24 * nnz_end, full + stg);
+      stage_copy(st->a10, A10, 24 * s, 24 * e, 24 * nnz_end, full + stg);
+      stage_copy(st->a11, A11, 8 * s, 8 * e, 8 * nnz_end, full + stg);
+      stage_copy(st->col, col_ind, 4 * s, 4 * e, 4 * nnz_end, full + stg);
+      stage_copy(st->rowp, row_ptr, rlo, rhi, rend, full + stg);
+      tma::mbar_arrive_expect_tx(full + stg, total);
+    }
+    return;
+  }
+  // ------------------------------ consumers: 8 lanes per row, 4 rows per warp and tile ------------------------------
+  // consumer group g (8 warps) owns stage g: it takes the tiles j = g, g + TS_STAGES, ... of this CTA
+  constexpr int G = 8;
+  const int lane = lane32 & (G - 1), grp = lane32 >> 3;
+  const unsigned gmask = 0xffu << (lane32 & ~(G - 1));
+  const int cgrp = warp / TS_CWARPS, cw = warp % TS_CWARPS;
+  int t = blockIdx.x + cgrp * gridDim.x;
+  for (int j = cgrp; t < ntile; j += TS_GROUPS, t += TS_GROUPS * gridDim.x) {
+    const int stg = j % TS_STAGES;
+    const unsigned ph = (unsigned)((j / TS_STAGES) & 1);
+    const int r0 = row0 + t * TS_TR, r1 = min(n_rows, r0 + TS_TR);
+    const int row = r0 + cw * 4 + grp;
+    const bool live = row < r1;
+    const SpmvStage* st = stages + stg;
+    tma::mbar_wait(full + stg, ph);
+    f64 y0, y1, y2, yp;
+    if (st->direct) {
+      int start = 0, len = 0;
+      if (live) { start = __ldg(row_ptr + row); len = __ldg(row_ptr + row + 1) - start; }
+      spmv_row_direct(A00 + (size_t)start * 9, A01 + (size_t)start * 3, A10 + (size_t)start * 3, A11 + start, col_ind + start, len,
+                      lane, gmask, x, x_poff, n_rows, y0, y1, y2, yp);
+    } else {
+      const int* rp = st->rowp + (r0 & 3);
+      const int s = rp[0];
+      int k0 = 0, len = 0;
+      if (live) { k0 = rp[row - r0] - s; len = rp[row - r0 + 1] - s - k0; }
+      const int sh = s & 1;
+      spmv_row_smem<G, false>(st->a00 + sh + 9 * k0, st->a01 + sh + 3 * k0, st->a10 + sh + 3 * k0, st->a11 + sh + k0,
+                              st->col + (s & 3) + k0, len, lane, gmask, x, x_poff, n_rows, y0, y1, y2, yp);
+    }
+    __syncwarp();
+    if (lane32 == 0) tma::mbar_arrive(empty + stg);   // this warp is done reading the stage
+    if (live && lane == 0) spmv_store(y, y_poff, row, alpha, beta, y0, y1, y2, yp);
+  }
+}
+
+// measured in-solve on B200 (1M tets): G=8 67.8 us, G=16 71.8 us, G=32 122 us per mat-vec
+static int spmv_group() { return options().spmv_g; }
+
+static bool spmv_tma_on() { return options().spmv_tma != 0; }   // 0 selects the register-staged kernel (A/B measurements)
 
 // rows [row0, row1)
 int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, const f64* A00, const f64* A01, const f64* A10,
@@ -214,22 +433,31 @@ int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, cons
                 const P2PView* pv = nullptr, unsigned long long hseq = 0, int n_interior = 0) {
   if (row1 <= row0) return DFB_OK;
   const i64 rows = row1 - row0;
-#ifdef DFB_ENABLE_PDL
-#define DFB_SPMV_PDL(G)                                                                                                          \
-  if (pdl_on()) {                                                                                                                \
-    auto kfn = k_spmv_fs<G, false>;                                                                                              \
-    DFB_CUDA(launch_pdl(kfn, dim3(ceil_div(rows * G, 256)), dim3(256), st, row0, row1, row_ptr, col_ind, A00, A01, A10, A11,     \
-                        alpha, x, x_poff, beta, y, y_poff, (const P2PView*)nullptr, 0ull, 0));                                   \
-  } else
-#else
-#define DFB_SPMV_PDL(G)
-#endif
+  if (!pv && spmv_tma_on() &&
+      (((uintptr_t)row_ptr | (uintptr_t)col_ind | (uintptr_t)A00 | (uintptr_t)A01 | (uintptr_t)A10 | (uintptr_t)A11) & 15u) == 0) {
+    constexpr size_t smem = sizeof(SpmvStage) * TS_STAGES + 2 * TS_STAGES * sizeof(uint64_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+      DFB_CUDA(cudaFuncSetAttribute(k_spmv_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      DFB_CUDA(cudaFuncSetAttribute(k_spmv_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    const int ntile = ceil_div(rows, TS_TR);
+    if (options().spmv_tma == 2)
+      k_spmv_tma<2><<<std::min(ntile, num_sms()), 32 * (TS_CWARPS * 2 + 1), smem, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11,
+                                                                                        alpha, x, x_poff, beta, y, y_poff);
+    else
+      k_spmv_tma<3><<<std::min(ntile, num_sms()), 32 * (TS_CWARPS * 3 + 1), smem, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11,
+                                                                                        alpha, x, x_poff, beta, y, y_poff);
+    DFB_LAUNCH_CHECK();
+    return DFB_OK;
+  }
 #define DFB_SPMV(G)                                                                                                              \
   do {                                                                                                                           \
     if (pv)                                                                                                                      \
       k_spmv_fs<G, true><<<ceil_div(rows * G, 256), 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x,   \
                                                                   x_poff, beta, y, y_poff, pv, hseq, n_interior);               \
-    else DFB_SPMV_PDL(G)                                                                                                         \
+    else                                                                                                                         \
       k_spmv_fs<G, false><<<ceil_div(rows * G, 256), 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x,  \
                                                                    x_poff, beta, y, y_poff, nullptr, 0ull, 0);                  \
   } while (0)
@@ -311,7 +539,6 @@ __global__ void k_pc_apply(int n, const f64* __restrict__ dinv00, const f64* __r
 __global__ void k_scale_pc_apply(int n, const f64* __restrict__ scale, const f64* __restrict__ dinv00,
                                  const f64* __restrict__ dinv11, f64* __restrict__ w, size_t w_poff, f64* __restrict__ z,
                                  size_t z_poff) {
-  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const f64 s = *scale;
@@ -476,7 +703,6 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
                                                   unsigned* ctr, const P2PView* __restrict__ pv, unsigned long long seq) {
   __shared__ f64 smj[8][JT];
   __shared__ f64 hsum[P2P_ACAP];
-  pdl_prologue();
   const int ngrp = gridDim.y, gbase = ncol / ngrp, grem = ncol - gbase * ngrp;
   const int j0 = blockIdx.y * gbase + min((int)blockIdx.y, grem);
   const int nj = gbase + ((int)blockIdx.y < grem ? 1 : 0);
@@ -554,7 +780,6 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
   constexpr int PW = 32 / USPLIT;  // row pairs per warp
   __shared__ f64 sh[128];
   __shared__ f64 sm[8];
-  pdl_prologue();
   if (pv) {   // fused all-reduce of h: wait for every rank's partial (stored into OUR mailbox), sum in rank order
     const int R = pv->nranks, par = (int)(seq & 1ull);
     for (int j = threadIdx.x; j < ncol; j += 256) {
@@ -1008,12 +1233,6 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
       prof.end(st);
     } else {
       prof.begin("scale_pc_apply", st);
-#ifdef DFB_ENABLE_PDL
-      if (pdl_on())
-        DFB_CUDA(launch_pdl(k_scale_pc_apply, dim3(ceil_div(n_own, 128)), dim3(128), st, n_own, (const f64*)&W->S->inv_norm, (const f64*)dinv00,
-                            (const f64*)dinv11, QCOL(iter), poffC, zvec, poffN));
-      else
-#endif
       k_scale_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, &W->S->inv_norm, dinv00, dinv11, QCOL(iter), poffC,
                                                             zvec, poffN);
       DFB_LAUNCH_CHECK();
@@ -1028,12 +1247,6 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     prof.begin("multidot", st);
     const int ny = ceil_div(ncol, JT);
     const int mg = std::max(1, std::min(mgrid, (4 * num_sms()) / ny));   // one resident wave of (row chunk, column group) blocks
-#ifdef DFB_ENABLE_PDL
-    if (pdl_on() && !pv)
-      DFB_CUDA(launch_pdl(k_multidot, dim3(mg, ny), dim3(256), st, nl, (const f64*)Q, ldq, ncol, (const f64*)w, W->part, HCOL(iter), W->ctr,
-                          pv, seq));
-    else
-#endif
     k_multidot<<<dim3(mg, ny), 256, 0, st>>>(nl, Q, ldq, ncol, w, W->part, HCOL(iter), W->ctr, pv, seq);
     DFB_LAUNCH_CHECK();
     prof.end(st);
@@ -1044,12 +1257,6 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     }
     // w -= Q h, fused with ||w||^2 and (single GPU) the scalar Givens step  (krylov.c:176-183, 229-277)
     prof.begin("update", st);
-#ifdef DFB_ENABLE_PDL
-    if (pdl_on() && !pv)
-      DFB_CUDA(launch_pdl(k_update, dim3(ugrid), dim3(256), st, nl, (const f64*)Q, ldq, ncol, HCOL(iter), w, W->part, &W->S->nrm2_live,
-                          W->ctr + 1, W->parallel ? 0 : 1, W->S, W->gv, W->beta, W->tailc, W->res_hist, pv, seq));
-    else
-#endif
     k_update<<<ugrid, 256, 0, st>>>(nl, Q, ldq, ncol, HCOL(iter), w, W->part, &W->S->nrm2_live, W->ctr + 1, W->parallel ? 0 : 1,
                                     W->S, W->gv, W->beta, W->tailc, W->res_hist, pv, seq);
     DFB_LAUNCH_CHECK();

@@ -26,6 +26,7 @@ _SIGS = {
     "dfb_last_error": (C.c_char_p, []),
     "dfb_version": (ci, []),
     "dfb_launch_count": (C.c_longlong, []),
+    "dfb_set_option": (ci, [C.c_char_p, C.c_char_p]),
     "dfb_pattern_rows": (ci, [ci, ci, vp, vp, C.POINTER(ci), vp]),
     "dfb_pattern_cols": (ci, [ci, ci, vp, vp, vp, vp]),
     "dfb_pattern_expand": (ci, [ci, vp, vp, ci, ci, vp, vp, vp]),
@@ -96,6 +97,11 @@ def check(status: int, what: str = ""):
     if status != 0:
         msg = load().dfb_last_error().decode(errors="replace")
         raise DfbError(f"{what} failed with status {status}: {msg}")
+
+
+def set_option(key: str, value) -> None:
+    """Switch a library variant (include/dedflow_b200.h dfb_set_option); keys are the DFB_* environment names."""
+    check(load().dfb_set_option(key.encode(), str(value).encode()), f"dfb_set_option({key})")
 
 
 def launch_count() -> int:

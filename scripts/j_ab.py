@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-from dedflow_b200 import api, boxmesh  # noqa: E402
+from dedflow_b200 import api, boxmesh, lib as dlib  # noqa: E402
 
 m = int(sys.argv[1]) if len(sys.argv) > 1 else 55
 mesh = boxmesh.make_box(m)
@@ -33,7 +33,8 @@ CFGS = [("pull", {"DFB_J_VARIANT": "pull"}),
         ("pairs R=16", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "morton", "DFB_J_PAIR_ROWS": "16"}),
         ("fused", {"DFB_J_VARIANT": "fused"})]
 for name, env in CFGS:
-    os.environ.update(env)
+    for k_, v_ in env.items():
+        dlib.set_option(k_, v_)
     fs = api.FlowSystem(mesh)
     st = fs._stream()
     call = lambda: fs.L.dfb_assemble_tet(fs.plan, P(fs.xg), P(d_wg), P(d_dwg), None, P(fs.A00), P(fs.A01), P(fs.A10), P(fs.A11), 1, 1, st)

@@ -10,7 +10,7 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 from conftest import delaunay_mesh  # noqa: E402
-from dedflow_b200 import api, boxmesh  # noqa: E402
+from dedflow_b200 import api, boxmesh, lib as dlib  # noqa: E402
 
 for mesh in (delaunay_mesh(120, 12), boxmesh.make_box(5)):
     N = mesh.num_node
@@ -22,9 +22,9 @@ for mesh in (delaunay_mesh(120, 12), boxmesh.make_box(5)):
         fs.assemble_system(wg, dwg, J=True, mode=mode)
     import os
     for variant in ("pull", "fused", "pairs"):       # the three atomic-free Jacobian kernels (read per call)
-        os.environ["DFB_J_VARIANT"] = variant
+        dlib.set_option("DFB_J_VARIANT", variant)
         fs.assemble_system(wg, dwg, J=True, mode="gather")
-    os.environ.pop("DFB_J_VARIANT")
+    dlib.set_option("DFB_J_VARIANT", "pairs")
     x = torch.randn(6 * N, dtype=torch.float64, device="cuda")
     y = torch.zeros_like(x)
     fs.matrix_matvec(x, y)

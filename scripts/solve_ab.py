@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-from dedflow_b200 import api, boxmesh  # noqa: E402
+from dedflow_b200 import api, boxmesh, lib as dlib  # noqa: E402
 
 m = int(sys.argv[1])
 cfgs = sys.argv[2:] or ["-"]
@@ -27,7 +27,7 @@ for cfg in cfgs:
     if cfg != "-":
         for kv in cfg.split(","):
             k, v = kv.split("=")
-            os.environ[k] = v
+            dlib.set_option(k, v)
             keys.append(k)
     ts = []
     for i in range(8):
@@ -44,6 +44,5 @@ for cfg in cfgs:
         base = sol
     d = float((sol - base).abs().max() / base.abs().max())
     print(f"{cfg:40s} solve {np.median(ts):7.3f} ms  ({it} its, {np.median(ts) / it * 1e3:6.1f} us/it)  diff vs first {d:.1e}", flush=True)
-    for k in keys:
-        os.environ.pop(k, None)
+    # (options stay as set: list every switch explicitly in each configuration)
 fs.close()

@@ -113,10 +113,11 @@ def test_assembly_matches_oracle(api, oracle, m, shuffle, state, mode):
 
 @pytest.mark.parametrize("variant", ["pairs", "pull", "fused"])
 @pytest.mark.parametrize("m,shuffle", [(2, False), (7, True), (16, False)])
-def test_jacobian_variants_match_oracle(api, oracle, monkeypatch, variant, m, shuffle):
-    """The three atomic-free Jacobian assemblies (node pairs = default, pull, fused row gather; DFB_J_VARIANT is read per call),
+def test_jacobian_variants_match_oracle(api, oracle, variant, m, shuffle):
+    """The three atomic-free Jacobian assemblies (node pairs = default, pull, fused row gather; switched with dfb_set_option),
     overwrite and accumulate, against the oracle."""
-    monkeypatch.setenv("DFB_J_VARIANT", variant)
+    from dedflow_b200 import lib as _dlib
+    _dlib.set_option("DFB_J_VARIANT", variant)
     mesh = shuffled_mesh(m) if shuffle else boxmesh.make_box(m)
     fs, wg, dwg = make_pair(api, oracle, mesh, "B")
     ref = oracle_system(oracle, mesh, wg, dwg)
@@ -146,6 +147,7 @@ def test_jacobian_variants_match_oracle(api, oracle, monkeypatch, variant, m, sh
     for b, name in zip(bufs, ("A00", "A01", "A10", "A11")):
         assert bool((b[:G] == CANARY).all()) and bool((b[-G:] == CANARY).all()), (variant, name, "guard overwritten")
     fs.close()
+    _dlib.set_option("DFB_J_VARIANT", "pairs")
 
 
 def test_assembly_interior_only_and_accumulate(api, oracle):
