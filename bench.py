@@ -124,6 +124,12 @@ def ev_ms(torch, fn, reps):
     return float(np.median(ts))
 
 
+def workload_text(m, E, N):
+    """config.workload of BOTH arms at N = 1 (identical text: the driver compares the strings)."""
+    return (f"BASELINE configs[1]: Kuhn box m={m}, {E} tets, {N} nodes, fp64, state B; step = AssembleSystem(F) + AssembleSystem(J) "
+            "(tets + weak-BC faces + Dirichlet) + KrylovSolve (GMRES(120), the reference's stopping rule)")
+
+
 def algorithmic_bytes(N, E, Z):
     """SURVEY.md §8(d) / DESIGN.md: compulsory bytes per launch."""
     return {
@@ -189,7 +195,7 @@ def run_reference(args, rank, world):
     wg, dwg = boxmesh.state_random(N)
     line = {"metric": METRIC, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"Kuhn box m={args.m}: {E} tets, {N} nodes; step = AssembleSystem(F)+AssembleSystem(J)+KrylovSolve"}}
+            "config": {"workload": workload_text(args.m, E, N)}}
     use_cuda_ref = False
     try:
         import torch
@@ -229,6 +235,13 @@ def run_reference(args, rank, world):
         xs = torch.randn(6 * N, dtype=torch.float64, device="cuda")
         ys = torch.zeros_like(xs)
         tmv = ev_ms(torch, lambda: R.matvec(xs, ys), 20)
+
+        def ref_solve():
+            dx.zero_()
+            R.solve(dx, F)
+        R.assemble(d_wg, d_dwg, F_t=F)
+        R.assemble(d_wg, d_dwg, J=True)
+        tS = ev_ms(torch, ref_solve, 3)          # KrylovSolve on its own (its own event pair, not a difference of medians)
         Z = int(R.spy1x1.contents.nnz)
         ab = algorithmic_bytes(N, E, Z)
         val = E / (ms * 1e-3)
@@ -239,7 +252,7 @@ def run_reference(args, rank, world):
                      "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                      "breakdown": {"assemble_F_ms": tF, "assemble_J_ms": tJ, "assemble_elems_per_s": E / ((tF + tJ) * 1e-3),
                                    "spmv_ms": tmv, "spmv_gbs_reference_format": ab["spmv_reference_format"] / (tmv * 1e-3) / 1e9,
-                                   "solve_s_per_step": max(ms - tF - tJ, 0.0) * 1e-3, "gmres_iters": its[0]}})
+                                   "solve_s_per_step": tS * 1e-3, "gmres_iters": its[0]}})
     else:
         # bounded sample on the host cores
         t0 = time.time()
@@ -288,20 +301,40 @@ def run_ours(args, rank, world):
         dx.zero_()
         state["iters"], state["hist"] = fs.krylov_solve(dx, F)
 
+    copy_stream = torch.cuda.Stream()
+    ev_wg, ev_dwg = torch.cuda.Event(), torch.cuda.Event()
+
     def step_e2e():
-        d_wg.copy_(h_wg, non_blocking=True)
-        d_dwg.copy_(h_dwg, non_blocking=True)
-        step()
+        """the same step through the C ABI with HOST buffers.  The Jacobian only reads the velocities of wgalpha, so it is
+        assembled first and the upload of dwgalpha rides under it on a copy stream; the download of dx is the tail."""
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(copy_stream):
+            d_wg[:3 * N].copy_(h_wg[:3 * N], non_blocking=True)      # the velocities: all the Jacobian reads
+            ev_wg.record(copy_stream)
+            d_wg[3 * N:].copy_(h_wg[3 * N:], non_blocking=True)
+            d_dwg.copy_(h_dwg, non_blocking=True)
+            ev_dwg.record(copy_stream)
+        cur.wait_event(ev_wg)
+        fs.assemble_system(d_wg, d_dwg, J=True, mode=args.mode)
+        cur.wait_event(ev_dwg)
+        fs.assemble_system(d_wg, d_dwg, F=F, mode=args.mode)
+        dx.zero_()
+        state["iters"], state["hist"] = fs.krylov_solve(dx, F)
         h_dx.copy_(dx, non_blocking=True)
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)      # nvidia-smi needs ~0.3 s to deliver its first sample: start it before the
-    sampler.start()                         # warm-up so that samples exist for the (short) timed region
+    sampler.start()                         # priming so that samples exist for the (short) timed region
+    # priming (NOT the warm-up): first-use work -- assembly plans, Krylov workspace, allocator pools -- and >= 1 s of load so
+    # that the clocks are up; then EXACTLY --warmup untimed steps
     t_w = time.time()
-    nw = 0
-    while nw < max(args.warmup, 3) or time.time() - t_w < 1.0:
+    prime = 0
+    while prime < 2 or time.time() - t_w < 1.0:
         step()
-        nw += 1
+        prime += 1
+    for _ in range(args.warmup):
+        step()
+    nw = args.warmup
     torch.cuda.synchronize()
     l0 = dlib.launch_count()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -383,7 +416,7 @@ def run_ours(args, rank, world):
     roofs = {
         "k_spmv_fs": {"ms": t_spmv, "bytes": ab["spmv"]},
         "k_pairJ (assemble J, node pairs)": {"ms": tJk, "bytes": ab["assemble_J"]},
-        "k_elemF+k_gatherF (assemble F, gather)": {"ms": tFk, "bytes": ab["assemble_F"]},
+        "k_patchF+k_gatherF2 (assemble F, element patches)": {"ms": tFk, "bytes": ab["assemble_F"]},
         "KrylovSolve (all kernels)": {"ms": t_solve, "bytes": krylov_bytes},
     }
     for k, v in roofs.items():
@@ -393,7 +426,7 @@ def run_ours(args, rank, world):
     # well.  Algorithmic flops per element (FMA = 2): hoisted Jacobian 1.5 kflop, residual 1.6 kflop; peak = 148 SMs x 64
     # FP64 lanes x 2 x the SM clock sampled during the run.
     fp64_peak = 148 * 64 * 2 * (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
-    for k, fl in (("k_pairJ (assemble J, node pairs)", 1500.0), ("k_elemF+k_gatherF (assemble F, gather)", 1600.0)):
+    for k, fl in (("k_pairJ (assemble J, node pairs)", 1500.0), ("k_patchF+k_gatherF2 (assemble F, element patches)", 1600.0)):
         v = roofs[k]
         v["fp64"] = {"flops": fl * E, "achieved_tflops": fl * E / (v["ms"] * 1e-3) / 1e12, "peak_tflops": fp64_peak,
                      "frac": fl * E / (v["ms"] * 1e-3) / 1e12 / fp64_peak}
@@ -401,12 +434,25 @@ def run_ours(args, rank, world):
     # stream comparable bytes.  The named kernel is the SpMV (the one BASELINE.json's metric quotes).
     spmv_share = its * t_spmv / ms
     traffic = None                      # dram__bytes_read+write per launch from the committed `ncu --set full` capture
-    tp = ROOT / "profiles" / "r01_ncu_traffic.json"
-    if tp.exists() and args.m == 55:
-        try:
-            traffic = json.loads(tp.read_text())["k_spmv_fs"]["dram_bytes_per_launch"]
-        except Exception:
-            traffic = None
+    if args.m == 55:
+        for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+            tp = ROOT / "profiles" / name
+            if tp.exists():
+                try:
+                    traffic = json.loads(tp.read_text())["k_spmv_fs"]["dram_bytes_per_launch"]
+                    break
+                except Exception:
+                    traffic = None
+    # per-kernel CUDA-event times of one more solve (events around every launch: a diagnostic, not the timed region)
+    solve_kernels = None
+    try:
+        dlib.set_option("DFB_PROFILE", -1)
+        solve()
+        solve_kernels = dlib.solve_profile(fs.gmres)
+    except Exception:
+        solve_kernels = None
+    finally:
+        dlib.set_option("DFB_PROFILE", 0)
     roofline = {"kernel": "k_spmv_fs", "bound": "hbm", "achieved": roofs["k_spmv_fs"]["achieved"], "peak": hbm, "unit": "GB/s",
                 "frac": roofs["k_spmv_fs"]["frac"], "traffic": traffic, "peak_source": hbm_src,
                 "bytes_per_launch": ab["spmv"], "ms_per_launch": t_spmv, "share_of_step": spmv_share,
@@ -414,9 +460,8 @@ def run_ours(args, rank, world):
     line = {
         "metric": METRIC, "value": E / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": nw,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[1]: Kuhn box m={args.m}, {E} tets, {N} nodes, nnz {Z}; step = AssembleSystem(F) + "
-                               f"AssembleSystem(J) (tets+weak-BC faces+Dirichlet) + KrylovSolve (GMRES(120), {its} iterations to the "
-                               "reference's stopping rule), state B", "assembly_mode": args.mode,
+        "config": {"workload": workload_text(args.m, E, N), "nnz": Z, "gmres_iters": its, "assembly_mode": args.mode,
+                   "prime_steps": prime,
                    "l2": "step: working set (matrix 16*nnz*8 B = 328 MB + Krylov basis) exceeds the 126 MB L2, no explicit flush; "
                          "roofline kernel: L2 flushed (256 MB read) before every timed launch"},
         "clocks": clocks,
@@ -429,12 +474,67 @@ def run_ours(args, rank, world):
                       "assemble_J_kernel_elems_per_s": E / (tJk * 1e-3), "spmv_ms": t_spmv, "spmv_back_to_back_ms": t_spmv_b2b, "spmv_gbs": roofs["k_spmv_fs"]["achieved"],
                       "spmv_pct_hbm": 100 * roofs["k_spmv_fs"]["frac"], "solve_s_per_step": t_solve * 1e-3, "gmres_iters": its,
                       "solve_fixed_iterations_s": None if t_solve120 is None else t_solve120 * 1e-3, "fixed_iterations": its120,
-                      "setup_s": setup_s, "final_residual": float(state["hist"][-1]), "initial_residual": float(state["hist"][0])},
+                      "setup_s": setup_s, "final_residual": float(state["hist"][-1]), "initial_residual": float(state["hist"][0]),
+                      "solve_kernels": solve_kernels},
     }
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(mesh, wg, dwg)
-    emit(line)
     fs.close()
+    del fs, d_wg, d_dwg, F, dx, xs, ys
+    torch.cuda.empty_cache()
+    # BASELINE configs[2] on ONE GPU (the 1-GPU denominator of the strong-scaling blocks the N > 1 lines carry)
+    if args.m == 55 and not args.no_strong:
+        try:
+            line["strong_16M"] = strong_one_gpu(139, local_rank, steps=3)
+            if args.strong64:
+                line["strong_64M"] = strong_one_gpu(220, local_rank, steps=2)
+        except Exception as e:                     # a reported extra, never a reason to lose the line
+            line["strong_16M"] = {"error": repr(e)[:200]}
+    emit(line)
+
+
+def strong_one_gpu(m, local_rank, steps=3, mesh=None):
+    """One GPU, the whole m^3 box (BASELINE configs[2]/[3]), the reference's stopping rule: ms per step with its own clock sample."""
+    import torch
+    from dedflow_b200 import api, boxmesh
+    mesh = mesh if mesh is not None else boxmesh.make_box(m)
+    N, E = mesh.num_node, mesh.num_tet
+    t0 = time.time()
+    fs = api.FlowSystem(mesh, device=f"cuda:{local_rank}", with_colors=False)
+    wg, dwg = boxmesh.state_random(N)
+    d_wg, d_dwg = torch.from_numpy(wg).cuda(), torch.from_numpy(dwg).cuda()
+    F = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    dx = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    st = {}
+
+    def step():
+        fs.assemble_system(d_wg, d_dwg, F=F)
+        fs.assemble_system(d_wg, d_dwg, J=True)
+        dx.zero_()
+        st["iters"], st["hist"] = fs.krylov_solve(dx, F)
+    step()
+    torch.cuda.synchronize()
+    setup_s = time.time() - t0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    tF = ev_ms(torch, lambda: fs.assemble_system(d_wg, d_dwg, F=F), 3)
+    tJ = ev_ms(torch, lambda: fs.assemble_system(d_wg, d_dwg, J=True), 3)
+    clocks = sampler.stop()
+    Z = fs.nnz
+    fs.close()
+    del fs, d_wg, d_dwg, F, dx
+    torch.cuda.empty_cache()
+    return {"m": m, "elems": E, "nodes": N, "nnz": Z, "n_gpus": 1, "steps": steps, "ms_per_step": ms, "elems_per_s": E / (ms * 1e-3),
+            "gmres_iters": int(st["iters"]), "assemble_F_ms": tF, "assemble_J_ms": tJ, "setup_s": setup_s, "clocks": clocks}
 
 
 def run_timesteps(args, fs, mesh_or_local, localize, world, setup_s, dist=None, rank=0, Eg=None, Ng=None):
@@ -499,6 +599,9 @@ def main():
     ap.add_argument("--timesteps", type=int, default=0,
                     help="run BASELINE configs[4] instead: this many time steps with Newton reassembly (see run_timesteps)")
     ap.add_argument("--fixed-m", action="store_true", help="N > 1: keep --m (strong scaling) instead of growing the mesh with N")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling blocks (16M-tet mesh; 64M at 8 GPUs)")
+    ap.add_argument("--strong64", action="store_true", help="N = 1: also run the 64M-tet mesh on one GPU (about a minute)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the embedded parity check against the oracle")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -84,7 +84,7 @@ struct Options {
   int f_variant = 1;        // 0 scratch (k_elemF + k_gatherF), 1 patch (k_patchF)
   int f_patch_ctas = 2;     // register budget of k_patchF: resident CTAs per SM (2: 232 registers, measured faster; 3: 168 + spills)
   int spmv_g = 8;
-  int spmv_tma = 1;
+  int spmv_tma = 0;        // 0 register-staged k_spmv_fs (default: measured faster in-solve), 1/2 TMA ring with 3/2 consumer groups
   int krylov_tma = 1;
   int graph = 1;
   int profile = 0;

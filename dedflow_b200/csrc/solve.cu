@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -41,7 +42,7 @@ struct SolveProfiler {
   std::vector<Rec> recs;
   bool on;
   int level;
-  SolveProfiler() { level = options().profile; on = level > 0; }
+  SolveProfiler() { level = options().profile; on = level != 0; }
   void begin(const char* name, cudaStream_t st) {
     if (!on) return;
     Rec r; r.name = name;
@@ -50,8 +51,10 @@ struct SolveProfiler {
     recs.push_back(r);
   }
   void end(cudaStream_t st) { if (on) cudaEventRecord(recs.back().b, st); }
-  void report() {
-    if (!on) return;
+  // aggregates the records (waits for the last event), prints them unless level < 0, and returns "name:launches:total_ms;..."
+  std::string report() {
+    std::string out;
+    if (!on) return out;
     struct Agg { const char* name; int n; double ms; };
     std::vector<Agg> agg;
     double total = 0.0;
@@ -66,9 +69,15 @@ struct SolveProfiler {
       for (auto& g : agg) if (!strcmp(g.name, r.name)) { g.n++; g.ms += ms; found = true; break; }
       if (!found) agg.push_back({r.name, 1, (double)ms});
     }
-    for (auto& g : agg) fprintf(stderr, "[dfb profile] %-18s n=%4d total=%9.3f ms avg=%8.2f us\n", g.name, g.n, g.ms, 1e3 * g.ms / g.n);
-    fprintf(stderr, "[dfb profile] sum of kernels %.3f ms\n", total);
+    char buf[160];
+    for (auto& g : agg) {
+      if (level > 0) fprintf(stderr, "[dfb profile] %-18s n=%4d total=%9.3f ms avg=%8.2f us\n", g.name, g.n, g.ms, 1e3 * g.ms / g.n);
+      snprintf(buf, sizeof(buf), "%s:%d:%.6f;", g.name, g.n, g.ms);
+      out += buf;
+    }
+    if (level > 0) fprintf(stderr, "[dfb profile] sum of kernels %.3f ms\n", total);
     recs.clear();
+    return out;
   }
 };
 
@@ -1061,6 +1070,7 @@ struct dfb_gmres {
   int n_interior = 0;
   dfb_parallel_ops par = {0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool parallel = false;
+  std::string last_profile;   // per-kernel event times of the last solve (DFB_PROFILE != 0), see dfb_gmres_profile
 };
 
 extern "C" {
@@ -1125,6 +1135,12 @@ void dfb_gmres_destroy(dfb_gmres* w) {
 }
 
 size_t dfb_gmres_bytes(const dfb_gmres* w) { return w ? w->bytes : 0; }
+
+int dfb_gmres_profile(const dfb_gmres* w, char* buf, int capacity) {
+  if (!w || !buf || capacity <= 0) { set_error("dfb_gmres_profile: bad argument"); return DFB_ERR_ARG; }
+  snprintf(buf, (size_t)capacity, "%s", w->last_profile.c_str());
+  return DFB_OK;
+}
 
 int dfb_gmres_set_parallel(dfb_gmres* w, const dfb_parallel_ops* ops) {
   if (!w) { set_error("dfb_gmres_set_parallel: bad argument"); return DFB_ERR_ARG; }
@@ -1324,7 +1340,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   if (res_hist)
     for (int k = 0; k <= iter; k++) res_hist[k] = hist[k];
   *iters = iter;
-  prof.report();
+  W->last_profile = prof.report();
 #undef QCOL
 #undef HCOL
   return DFB_OK;

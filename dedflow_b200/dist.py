@@ -362,37 +362,75 @@ def weak_scaling_m(m1: int, world: int) -> int:
     return int(round(m1 * world ** (1.0 / 3.0)))
 
 
-def bench_main(args, rank, world, local_rank, B=None):
-    """bench.py --gpus N (N > 1): weak scaling, ~the configs[1] element count per GPU.  B = the bench module (it owns the
-    protected stdout the JSON line goes to)."""
-    import torch
-    import torch.distributed as dist
-    from . import boxmesh, lib as dlib
-    if B is None:
-        import bench as B
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    m = args.m if args.fixed_m else weak_scaling_m(args.m, world)
-    t0 = time.time()
+def gather_owned(lm, v_local, dist, torch):
+    """global 6N vector (on every rank) from the owned entries of the ranks' local vectors"""
+    g = np.zeros(6 * lm.num_node_global)
+    lm.scatter_owned(v_local, g)
+    t = torch.from_numpy(g).cuda()
+    dist.all_reduce(t)
+    return t.cpu().numpy()
+
+
+def bench_parity(dist, torch, rank, world, local_rank, owner_fn=None, m=20):
+    """The embedded parity check of `bench.py --gpus N`: BASELINE configs[0] (m=20, 48,000 tets) split over ALL N ranks, the
+    same collectives mode as the timed run (peer memory when available), one assembly + solve, gathered and compared on rank 0
+    with the single-domain CPU oracle.  Bars: F <= 1e-12, dx and residual history <= 1e-10, identical iteration count."""
+    from . import boxmesh
     mesh = boxmesh.make_box(m)
-    npart = slab_owner(mesh, world)
+    Ng = mesh.num_node
+    npart = (owner_fn or slab_owner)(mesh, world)
+    lm = partition(mesh, npart, rank, world)
+    wg_g, dwg_g = boxmesh.state_random(Ng)
+    fs = DistFlowSystem(lm, f"cuda:{local_rank}")
+    N = fs.N
+    d_wg, d_dwg = torch.from_numpy(lm.localize(wg_g)).cuda(), torch.from_numpy(lm.localize(dwg_g)).cuda()
+    F = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    dx = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    fs.assemble_system(d_wg, d_dwg, F=F)
+    fs.assemble_system(d_wg, d_dwg, J=True)
+    it, hist = fs.krylov_solve(dx, F)
+    torch.cuda.synchronize()
+    Fg = gather_owned(lm, F.cpu().numpy(), dist, torch)
+    xg = gather_owned(lm, dx.cpu().numpy(), dist, torch)
+    ghost = float(np.abs(lm.localize(xg)[:4 * N] - dx.cpu().numpy()[:4 * N]).max())   # ghosts of the solution after the final halo
+    out = {"mesh": f"Kuhn box m={m} ({mesh.num_tet} tets) over {world} ranks", "collectives": "peer-memory" if fs.p2p else "nccl",
+           "checker": "oracle/oracle.c (CPU, single domain)"}
+    ok = True
+    if rank == 0:
+        from oracle import pyoracle
+        ref = pyoracle.get().reference_step(mesh, wg_g, dwg_g)
+        rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+        out["F_rel"] = rel(Fg, ref["F"])
+        out["dx_rel"] = rel(xg[:4 * Ng], ref["dx"][:4 * Ng])
+        out["iters"] = int(it)
+        out["iters_equal"] = bool(it == ref["iters"])
+        out["hist_rel"] = float(np.abs(hist - ref["hist"]).max() / ref["hist"][0]) if out["iters_equal"] else float("inf")
+        out["ghost_abs"] = ghost
+        ok = (out["F_rel"] <= 1e-12 and out["dx_rel"] <= 1e-10 and out["hist_rel"] <= 1e-10 and out["iters_equal"] and
+              ghost <= 1e-12 * float(np.abs(ref["dx"]).max()))
+        out["ok"] = ok
+    fs.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    out["ok"] = bool(flag.item())
+    return out
+
+
+def _bench_case(B, args, dist, torch, dlib, mesh, rank, world, local_rank, fixed_its, steps, warmup, full, owner_fn=None):
+    """one mesh over all ranks: setup, warm-up, timed steps (barrier + synchronize on both sides, max over ranks)"""
+    from . import boxmesh
+    t0 = time.time()
+    npart = (owner_fn or slab_owner)(mesh, world)
     lm = partition(mesh, npart, rank, world)
     Ng, Eg = mesh.num_node, mesh.num_tet
     wg_g, dwg_g = boxmesh.state_random(Ng)
     wg, dwg = lm.localize(wg_g), lm.localize(dwg_g)
-    del mesh, wg_g, dwg_g
-    # Weak scaling keeps the work per GPU fixed: the mesh grows with N, and so would the iteration count the reference's
-    # stopping rule needs (40 at 1M tets, 60 at 4-8M).  The solve is therefore pinned to the 40 iterations configs[1] needs
-    # on one GPU; strong scaling (--fixed-m) runs the reference's stopping rule unchanged.
-    fixed_its = None if (args.fixed_m or getattr(args, "timesteps", 0) > 0) else 40
+    del wg_g, dwg_g
     fs = (DistFlowSystem(lm, f"cuda:{local_rank}") if fixed_its is None else
           DistFlowSystem(lm, f"cuda:{local_rank}", max_iter=fixed_its, atol=0.0, rtol=0.0))
     torch.cuda.synchronize()
     setup_s = time.time() - t0
     N = fs.N
-    if getattr(args, "timesteps", 0) > 0:
-        ret = B.run_timesteps(args, fs, lm, lm.localize, world, setup_s, dist=dist, rank=rank, Eg=Eg, Ng=Ng)
-        dist.destroy_process_group()
-        return ret
     h_wg, h_dwg = torch.from_numpy(wg).pin_memory(), torch.from_numpy(dwg).pin_memory()
     h_dx = torch.zeros(6 * N, dtype=torch.float64).pin_memory()
     d_wg, d_dwg = h_wg.cuda(), h_dwg.cuda()
@@ -406,27 +444,25 @@ def bench_main(args, rank, world, local_rank, B=None):
         dx.zero_()
         state["iters"], state["hist"] = fs.krylov_solve(dx, F)
 
+    copy_stream = torch.cuda.Stream()
+    ev_wg, ev_dwg = torch.cuda.Event(), torch.cuda.Event()
+
     def step_e2e():
-        d_wg.copy_(h_wg, non_blocking=True)
-        d_dwg.copy_(h_dwg, non_blocking=True)
-        step()
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(copy_stream):
+            d_wg[:3 * N].copy_(h_wg[:3 * N], non_blocking=True)      # the velocities: all the Jacobian reads
+            ev_wg.record(copy_stream)
+            d_wg[3 * N:].copy_(h_wg[3 * N:], non_blocking=True)
+            d_dwg.copy_(h_dwg, non_blocking=True)
+            ev_dwg.record(copy_stream)
+        cur.wait_event(ev_wg)
+        fs.assemble_system(d_wg, d_dwg, J=True)
+        cur.wait_event(ev_dwg)
+        fs.assemble_system(d_wg, d_dwg, F=F)
+        dx.zero_()
+        state["iters"], state["hist"] = fs.krylov_solve(dx, F)
         h_dx.copy_(dx, non_blocking=True)
         torch.cuda.synchronize()
-
-    sampler = B.ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    nw = 0
-    t_w = time.time()
-    while nw < max(args.warmup, 3) or (nw < 50 and time.time() - t_w < 1.0):
-        step()
-        nw += 1
-    # the warm-up count must agree on all ranks
-    nwt = torch.tensor([nw], device="cuda")
-    dist.all_reduce(nwt, op=dist.ReduceOp.MAX)
-    for _ in range(int(nwt.item()) - nw):
-        step()
-    nw = int(nwt.item())
 
     def timed(fn, k):
         torch.cuda.synchronize()
@@ -443,51 +479,155 @@ def bench_main(args, rank, world, local_rank, B=None):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)          # max over ranks
         return t.item() / k
 
+    sampler = B.ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # priming (first-use work + >= 1 s of load; a fixed count so that all ranks agree), then exactly `warmup` untimed steps
+    prime = 2 if not full else max(2, int(np.ceil(1.0 / 0.006 / 8)))
+    for _ in range(prime + warmup):
+        step()
     l0 = dlib.launch_count()
-    ms = timed(step, args.steps)
+    ms = timed(step, steps)
     launches = dlib.launch_count() - l0
-    ms_e2e = timed(step_e2e, args.steps)
-    tF = timed(lambda: fs.assemble_system(d_wg, d_dwg, F=F), 5)
-    tJ = timed(lambda: fs.assemble_system(d_wg, d_dwg, J=True), 5)
+    res = {"ms": ms, "launches": int(launches), "setup_s": setup_s, "N_local": N, "Ng": Ng, "Eg": Eg, "prime": prime,
+           "p2p": bool(fs.p2p)}
+    if full:
+        res["ms_e2e"] = timed(step_e2e, steps)
+    res["tF"] = timed(lambda: fs.assemble_system(d_wg, d_dwg, F=F), 3)
+    res["tJ"] = timed(lambda: fs.assemble_system(d_wg, d_dwg, J=True), 3)
 
     def solve():
         dx.zero_()
         state["iters"], state["hist"] = fs.krylov_solve(dx, F)
-    t_solve = timed(solve, 3)
-    xs = torch.randn(6 * N, dtype=torch.float64, device="cuda")
-    ys = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
-    t_spmv = timed(lambda: fs.matvec_owned(xs, ys), 20)
-    clocks = sampler.stop() if rank == 0 else None
+    res["t_solve"] = timed(solve, 3)
+    res["iters"], res["hist"] = int(state["iters"]), state["hist"]
+    # per-kernel CUDA-event times of one more solve on every rank (diagnostic): the in-solve mat-vec (halo wait included) is the
+    # roofline kernel, the waits of the fused collectives show up in the kernels that poll for them
+    dlib.set_option("DFB_PROFILE", -1)
+    solve()
+    prof = dlib.solve_profile(fs.gmres)
+    dlib.set_option("DFB_PROFILE", 0)
+    keys = sorted(prof)
+    t = torch.tensor([prof[k]["avg_us"] for k in keys], device="cuda", dtype=torch.float64)
+    tmax, tmin = t.clone(), t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+    res["solve_kernels"] = {k: {"launches": prof[k]["launches"], "avg_us_max_rank": float(a), "avg_us_min_rank": float(b)}
+                            for k, a, b in zip(keys, tmax.tolist(), tmin.tolist())}
+    res["clocks"] = sampler.stop() if rank == 0 else None
     Zt = torch.tensor([float(fs.row_ptr[fs.n_own].item())], device="cuda", dtype=torch.float64)   # owned nonzeros
     dist.all_reduce(Zt)
+    res["Zg"] = int(Zt.item())
+    fs.close()
+    del fs, d_wg, d_dwg, F, dx
+    torch.cuda.empty_cache()
+    return res
+
+
+def _strong_block(B, args, dist, torch, dlib, m, rank, world, local_rank, steps):
+    """BASELINE configs[2] / [3]: the m^3 box split over all ranks with the reference's stopping rule, followed by the SAME mesh
+    on rank 0's GPU alone (the other ranks wait) -- the 1-GPU denominator, measured in the same run at the same clocks."""
+    from . import boxmesh
+    mesh = boxmesh.make_box(m)
+    r = _bench_case(B, args, dist, torch, dlib, mesh, rank, world, local_rank, None, steps, 1, False)
+    one = None
+    if rank == 0:
+        try:
+            one = B.strong_one_gpu(m, local_rank, steps=steps, mesh=mesh)
+        except Exception as e:
+            one = {"error": repr(e)[:200]}
+    del mesh
+    dist.barrier()
+    if rank != 0:
+        return None
+    blk = {"m": m, "elems": r["Eg"], "nodes": r["Ng"], "n_gpus": world, "steps": steps, "ms_per_step": r["ms"],
+           "elems_per_s": r["Eg"] / (r["ms"] * 1e-3), "gmres_iters": r["iters"], "assemble_F_ms": r["tF"], "assemble_J_ms": r["tJ"],
+           "solve_ms": r["t_solve"], "setup_s": r["setup_s"], "clocks": r["clocks"], "solve_kernels": r["solve_kernels"],
+           "one_gpu": one}
+    if one and "ms_per_step" in one:
+        blk["efficiency_vs_one_gpu_same_run"] = one["ms_per_step"] / (world * r["ms"])
+    return blk
+
+
+def bench_main(args, rank, world, local_rank, B=None):
+    """bench.py --gpus N (N > 1).  In this order: (1) the embedded parity check (m=20 over all N ranks against the CPU oracle; a
+    missed bar fails the run), (2) the timed weak-scaling case (~the configs[1] element count per GPU), (3) the strong-scaling
+    blocks on the north star's meshes (16M tets; 64M at N = 8) with their 1-GPU denominators.  B = the bench module (it owns
+    the protected stdout the JSON line goes to)."""
+    import torch
+    import torch.distributed as dist
+    from . import boxmesh, lib as dlib
+    if B is None:
+        import bench as B
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if getattr(args, "timesteps", 0) > 0:
+        m = args.m if args.fixed_m else weak_scaling_m(args.m, world)
+        t0 = time.time()
+        mesh = boxmesh.make_box(m)
+        lm = partition(mesh, slab_owner(mesh, world), rank, world)
+        Ng, Eg = mesh.num_node, mesh.num_tet
+        del mesh
+        fs = DistFlowSystem(lm, f"cuda:{local_rank}")
+        torch.cuda.synchronize()
+        ret = B.run_timesteps(args, fs, lm, lm.localize, world, time.time() - t0, dist=dist, rank=rank, Eg=Eg, Ng=Ng)
+        dist.destroy_process_group()
+        return ret
+    parity = None
+    if not getattr(args, "no_parity", False):
+        parity = bench_parity(dist, torch, rank, world, local_rank)
+        if not parity["ok"]:
+            if rank == 0:
+                print("bench.py: embedded parity check FAILED: " + json.dumps(parity), file=sys.stderr)
+            dist.destroy_process_group()
+            raise SystemExit(1)
+    m = args.m if args.fixed_m else weak_scaling_m(args.m, world)
+    # Weak scaling keeps the work per GPU fixed: the mesh grows with N, and so would the iteration count the reference's
+    # stopping rule needs (40 at 1M tets, 60 at 4-8M).  The solve is therefore pinned to the 40 iterations configs[1] needs
+    # on one GPU; strong scaling (--fixed-m and the strong blocks) runs the reference's stopping rule unchanged.
+    fixed_its = None if args.fixed_m else 40
+    mesh = boxmesh.make_box(m)
+    r = _bench_case(B, args, dist, torch, dlib, mesh, rank, world, local_rank, fixed_its, args.steps, args.warmup, True)
+    del mesh
+    strong = {}
+    if not args.fixed_m and not getattr(args, "no_strong", False) and args.m == 55:
+        strong["strong_16M"] = _strong_block(B, args, dist, torch, dlib, 139, rank, world, local_rank, 3)
+        if world >= 8:
+            strong["strong_64M"] = _strong_block(B, args, dist, torch, dlib, 220, rank, world, local_rank, 2)
     if rank == 0:
         hbm, hbm_src = B.measured_hbm_peak()
-        Zg = int(Zt.item())
+        Ng, Eg, Zg, N = r["Ng"], r["Eg"], r["Zg"], r["N_local"]
         ab = B.algorithmic_bytes(Ng, Eg, Zg)
+        its = r["iters"]
+        # roofline kernel: the mat-vec AS IT RUNS INSIDE THE SOLVE (peer-memory mode: one launch whose boundary-row blocks wait
+        # for the neighbours' halo stores), slowest rank, all ranks' bytes
+        t_spmv = r["solve_kernels"].get("spmv", {}).get("avg_us_max_rank", float("nan")) * 1e-3
         spmv_gbs = ab["spmv"] / (t_spmv * 1e-3) / 1e9
-        its = state["iters"]
         line = {
-            "metric": B.METRIC, "value": Eg / (ms * 1e-3), "unit": B.UNIT, "n_gpus": world, "steps": args.steps, "warmup": nw,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.fixed_m else "weak", "vs_baseline": None,
+            "metric": B.METRIC, "value": Eg / (r["ms"] * 1e-3), "unit": B.UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "strong" if args.fixed_m else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"Kuhn box m={m}: {Eg} tets, {Ng} nodes over {world} GPUs (z-slab node ownership, ghost elements "
-                                   f"recomputed; halo + all-reduces {'fused into the Krylov kernels over NVLink peer memory' if fs.p2p else 'by NCCL'}); "
+                                   f"recomputed; halo + all-reduces {'fused into the Krylov kernels over NVLink peer memory' if r['p2p'] else 'by NCCL'}); "
                                    f"step = AssembleSystem(F)+AssembleSystem(J)+KrylovSolve ({its} GMRES iterations"
                                    f"{', pinned: weak scaling keeps per-GPU work fixed' if fixed_its else ', reference stopping rule'}), state B",
-                       "elements_per_gpu": Eg / world, "collectives": "peer-memory" if fs.p2p else "nccl",
+                       "elements_per_gpu": Eg / world, "collectives": "peer-memory" if r["p2p"] else "nccl", "prime_steps": r["prime"],
                        "l2": "per-GPU working set exceeds the 126 MB L2; no explicit flush"},
-            "clocks": clocks,
-            "e2e": {"value": Eg / (ms_e2e * 1e-3), "unit": B.UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 2 * 6 * N * 8 * world,
+            "clocks": r["clocks"],
+            "parity": parity,
+            "e2e": {"value": Eg / (r["ms_e2e"] * 1e-3), "unit": B.UNIT, "ms_per_step": r["ms_e2e"], "h2d_bytes_per_step": 2 * 6 * N * 8 * world,
                     "d2h_bytes_per_step": 6 * N * 8 * world},
-            "gpu_launches": int(launches),
-            "roofline": {"kernel": "k_spmv_fs (+halo)", "bound": "hbm", "achieved": spmv_gbs, "peak": hbm * world, "unit": "GB/s",
-                         "frac": spmv_gbs / (hbm * world), "traffic": None, "peak_source": hbm_src + f" x {world} GPUs",
-                         "bytes_per_launch": ab["spmv"], "ms_per_launch": t_spmv},
-            "breakdown": {"assemble_F_ms": tF, "assemble_J_ms": tJ, "assemble_elems_per_s": Eg / ((tF + tJ) * 1e-3), "spmv_ms": t_spmv,
-                          "spmv_gbs": spmv_gbs, "spmv_pct_hbm": 100 * spmv_gbs / (hbm * world), "solve_s_per_step": t_solve * 1e-3,
-                          "gmres_iters": its, "setup_s": setup_s, "final_residual": float(state["hist"][-1]),
-                          "initial_residual": float(state["hist"][0])},
+            "gpu_launches": r["launches"],
+            "roofline": {"kernel": "k_spmv_fs<8,peer> as launched inside the solve (halo wait included), slowest rank", "bound": "hbm",
+                         "achieved": spmv_gbs, "peak": hbm * world, "unit": "GB/s", "frac": spmv_gbs / (hbm * world),
+                         "traffic": None, "traffic_note": "ncu is a one-GPU tool here (never run on a multi-rank command); the per-launch "
+                                                           "DRAM bytes of the same kernel at N=1 are in the N=1 line",
+                         "peak_source": hbm_src + f" x {world} GPUs", "bytes_per_launch": ab["spmv"], "ms_per_launch": t_spmv},
+            "breakdown": {"assemble_F_ms": r["tF"], "assemble_J_ms": r["tJ"], "assemble_elems_per_s": Eg / ((r["tF"] + r["tJ"]) * 1e-3),
+                          "spmv_ms": t_spmv, "spmv_gbs": spmv_gbs, "spmv_pct_hbm": 100 * spmv_gbs / (hbm * world),
+                          "solve_s_per_step": r["t_solve"] * 1e-3, "gmres_iters": its, "setup_s": r["setup_s"],
+                          "final_residual": float(r["hist"][-1]), "initial_residual": float(r["hist"][0]),
+                          "solve_kernels": r["solve_kernels"]},
         }
+        line.update({k: v for k, v in strong.items() if v is not None})
         B.emit(line)
-    fs.close()
     dist.destroy_process_group()

@@ -27,6 +27,7 @@ _SIGS = {
     "dfb_version": (ci, []),
     "dfb_launch_count": (C.c_longlong, []),
     "dfb_set_option": (ci, [C.c_char_p, C.c_char_p]),
+    "dfb_gmres_profile": (ci, [vp, C.c_char_p, ci]),
     "dfb_pattern_rows": (ci, [ci, ci, vp, vp, C.POINTER(ci), vp]),
     "dfb_pattern_cols": (ci, [ci, ci, vp, vp, vp, vp]),
     "dfb_pattern_expand": (ci, [ci, vp, vp, ci, ci, vp, vp, vp]),
@@ -102,6 +103,18 @@ def check(status: int, what: str = ""):
 def set_option(key: str, value) -> None:
     """Switch a library variant (include/dedflow_b200.h dfb_set_option); keys are the DFB_* environment names."""
     check(load().dfb_set_option(key.encode(), str(value).encode()), f"dfb_set_option({key})")
+
+
+def solve_profile(ws) -> dict:
+    """{kernel: {"launches": n, "total_ms": t, "avg_us": a}} of the last solve of a dfb_gmres workspace (DFB_PROFILE != 0)."""
+    buf = C.create_string_buffer(4096)
+    check(load().dfb_gmres_profile(ws, buf, 4096), "dfb_gmres_profile")
+    out = {}
+    for item in buf.value.decode().split(";"):
+        if item:
+            name, n, ms = item.rsplit(":", 2)
+            out[name] = {"launches": int(n), "total_ms": float(ms), "avg_us": 1e3 * float(ms) / max(1, int(n))}
+    return out
 
 
 def launch_count() -> int:

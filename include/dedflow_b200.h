@@ -147,6 +147,9 @@ typedef struct dfb_gmres dfb_gmres;
 int dfb_gmres_create(dfb_gmres** ws, int num_node, int max_iter);
 void dfb_gmres_destroy(dfb_gmres* ws);
 size_t dfb_gmres_bytes(const dfb_gmres* ws);
+/* Per-kernel CUDA-event times of the LAST solve of this workspace, "name:launches:total_ms;..." (empty unless the option
+ * DFB_PROFILE is non-zero: 1 also prints the table to stderr, 2 every launch, -1 only records). */
+int dfb_gmres_profile(const dfb_gmres* w, char* buf, int capacity);
 /* Optional data-parallel hooks (multi-GPU, one process per GPU).  Local node numbering of a rank is
  * [interior-owned | boundary-owned | ghost]: rows [0,n_own) are owned and assembled completely on this rank, rows
  * [0,n_interior) reference no ghost column.  Inner products run over the owned rows and are summed over ranks with

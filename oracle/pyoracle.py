@@ -307,6 +307,31 @@ class Oracle:
     def num_threads(self):
         return int(self.L.orc_num_threads())
 
+    def reference_step(self, mesh, wg, dwg, solve=True):
+        """One step of the hot path as main.c:31-75 + :215-221 runs it (assemble F and J with weak-BC faces and Dirichlet rows,
+        then the GMRES solve): the checker of the bench-embedded parity test and of tests/test_gpu_parity.py."""
+        ctx = self.driver_setup(mesh)
+        N = mesh.num_node
+        rp, ci = ctx["pattern"]
+        Z = ci.size
+        F = np.zeros(6 * N)
+        blocks = [np.zeros(9 * Z), np.zeros(3 * Z), np.zeros(3 * Z), np.zeros(Z)]
+        self.assemble_tet(N, mesh.ien, mesh.xg, ctx["off"], ctx["ind"], wg, dwg, F=F)
+        self.assemble_tet(N, mesh.ien, mesh.xg, ctx["off"], ctx["ind"], wg, dwg, pattern=(rp, ci), blocks=blocks)
+        if mesh.num_bound > 4:
+            f2e, forn = mesh.bound_faces(4)
+            self.assemble_face(f2e, forn, N, mesh.ien, mesh.xg, ctx["color"], ctx["nc"], wg, dwg, F=F)
+            self.assemble_face(f2e, forn, N, mesh.ien, mesh.xg, ctx["color"], ctx["nc"], wg, dwg, pattern=(rp, ci), blocks=blocks)
+        F[4 * N:] = 0
+        for b, t in self.BCS.items():
+            if b < mesh.num_bound:
+                self.dirichlet_vec(mesh.bound_nodes(b), np.array(t, np.int32), F)
+                self.dirichlet_mat(mesh.bound_nodes(b), np.array(t, np.int32), N, (rp, ci), blocks[0], blocks[1])
+        out = dict(pattern=(rp, ci), F=F, blocks=blocks)
+        if solve:
+            out["dx"], out["iters"], out["hist"] = self.gmres((rp, ci), blocks, F)
+        return out
+
 
 # ----------------------------------------------------------------------------------------
 # cuRAND host generator (libcurand is a CPU library for the *Host generator): the reference draws its
