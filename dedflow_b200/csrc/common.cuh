@@ -85,6 +85,7 @@ struct Options {
   int f_patch_ctas = 2;     // register budget of k_patchF: resident CTAs per SM (2: 232 registers, measured faster; 3: 168 + spills)
   int spmv_g = 8;
   int spmv_tma = 0;        // 0 register-staged k_spmv_fs (default: measured faster in-solve), 1/2 TMA ring with 3/2 consumer groups
+  int spmv_peer_split = 0;  // peer-memory mat-vec as two launches (interior rows by the plain kernel)
   int krylov_tma = 1;
   int graph = 1;
   int profile = 0;

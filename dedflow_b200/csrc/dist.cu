@@ -91,6 +91,18 @@ __global__ void k_halo_unpack(int n, const int* __restrict__ nodes, const f64* _
   xu[0] = b[0]; xu[1] = b[1]; xu[2] = b[2]; x[poff + nd] = b[3];
 }
 
+// the same for a vector in the solver's interleaved layout x[4 node + c]
+__global__ void k_halo_pack_aos(int n, const int* __restrict__ nodes, const f64* __restrict__ x, f64* __restrict__ buf) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * n) return;
+  reinterpret_cast<double2*>(buf)[t] = reinterpret_cast<const double2*>(x)[(size_t)nodes[t >> 1] * 2 + (t & 1)];
+}
+__global__ void k_halo_unpack_aos(int n, const int* __restrict__ nodes, const f64* __restrict__ buf, f64* __restrict__ x) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * n) return;
+  reinterpret_cast<double2*>(x)[(size_t)nodes[t >> 1] * 2 + (t & 1)] = reinterpret_cast<const double2*>(buf)[t];
+}
+
 }  // namespace dfb
 
 using namespace dfb;
@@ -194,7 +206,7 @@ int dfb_comm_allreduce(double* d_buf, int count, void* stream, void* user) {
 
 // pack -> grouped send/recv -> unpack on the communicator's own stream, ordered after everything already
 // enqueued on `stream`; the caller keeps computing on `stream` until dfb_comm_halo_end.
-int dfb_comm_halo_begin(double* d_x, void* stream, void* user) {
+static int halo_begin_impl(double* d_x, void* stream, void* user, bool aos) {
   dfb_comm* c = reinterpret_cast<dfb_comm*>(user);
   if (!c || !d_x) { set_error("dfb_comm_halo_begin: bad argument"); return DFB_ERR_ARG; }
   if (c->nranks == 1 || c->nbr.empty()) return DFB_OK;
@@ -203,7 +215,8 @@ int dfb_comm_halo_begin(double* d_x, void* stream, void* user) {
   DFB_CUDA(cudaEventRecord(c->ev_ready, st));
   DFB_CUDA(cudaStreamWaitEvent(cs, c->ev_ready, 0));
   if (c->n_send) {
-    k_halo_pack<<<ceil_div(c->n_send, 256), 256, 0, cs>>>(c->n_send, c->d_send_nodes, d_x, poff, c->d_send_buf);
+    if (aos) k_halo_pack_aos<<<ceil_div(2 * (i64)c->n_send, 256), 256, 0, cs>>>(c->n_send, c->d_send_nodes, d_x, c->d_send_buf);
+    else k_halo_pack<<<ceil_div(c->n_send, 256), 256, 0, cs>>>(c->n_send, c->d_send_nodes, d_x, poff, c->d_send_buf);
     DFB_LAUNCH_CHECK();
   }
   DFB_NCCL(g_nccl.GroupStart());
@@ -215,12 +228,15 @@ int dfb_comm_halo_begin(double* d_x, void* stream, void* user) {
   DFB_NCCL(g_nccl.GroupEnd());
   count_launch();
   if (c->n_recv) {
-    k_halo_unpack<<<ceil_div(c->n_recv, 256), 256, 0, cs>>>(c->n_recv, c->d_recv_nodes, c->d_recv_buf, d_x, poff);
+    if (aos) k_halo_unpack_aos<<<ceil_div(2 * (i64)c->n_recv, 256), 256, 0, cs>>>(c->n_recv, c->d_recv_nodes, c->d_recv_buf, d_x);
+    else k_halo_unpack<<<ceil_div(c->n_recv, 256), 256, 0, cs>>>(c->n_recv, c->d_recv_nodes, c->d_recv_buf, d_x, poff);
     DFB_LAUNCH_CHECK();
   }
   DFB_CUDA(cudaEventRecord(c->ev_done, cs));
   return DFB_OK;
 }
+int dfb_comm_halo_begin(double* d_x, void* stream, void* user) { return halo_begin_impl(d_x, stream, user, false); }
+int dfb_comm_halo_begin_aos(double* d_x4, void* stream, void* user) { return halo_begin_impl(d_x4, stream, user, true); }
 
 int dfb_comm_halo_end(double* d_x, void* stream, void* user) {
   dfb_comm* c = reinterpret_cast<dfb_comm*>(user);

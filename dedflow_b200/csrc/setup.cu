@@ -40,6 +40,7 @@ static bool apply_option(Options& o, const char* key, const char* v) {
   if (is("DFB_F_PATCH_CTAS")) { o.f_patch_ctas = atoi(v) == 3 ? 3 : 2; return true; }
   if (is("DFB_SPMV_G")) { const int g = atoi(v); o.spmv_g = (g == 4 || g == 8 || g == 16 || g == 32) ? g : 8; return true; }
   if (is("DFB_SPMV_TMA")) { o.spmv_tma = atoi(v); return true; }
+  if (is("DFB_SPMV_PEER_SPLIT")) { o.spmv_peer_split = atoi(v) != 0; return true; }
   if (is("DFB_KRYLOV_TMA")) { o.krylov_tma = atoi(v) != 0; return true; }
   if (is("DFB_GRAPH")) { o.graph = atoi(v) != 0; return true; }
   if (is("DFB_PROFILE")) { o.profile = atoi(v); return true; }
@@ -55,7 +56,7 @@ Options& options() {
   static Options o = [] {
     Options t;
     static const char* keys[] = {"DFB_J_VARIANT", "DFB_J_PAIR_ROWS", "DFB_J_PAIR_ORDER", "DFB_J_PULL_PLAIN", "DFB_F_VARIANT", "DFB_F_PATCH_CTAS", "DFB_SPMV_G",
-                                 "DFB_SPMV_TMA", "DFB_KRYLOV_TMA", "DFB_GRAPH", "DFB_PROFILE", "DFB_VERBOSE", "DFB_ASSEMBLE_MODE"};
+                                 "DFB_SPMV_TMA", "DFB_SPMV_PEER_SPLIT", "DFB_KRYLOV_TMA", "DFB_GRAPH", "DFB_PROFILE", "DFB_VERBOSE", "DFB_ASSEMBLE_MODE"};
     for (const char* k : keys) {
       const char* v = getenv(k);
       if (v && *v) apply_option(t, k, v);

@@ -90,7 +90,7 @@ struct GmresScalars {
   f64 cw;          // peer-memory mode: dead-tail coefficient of the current w, -sum_j h_j tailc_j (set by k_update)
 };
 
-__device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist);
+__device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist, f64* qs);
 
 // ------------------------------------------------------------------------------------------------------------
 // SpMV.  Row i of the output: u -> y[3*i + ii], p -> y[y_poff + i]; input x: u -> x[3*c + l], p -> x[x_poff + c].
@@ -108,7 +108,9 @@ __device__ __forceinline__ f64 ld_x(const f64* p, bool ghost) { return (PEER && 
 // One nodal row by the G lanes of a group.  p00/p01/p10/p11/pcol point at the row's value / column streams (global memory, or
 // a shared-memory stage filled by the TMA unit: SMEM), len = nodal nonzeros of the row.  Returns the group-reduced
 // (y0, y1, y2, yp) in every lane of the group.
-template <int G, bool PEER, bool SMEM>
+// AOSX: x is interleaved per node, x[4*node + c] (c = 0..2 velocity, 3 pressure) -- the solver's own layout, one 32-byte sector
+// per gathered column -- instead of the ABI layout x[3*node + c] / x[x_poff + node].
+template <int G, bool PEER, bool SMEM, bool AOSX>
 __device__ __forceinline__ void spmv_row(const f64* __restrict__ p00, const f64* __restrict__ p01, const f64* __restrict__ p10,
                                          const f64* __restrict__ p11, const int* __restrict__ pcol, int len, int lane, unsigned gmask,
                                          const f64* __restrict__ x, size_t x_poff, int n_rows, f64& y0, f64& y1, f64& y2, f64& yp) {
@@ -143,14 +145,14 @@ __device__ __forceinline__ void spmv_row(const f64* __restrict__ p00, const f64*
       bp = __ldcs(p11 + kk);
       col = __ldg(pcol + kk);
     }
-    const f64 xp = okk ? ld_x<PEER>(x + x_poff + col, col >= n_rows) : 0.0;
+    const f64 xp = okk ? ld_x<PEER>(AOSX ? x + (size_t)col * 4 + 3 : x + x_poff + col, col >= n_rows) : 0.0;
     f64 xv[3];
 #pragma unroll
     for (int u = 0; u < 3; u++) {
       const int q = u * G + lane;          // position inside the chunk's 3*G velocity entries
       const int kl = q / 3, l = q - 3 * kl;
       const int cu = __shfl_sync(gmask, col, kl, G);
-      xv[u] = oku[u] ? ld_x<PEER>(x + (size_t)cu * 3 + l, cu >= n_rows) : 0.0;
+      xv[u] = oku[u] ? ld_x<PEER>(x + (size_t)cu * (AOSX ? 4 : 3) + l, cu >= n_rows) : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < 3; u++) {
@@ -173,10 +175,11 @@ __device__ __forceinline__ void spmv_row(const f64* __restrict__ p00, const f64*
   }
 }
 
+template <bool AOSY>
 __device__ __forceinline__ void spmv_store(f64* __restrict__ y, size_t y_poff, int row, f64 alpha, f64 beta, f64 y0, f64 y1, f64 y2,
                                            f64 yp) {
-  f64* yu = y + (size_t)row * 3;
-  f64* ypp = y + y_poff + row;
+  f64* yu = y + (size_t)row * (AOSY ? 4 : 3);
+  f64* ypp = AOSY ? yu + 3 : y + y_poff + row;
   if (beta == 0.0) {
     yu[0] = alpha * y0; yu[1] = alpha * y1; yu[2] = alpha * y2; *ypp = alpha * yp;
   } else {
@@ -188,7 +191,7 @@ __device__ __forceinline__ void spmv_store(f64* __restrict__ y, size_t y_poff, i
 // The same row out of a shared-memory stage, two chunks of G nonzeros per trip: the values cost nothing to fetch, the only
 // long latency left is the x gather through L2, so all 8 gathers of a lane (rows of up to 2G nonzeros: ONE trip) are issued
 // before the first FMA.  Same summation order as spmv_row (chunk by chunk), hence bit-identical results.
-template <int G, bool PEER>
+template <int G, bool PEER, bool AOSX>
 __device__ __forceinline__ void spmv_row_smem(const f64* __restrict__ p00, const f64* __restrict__ p01, const f64* __restrict__ p10,
                                               const f64* __restrict__ p11, const int* __restrict__ pcol, int len, int lane,
                                               unsigned gmask, const f64* __restrict__ x, size_t x_poff, int n_rows, f64& y0, f64& y1,
@@ -205,7 +208,7 @@ __device__ __forceinline__ void spmv_row_smem(const f64* __restrict__ p00, const
       const bool okk = k < len;
       kk[h] = okk ? k : -1;
       const int col = okk ? pcol[k] : 0;
-      xp[h] = okk ? ld_x<PEER>(x + x_poff + col, col >= n_rows) : 0.0;
+      xp[h] = okk ? ld_x<PEER>(AOSX ? x + (size_t)col * 4 + 3 : x + x_poff + col, col >= n_rows) : 0.0;
 #pragma unroll
       for (int u = 0; u < 3; u++) {
         const int q = u * G + lane;
@@ -214,7 +217,7 @@ __device__ __forceinline__ void spmv_row_smem(const f64* __restrict__ p00, const
         const int t = 3 * cb + q;
         const bool ok = t < len3;
         tt[h][u] = ok ? t : -1;
-        xv[h][u] = ok ? ld_x<PEER>(x + (size_t)cu * 3 + l, cu >= n_rows) : 0.0;
+        xv[h][u] = ok ? ld_x<PEER>(x + (size_t)cu * (AOSX ? 4 : 3) + l, cu >= n_rows) : 0.0;
       }
     }
 #pragma unroll
@@ -243,7 +246,7 @@ __device__ __forceinline__ void spmv_row_smem(const f64* __restrict__ p00, const
   }
 }
 
-template <int G, bool PEER>
+template <int G, bool PEER, bool AOSX, bool AOSY>
 __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
                                                  const f64* __restrict__ A00, const f64* __restrict__ A01,
                                                  const f64* __restrict__ A10, const f64* __restrict__ A11, f64 alpha,
@@ -269,9 +272,9 @@ __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int
     len = __ldg(row_ptr + row + 1) - start;
   }
   f64 y0, y1, y2, yp;
-  spmv_row<G, PEER, false>(A00 + (size_t)start * 9, A01 + (size_t)start * 3, A10 + (size_t)start * 3, A11 + start, col_ind + start, len,
-                           lane, gmask, x, x_poff, n_rows, y0, y1, y2, yp);
-  if (live && lane == 0) spmv_store(y, y_poff, row, alpha, beta, y0, y1, y2, yp);
+  spmv_row<G, PEER, false, AOSX>(A00 + (size_t)start * 9, A01 + (size_t)start * 3, A10 + (size_t)start * 3, A11 + start,
+                                 col_ind + start, len, lane, gmask, x, x_poff, n_rows, y0, y1, y2, yp);
+  if (live && lane == 0) spmv_store<AOSY>(y, y_poff, row, alpha, beta, y0, y1, y2, yp);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -329,13 +332,14 @@ __device__ __forceinline__ unsigned stage_bytes(size_t lo_b, size_t hi_b, size_t
 
 // oversized tile: the register-staged row routine straight from global memory (kept out of line: it must not set the register
 // budget of the streaming path)
+template <bool AOSX>
 __device__ __noinline__ void spmv_row_direct(const f64* p00, const f64* p01, const f64* p10, const f64* p11, const int* pcol, int len,
                                              int lane, unsigned gmask, const f64* x, size_t x_poff, int n_rows, f64& y0, f64& y1,
                                              f64& y2, f64& yp) {
-  spmv_row<8, false, false>(p00, p01, p10, p11, pcol, len, lane, gmask, x, x_poff, n_rows, y0, y1, y2, yp);
+  spmv_row<8, false, false, AOSX>(p00, p01, p10, p11, pcol, len, lane, gmask, x, x_poff, n_rows, y0, y1, y2, yp);
 }
 
-template <int TS_GROUPS>
+template <int TS_GROUPS, bool AOSX, bool AOSY>
 __global__ void __launch_bounds__(32 * (TS_CWARPS * TS_GROUPS + 1), 1)
 k_spmv_tma(int row0, int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_ind, const f64* __restrict__ A00,
            const f64* __restrict__ A01, const f64* __restrict__ A10, const f64* __restrict__ A11, f64 alpha,
@@ -414,7 +418,7 @@ k_spmv_tma(int row0, int n_rows, const int* __restrict__ row_ptr, const int* __r
     if (st->direct) {
       int start = 0, len = 0;
       if (live) { start = __ldg(row_ptr + row); len = __ldg(row_ptr + row + 1) - start; }
-      spmv_row_direct(A00 + (size_t)start * 9, A01 + (size_t)start * 3, A10 + (size_t)start * 3, A11 + start, col_ind + start, len,
+      spmv_row_direct<AOSX>(A00 + (size_t)start * 9, A01 + (size_t)start * 3, A10 + (size_t)start * 3, A11 + start, col_ind + start, len,
                       lane, gmask, x, x_poff, n_rows, y0, y1, y2, yp);
     } else {
       const int* rp = st->rowp + (r0 & 3);
@@ -422,12 +426,12 @@ k_spmv_tma(int row0, int n_rows, const int* __restrict__ row_ptr, const int* __r
       int k0 = 0, len = 0;
       if (live) { k0 = rp[row - r0] - s; len = rp[row - r0 + 1] - s - k0; }
       const int sh = s & 1;
-      spmv_row_smem<G, false>(st->a00 + sh + 9 * k0, st->a01 + sh + 3 * k0, st->a10 + sh + 3 * k0, st->a11 + sh + k0,
+      spmv_row_smem<G, false, AOSX>(st->a00 + sh + 9 * k0, st->a01 + sh + 3 * k0, st->a10 + sh + 3 * k0, st->a11 + sh + k0,
                               st->col + (s & 3) + k0, len, lane, gmask, x, x_poff, n_rows, y0, y1, y2, yp);
     }
     __syncwarp();
     if (lane32 == 0) tma::mbar_arrive(empty + stg);   // this warp is done reading the stage
-    if (live && lane == 0) spmv_store(y, y_poff, row, alpha, beta, y0, y1, y2, yp);
+    if (live && lane == 0) spmv_store<AOSY>(y, y_poff, row, alpha, beta, y0, y1, y2, yp);
   }
 }
 
@@ -436,47 +440,61 @@ static int spmv_group() { return options().spmv_g; }
 
 static bool spmv_tma_on() { return options().spmv_tma != 0; }   // 0 selects the register-staged kernel (A/B measurements)
 
-// rows [row0, row1)
+// rows [row0, row1).  layout: bit 0 = x interleaved per node (x[4 node + c]), bit 1 = y interleaved; 0 = the ABI layout.
+enum { LAY_ABI = 0, LAY_XAOS = 1, LAY_YAOS = 2 };
 int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, const f64* A00, const f64* A01, const f64* A10,
                 const f64* A11, f64 alpha, const f64* x, size_t x_poff, f64 beta, f64* y, size_t y_poff, cudaStream_t st,
-                const P2PView* pv = nullptr, unsigned long long hseq = 0, int n_interior = 0) {
+                int layout = LAY_ABI, const P2PView* pv = nullptr, unsigned long long hseq = 0, int n_interior = 0) {
   if (row1 <= row0) return DFB_OK;
   const i64 rows = row1 - row0;
-  if (!pv && spmv_tma_on() &&
+  if (pv && layout != (LAY_XAOS | LAY_YAOS)) { set_error("launch_spmv: the peer-memory mat-vec runs on interleaved vectors only"); return DFB_ERR_ARG; }
+  if (!pv && spmv_tma_on() && layout != LAY_YAOS &&
       (((uintptr_t)row_ptr | (uintptr_t)col_ind | (uintptr_t)A00 | (uintptr_t)A01 | (uintptr_t)A10 | (uintptr_t)A11) & 15u) == 0) {
     constexpr size_t smem = sizeof(SpmvStage) * TS_STAGES + 2 * TS_STAGES * sizeof(uint64_t);
     static bool attr_set = false;
     if (!attr_set) {
-      DFB_CUDA(cudaFuncSetAttribute(k_spmv_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      DFB_CUDA(cudaFuncSetAttribute(k_spmv_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      DFB_CUDA(cudaFuncSetAttribute(k_spmv_tma<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      DFB_CUDA(cudaFuncSetAttribute(k_spmv_tma<3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      DFB_CUDA(cudaFuncSetAttribute(k_spmv_tma<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      DFB_CUDA(cudaFuncSetAttribute(k_spmv_tma<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set = true;
     }
-    const int ntile = ceil_div(rows, TS_TR);
-    if (options().spmv_tma == 2)
-      k_spmv_tma<2><<<std::min(ntile, num_sms()), 32 * (TS_CWARPS * 2 + 1), smem, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11,
-                                                                                        alpha, x, x_poff, beta, y, y_poff);
-    else
-      k_spmv_tma<3><<<std::min(ntile, num_sms()), 32 * (TS_CWARPS * 3 + 1), smem, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11,
-                                                                                        alpha, x, x_poff, beta, y, y_poff);
+    const int ntile = ceil_div(rows, TS_TR), grid = std::min(ntile, num_sms());
+    const bool two = options().spmv_tma == 2;
+#define DFB_TMA(GR, AX, AY)                                                                                                        \
+  k_spmv_tma<GR, AX, AY><<<grid, 32 * (TS_CWARPS * GR + 1), smem, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x, \
+                                                                       x_poff, beta, y, y_poff)
+    if (layout == LAY_ABI) { if (two) DFB_TMA(2, false, false); else DFB_TMA(3, false, false); }
+    else { if (two) DFB_TMA(2, true, true); else DFB_TMA(3, true, true); }
+#undef DFB_TMA
     DFB_LAUNCH_CHECK();
     return DFB_OK;
   }
+  const int grid8 = ceil_div(rows * 8, 256);
+  if (pv) {
+    k_spmv_fs<8, true, true, true><<<grid8, 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x, x_poff, beta, y,
+                                                         y_poff, pv, hseq, n_interior);
+  } else if (layout == LAY_YAOS) {
+    k_spmv_fs<8, false, false, true><<<grid8, 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x, x_poff, beta, y,
+                                                           y_poff, nullptr, 0ull, 0);
+  } else if (layout == (LAY_XAOS | LAY_YAOS)) {
+    k_spmv_fs<8, false, true, true><<<grid8, 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x, x_poff, beta, y,
+                                                          y_poff, nullptr, 0ull, 0);
+  } else if (layout == LAY_ABI) {
 #define DFB_SPMV(G)                                                                                                              \
-  do {                                                                                                                           \
-    if (pv)                                                                                                                      \
-      k_spmv_fs<G, true><<<ceil_div(rows * G, 256), 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x,   \
-                                                                  x_poff, beta, y, y_poff, pv, hseq, n_interior);               \
-    else                                                                                                                         \
-      k_spmv_fs<G, false><<<ceil_div(rows * G, 256), 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x,  \
-                                                                   x_poff, beta, y, y_poff, nullptr, 0ull, 0);                  \
-  } while (0)
-  switch (spmv_group()) {
-    case 4: DFB_SPMV(4); break;
-    case 32: DFB_SPMV(32); break;
-    case 16: DFB_SPMV(16); break;
-    default: DFB_SPMV(8); break;
-  }
+  k_spmv_fs<G, false, false, false><<<ceil_div(rows * G, 256), 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11,   \
+                                                                             alpha, x, x_poff, beta, y, y_poff, nullptr, 0ull, 0)
+    switch (spmv_group()) {
+      case 4: DFB_SPMV(4); break;
+      case 32: DFB_SPMV(32); break;
+      case 16: DFB_SPMV(16); break;
+      default: DFB_SPMV(8); break;
+    }
 #undef DFB_SPMV
+  } else {
+    set_error("launch_spmv: unsupported layout %d", layout);
+    return DFB_ERR_ARG;
+  }
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
@@ -543,87 +561,54 @@ __global__ void k_pc_apply(int n, const f64* __restrict__ dinv00, const f64* __r
   for (size_t t = i; t < tail_n; t += n) y[y_toff + t] = x[x_toff + t];
 }
 
-// Fused normalisation + preconditioner (one pass instead of k_scale + k_pc_apply): q = w * (*scale) is written back over
-// w (compact layout) and z = P^-1 q is written in the local layout.
-__global__ void k_scale_pc_apply(int n, const f64* __restrict__ scale, const f64* __restrict__ dinv00,
-                                 const f64* __restrict__ dinv11, f64* __restrict__ w, size_t w_poff, f64* __restrict__ z,
-                                 size_t z_poff) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+// The solver's own copy of the preconditioner: one 96-byte record per node, laid out for the two lanes that share a node in
+// the update kernel (interleaved Krylov vectors: lane "half 0" holds (u0,u1) of the node, "half 1" holds (u2,p)):
+//   [0..5]  D0 D1 | D3 D4 | D6 D7     -> half 0 forms z0 = D0 x0 + D3 x1 + D6 x2,  z1 = D1 x0 + D4 x1 + D7 x2
+//   [6..11] D2 D5 | D8 d11 | 0 0      -> half 1 forms z2 = D2 x0 + D5 x1 + D8 x2,  zp = d11 xp
+// (D = dinv00[9 node ..], column-major (B^-1)^T of defect D3; d11 = dinv11[node]).
+constexpr int PCREC = 12;
+__global__ void k_pc_pack(int n, const f64* __restrict__ dinv00, const f64* __restrict__ dinv11, f64* __restrict__ rec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const f64 s = *scale;
   const f64* D = dinv00 + (size_t)i * 9;
-  f64* wu = w + (size_t)i * 3;
-  const f64 x0 = wu[0] * s, x1 = wu[1] * s, x2 = wu[2] * s, xp = w[w_poff + i] * s;
-  wu[0] = x0; wu[1] = x1; wu[2] = x2; w[w_poff + i] = xp;
-  f64* zu = z + (size_t)i * 3;
-  zu[0] = D[0] * x0 + D[3] * x1 + D[6] * x2;
-  zu[1] = D[1] * x0 + D[4] * x1 + D[7] * x2;
-  zu[2] = D[2] * x0 + D[5] * x1 + D[8] * x2;
-  z[z_poff + i] = xp * dinv11[i];
+  f64* r = rec + (size_t)i * PCREC;
+  r[0] = D[0]; r[1] = D[1]; r[2] = D[3]; r[3] = D[4]; r[4] = D[6]; r[5] = D[7];
+  r[6] = D[2]; r[7] = D[5]; r[8] = D[8]; r[9] = dinv11[i]; r[10] = 0.0; r[11] = 0.0;
 }
 
-// Peer-memory variant of the kernel above, with both neighbouring collectives fused in:
-//   prologue (seq != 0): every block waits for all ranks' partial ||w||^2 of the previous Arnoldi step (stored into OUR
-//     mailbox by their k_update), sums them in rank order and forms 1/||w||; block 0 also runs the scalar Givens step;
-//   epilogue: boundary-owned nodes store their (u,p) of z straight into the ghost slots of the neighbours' z; the last
-//     block to finish raises this mat-vec's halo flag on every neighbour.
-__global__ void __launch_bounds__(128) k_scale_pc_apply_peer(int n, const f64* __restrict__ dinv00, const f64* __restrict__ dinv11,
-                                                             f64* __restrict__ w, size_t w_poff, f64* __restrict__ z, size_t z_poff,
-                                                             const P2PView* __restrict__ pv, unsigned long long seq,
-                                                             unsigned long long hseq, int it_prev, GmresScalars* S, f64* hcol_prev,
-                                                             f64* gv, f64* beta, f64* tailc, f64* res_hist) {
-  __shared__ f64 s_scale;
-  __shared__ bool is_last;
-  __shared__ f64 s_part[P2P_MAXR];
-  if (seq) {
-    const int R = pv->nranks, par = (int)(seq & 1ull);
-    if ((int)threadIdx.x < R) s_part[threadIdx.x] = ll_load(pv, pv->mbox_local + p2p_b_ll(R, par, threadIdx.x), (unsigned)seq);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      f64 nrm2 = 0.0;
-      for (int r = 0; r < R; r++) nrm2 += s_part[r];
-      const f64 cw = S->cw;
-      s_scale = 1.0 / sqrt(nrm2 + cw * cw * S->tail2);
-      if (blockIdx.x == 0) {
-        S->nrm2_live = nrm2;
-        gmres_step_dev(it_prev, S, hcol_prev, gv, beta, tailc, res_hist);
-      }
-    }
-  } else if (threadIdx.x == 0) {
-    s_scale = S->inv_norm;
+// one half (two of the four entries) of z = P^-1 x for one node; x0 x1 x2 xp = the node's entries
+__device__ __forceinline__ double2 pc_half(const f64* __restrict__ rec, int half, f64 x0, f64 x1, f64 x2, f64 xp) {
+  const double2* r2 = reinterpret_cast<const double2*>(rec) + 3 * half;
+  const double2 a = __ldg(r2), b = __ldg(r2 + 1);
+  if (half == 0) {
+    const double2 c = __ldg(r2 + 2);
+    return make_double2(a.x * x0 + b.x * x1 + c.x * x2, a.y * x0 + b.y * x1 + c.y * x2);
   }
-  __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const f64 s = s_scale;
-    const f64* D = dinv00 + (size_t)i * 9;
-    f64* wu = w + (size_t)i * 3;
-    const f64 x0 = wu[0] * s, x1 = wu[1] * s, x2 = wu[2] * s, xp = w[w_poff + i] * s;
-    wu[0] = x0; wu[1] = x1; wu[2] = x2; w[w_poff + i] = xp;
-    const f64 z0 = D[0] * x0 + D[3] * x1 + D[6] * x2, z1 = D[1] * x0 + D[4] * x1 + D[7] * x2, z2 = D[2] * x0 + D[5] * x1 + D[8] * x2;
-    const f64 zp = xp * dinv11[i];
-    f64* zu = z + (size_t)i * 3;
-    zu[0] = z0; zu[1] = z1; zu[2] = z2;
-    z[z_poff + i] = zp;
-    const int b = i - pv->tgt_base;
-    if (b >= 0 && b < pv->tgt_n) {
-      for (int t = pv->tgt_ptr[b]; t < pv->tgt_ptr[b + 1]; t++) {
-        const int q = pv->tgt_q[t], rid = pv->tgt_rid[t];
-        f64* zr = pv->z_peer[pv->nbr[q]];
-        zr[(size_t)rid * 3] = z0; zr[(size_t)rid * 3 + 1] = z1; zr[(size_t)rid * 3 + 2] = z2;
-        zr[pv->nbr_poff[q] + rid] = zp;
-      }
-      __threadfence_system();
-    }
+  return make_double2(a.x * x0 + a.y * x1 + b.x * x2, xp * b.y);
+}
+
+// halo push of one half node record into the neighbours' z (peer-memory mode): node i is boundary-owned
+__device__ __forceinline__ void push_half(const P2PView* __restrict__ pv, int i, int half, double2 v) {
+  const int b = i - pv->tgt_base;
+  if (b < 0 || b >= pv->tgt_n) return;
+  for (int t = pv->tgt_ptr[b]; t < pv->tgt_ptr[b + 1]; t++) {
+    f64* zr = pv->z_peer[pv->nbr[pv->tgt_q[t]]];
+    *reinterpret_cast<double2*>(zr + (size_t)pv->tgt_rid[t] * 4 + 2 * half) = v;
   }
+  __threadfence_system();
+}
+
+// raise this mat-vec's halo flag on every neighbour once the whole grid has pushed (last-block election on pv->push_ctr)
+__device__ __forceinline__ void push_flag(const P2PView* __restrict__ pv, unsigned long long hseq) {
+  __shared__ bool push_last;
   if (pv->n_nbr == 0) return;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    is_last = atomicAdd(pv->push_ctr, 1u) == gridDim.x - 1;
+    push_last = atomicAdd(pv->push_ctr, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (!is_last) return;
+  if (!push_last) return;
   if (threadIdx.x == 0) *pv->push_ctr = 0u;
   if ((int)threadIdx.x < pv->n_nbr) {
     __threadfence_system();
@@ -631,9 +616,47 @@ __global__ void __launch_bounds__(128) k_scale_pc_apply_peer(int n, const f64* _
   }
 }
 
+// z (interleaved, local numbering) = P^-1 w (interleaved, owned nodes): the first basis vector of a solve (every later one
+// leaves the update kernel already preconditioned).  One thread per half node.  pv != NULL: + halo push and flag.
+__global__ void __launch_bounds__(256) k_pc_apply_aos(int n, const f64* __restrict__ rec, const f64* __restrict__ w, f64* __restrict__ z,
+                                                      const P2PView* __restrict__ pv, unsigned long long hseq) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(t >> 1), half = (int)(t & 1);
+  if (i < n) {
+    const double2* w2 = reinterpret_cast<const double2*>(w) + (size_t)i * 2;
+    const double2 lo = w2[0], hi = w2[1];
+    const double2 v = pc_half(rec + (size_t)i * PCREC, half, lo.x, lo.y, hi.x, hi.y);
+    reinterpret_cast<double2*>(z)[t] = v;
+    if (pv) push_half(pv, i, half, v);
+  }
+  if (pv) push_flag(pv, hseq);
+}
+
+// x (ABI layout, 6N) += P^-1 t (interleaved, owned nodes)   (krylov.c:313-319: the preconditioner on the combination)
+__global__ void k_pc_add_live(int n, const f64* __restrict__ rec, const f64* __restrict__ t, f64* __restrict__ x, size_t poff) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double2* t2 = reinterpret_cast<const double2*>(t) + (size_t)i * 2;
+  const double2 lo = t2[0], hi = t2[1];
+  const double2 a = pc_half(rec + (size_t)i * PCREC, 0, lo.x, lo.y, hi.x, hi.y);
+  const double2 b = pc_half(rec + (size_t)i * PCREC, 1, lo.x, lo.y, hi.x, hi.y);
+  f64* xu = x + (size_t)i * 3;
+  xu[0] += a.x; xu[1] += a.y; xu[2] += b.x;
+  x[poff + i] += b.y;
+}
+
 // ------------------------------------------------------------------------------------------------------------
-// Krylov vector kernels.  A "live" vector has nl = 4*n_own entries stored compactly: u of the owned nodes
-// [0, 3 n_own) followed by p [3 n_own, 4 n_own).
+// Krylov vector kernels.  A "live" vector has nl = 4*n_own entries, INTERLEAVED per node: v[4 i + c], c = 0..2 velocity,
+// c = 3 pressure (whole nodes stay together, so the block-Jacobi preconditioner can be applied where a vector is produced).
+//
+// The basis is stored UNNORMALISED: column j holds w~_j with v_j = s_j w~_j, s_j = 1/||w~_j|| kept on the device (qs[]).  One
+// Arnoldi step is then three kernels instead of four, and no kernel waits for a norm that was only just reduced:
+//   mat-vec   w_raw = A z~_j                       z~_j = P^-1 w~_j left behind by the previous update (j = 0: k_pc_apply_aos)
+//   multi-dot d_i = w~_i . w_raw, i <= j           raw partial sums; nothing scalar is needed
+//   update    h_i = s_i s_j d_i;  w~_{j+1} = s_j w_raw - sum_i (h_i s_i) w~_i;  ||w~_{j+1}||^2;  z~_{j+1} = P^-1 w~_{j+1}
+// The scale s_j (the norm reduced at the end of the PREVIOUS update) is first needed in the update's prologue, a mat-vec and a
+// multi-dot later: on several GPUs its all-reduce is off the critical path, and the halo of z~ leaves from the update's epilogue.
+// In exact arithmetic this is the reference's recurrence (krylov.c:140-290); the roundings differ at the 1e-16 level.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int NCHUNK = 296;    // 2 x 148 SMs: row chunks (partial-sum slots) of the multi-dot and the plain reductions
 constexpr int UCHUNK = 9472;   // 64 x 148 SMs: most blocks of the update kernel (one partial sum each)
@@ -703,7 +726,8 @@ __device__ __forceinline__ void md_accum(const double2* __restrict__ q2, const d
   }
 }
 
-// h[j] = sum_i Q[i, j] * w[i],  j in [0, ncol): stage 1 = per-(chunk, column) partials, stage 2 by the last block.
+// d[j] = sum_i Q[i, j] * w[i],  j in [0, ncol) (raw dots of the unnormalised columns): stage 1 = per-(chunk, column) partials,
+// stage 2 by the last block.
 // The columns are dealt EVENLY to the gridDim.y column groups (at most JT each: 20 columns -> 7 + 7 + 6, not 8 + 8 + 4), so
 // that every block of the single resident wave streams the same number of bytes.  nl is a multiple of 4 and every column
 // starts 32-byte aligned.
@@ -771,53 +795,90 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
   if (threadIdx.x == 0) *ctr = 0u;
 }
 
-// w[i] -= sum_j Q[i,j] h[j], fused with the sum of squares of the new w (stage 2 by the last block -> *nrm2).
-// With do_step the last block also runs the scalar Arnoldi/Givens step (single GPU: no cross-rank sum needed).
-// One resident wave of blocks (4 per SM) strides over 16-byte row pairs; a thread keeps 8 independent 16-byte loads in
-// flight.  (USPLIT > 1 splits the columns of a row pair over lane groups; measured slower, kept as a compile-time knob.)
+// The update of one Arnoldi step (see the header above): w~_{j+1} = s_j w_raw - sum_i (h_i s_i) w~_i with h_i = s_i s_j d_i,
+// fused with (a) the sum of squares of the new vector (stage 2 by the last block), (b) z~_{j+1} = P^-1 w~_{j+1}: a node's four
+// entries sit in two adjacent lanes, which swap their halves with one shuffle each and write z with coalesced 16-byte stores,
+// (c) mode 0 (one GPU): the scalar Arnoldi/Givens step in the last block, (d) mode 2 (peer memory): the all-reduce of the raw
+// dots and of the PREVIOUS step's norm in the prologue (block 0 also runs that step's Givens update), the halo push of z~ in
+// the epilogue and the publication of this step's partial norm by the last block.
+// One resident wave of blocks (4 per SM) strides over 16-byte row pairs; a thread keeps 8 independent 16-byte loads in flight.
 #ifndef UPDATE_REVERSE
 #define UPDATE_REVERSE 1
 #endif
 #ifndef UPDATE_LD
 #define UPDATE_LD __ldcs
 #endif
-constexpr int USPLIT = 1;   // measured on B200 (m=55): 1 -> 27 us average per launch, 4 -> 37 us
-__global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict__ Q, size_t ldq, int ncol, f64* h,
-                                                f64* __restrict__ w, f64* part, f64* nrm2, unsigned* ctr, int do_step,
-                                                GmresScalars* S, f64* gv, f64* beta, f64* tailc, f64* res_hist,
-                                                const P2PView* __restrict__ pv, unsigned long long seq) {
-  constexpr int PW = 32 / USPLIT;  // row pairs per warp
-  __shared__ f64 sh[128];
+struct UpdateScalars {   // device arrays of the recurrence (all persistent in the workspace)
+  GmresScalars* S;
+  f64 *qs, *gv, *beta, *tailc, *res_hist;
+};
+__global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict__ Q, size_t ldq, int ncol, const f64* __restrict__ draw,
+                                                f64* hcol, f64* hcol_prev, f64* __restrict__ w, f64* part, unsigned* ctr, int mode,
+                                                UpdateScalars U, const f64* __restrict__ pcrec, f64* __restrict__ z,
+                                                const P2PView* __restrict__ pv, unsigned long long seq, unsigned long long seq_prev,
+                                                unsigned long long hseq) {
+  __shared__ f64 sh[128];    // c_i = h_i s_i: coefficient of the stored (unnormalised) column i
+  __shared__ f64 shh[128];   // h_i: the Hessenberg column
   __shared__ f64 sm[8];
-  if (pv) {   // fused all-reduce of h: wait for every rank's partial (stored into OUR mailbox), sum in rank order
-    const int R = pv->nranks, par = (int)(seq & 1ull);
-    for (int j = threadIdx.x; j < ncol; j += 256) {
-      f64 s = 0.0;
-      for (int r = 0; r < R; r++) s += ll_load(pv, pv->mbox_local + p2p_a_ll(R, par, r, j), (unsigned)seq);
-      sh[j] = s;
-      if (blockIdx.x == 0) h[j] = s;
+  __shared__ f64 s_sj, s_tcj;
+  const int jc = ncol - 1;   // index of the newest column w~_j (the one A z~ was formed from)
+  if (threadIdx.x == 0) {
+    f64 sj = U.qs[jc], tcj = U.tailc[jc];
+    if (pv && seq_prev) {   // the norm of w~_j is still in the mailbox: sum the ranks' partials in rank order
+      const int R = pv->nranks, par = (int)(seq_prev & 1ull);
+      f64 nrm2 = 0.0;
+      for (int r = 0; r < R; r++) nrm2 += ll_load(pv, pv->mbox_local + p2p_b_ll(R, par, r), (unsigned)seq_prev);
+      const f64 cw = U.S->cw;
+      sj = 1.0 / sqrt(nrm2 + cw * cw * U.S->tail2);   // same expressions as gmres_step_dev: identical on every block and rank
+      tcj = cw * sj;
+      if (blockIdx.x == 0) {
+        U.S->nrm2_live = nrm2;
+        gmres_step_dev(jc - 1, U.S, hcol_prev, U.gv, U.beta, U.tailc, U.res_hist, U.qs);
+      }
     }
-  } else {
-    for (int j = threadIdx.x; j < ncol; j += 256) sh[j] = h[j];
+    s_sj = sj;
+    s_tcj = tcj;
   }
   __syncthreads();
+  {
+    const f64 sj = s_sj;
+    for (int i = threadIdx.x; i < ncol; i += 256) {
+      f64 d;
+      if (pv) {   // fused all-reduce of the raw dots: every rank's partial was stored into OUR mailbox, summed in rank order
+        const int R = pv->nranks, par = (int)(seq & 1ull);
+        d = 0.0;
+        for (int r = 0; r < R; r++) d += ll_load(pv, pv->mbox_local + p2p_a_ll(R, par, r, i), (unsigned)seq);
+      } else {
+        d = draw[i];
+      }
+      const f64 si = i == jc ? sj : U.qs[i];
+      const f64 h = si * sj * d;
+      shh[i] = h;
+      sh[i] = h * si;
+      if (pv && blockIdx.x == 0) hcol[i] = h;   // the next kernel's Givens step reads the column from global memory
+    }
+  }
+  __syncthreads();
+  const f64 sj = s_sj;
   const double2* q2 = reinterpret_cast<const double2*>(Q);
   double2* w2 = reinterpret_cast<double2*>(w);
-  const size_t np = nl >> 1, ld2 = ldq >> 1;
-  const int lane = threadIdx.x & 31, sub = lane / PW, pl = lane % PW;
+  double2* z2 = reinterpret_cast<double2*>(z);
+  const size_t np = nl >> 1, ld2 = ldq >> 1;   // np = 2 n_own: even, so the two halves of a node are always both in range
+  const int lane = threadIdx.x & 31;
   const size_t warp0 = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5, nwarp = ((size_t)gridDim.x * 256) >> 5;
   f64 ss = 0.0;
   // The multi-dot has just swept the rows in ASCENDING order, so the highest rows of every column are what the 126 MB L2
   // still holds: sweep DESCENDING here (and leave the lowest rows behind for the next multi-dot's ascending sweep).
   const bool reverse = UPDATE_REVERSE;
-  for (size_t base = warp0 * PW; base < np; base += nwarp * PW) {   // warp-uniform trip count
-    const size_t ib = base + pl;
+  for (size_t base = warp0 * 32; base < np; base += nwarp * 32) {   // warp-uniform trip count
+    const size_t ib = base + lane;
     const bool ok = ib < np;
-    const size_t i = reverse ? (np - 1 - (ok ? ib : 0)) : ib;
+    const size_t i = reverse ? (np - 1 - (ok ? ib : 0)) : (ok ? ib : 0);
     f64 ax[2] = {0.0, 0.0}, ay[2] = {0.0, 0.0};
+    double2 wn = make_double2(0.0, 0.0);
     if (ok) {
       const double2* qi = q2 + i;
-      for (int j = sub * 8; j < ncol; j += 8 * USPLIT) {
+      for (int j = 0; j < ncol; j += 8) {
         if (j + 8 <= ncol) {
           double2 v[8];
 #pragma unroll
@@ -835,39 +896,44 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
           }
         }
       }
-    }
-    f64 sx = ax[0] + ax[1], sy = ay[0] + ay[1];
-#pragma unroll
-    for (int o = PW; o < 32; o <<= 1) {
-      sx += __shfl_xor_sync(FULLM, sx, o);
-      sy += __shfl_xor_sync(FULLM, sy, o);
-    }
-    if (ok && sub == 0) {
-      double2 wn = w2[i];
-      wn.x -= sx;
-      wn.y -= sy;
+      wn = w2[i];
+      wn.x = sj * wn.x - (ax[0] + ax[1]);
+      wn.y = sj * wn.y - (ay[0] + ay[1]);
       w2[i] = wn;
       ss = fma(wn.y, wn.y, fma(wn.x, wn.x, ss));
     }
+    // z~ = P^-1 w~ for the node this lane shares with its neighbour lane (pair index i: node i >> 1, half i & 1)
+    const f64 ox = __shfl_xor_sync(FULLM, wn.x, 1), oy = __shfl_xor_sync(FULLM, wn.y, 1);
+    if (ok) {
+      const int half = (int)(i & 1), node = (int)(i >> 1);
+      const double2 v = half == 0 ? pc_half(pcrec + (size_t)node * PCREC, 0, wn.x, wn.y, ox, oy)
+                                  : pc_half(pcrec + (size_t)node * PCREC, 1, ox, oy, wn.x, wn.y);
+      z2[i] = v;
+      if (pv) push_half(pv, node, half, v);
+    }
   }
+  if (pv) push_flag(pv, hseq);
   f64 r = block_sum_256(ss, sm);
   if (threadIdx.x == 0) part[blockIdx.x] = r;
   if (!last_block(ctr, gridDim.x)) return;
   f64 s = 0.0;
   for (int c = threadIdx.x; c < (int)gridDim.x; c += 256) s += __ldcg(part + c);
   s = block_sum_256(s, sm);
+  if (!pv)
+    for (int i = threadIdx.x; i < ncol; i += 256) hcol[i] = shh[i];
+  __syncthreads();
   if (threadIdx.x == 0) {
     *ctr = 0u;
-    if (pv) {   // publish the partial sum of squares; the next kernel (scale+PC or the step kernel) sums the ranks
+    if (pv) {   // publish the partial sum of squares; the next update (or the step kernel) sums the ranks
       const int R = pv->nranks, par = (int)(seq & 1ull);
       f64 cw = 0.0;
-      for (int j = 0; j < ncol; j++) cw -= sh[j] * tailc[j];   // same expression and order as gmres_step_dev
-      S->cw = cw;
+      for (int i = 0; i < ncol; i++) cw -= shh[i] * (i == jc ? s_tcj : U.tailc[i]);   // same expression and order as gmres_step_dev
+      U.S->cw = cw;
       __threadfence();   // S->cw before the norm becomes visible anywhere
-      for (int r = 0; r < R; r++) ll_store(pv->mbox_peer[r] + p2p_b_ll(R, par, pv->rank), s, (unsigned)seq);
+      for (int rr = 0; rr < R; rr++) ll_store(pv->mbox_peer[rr] + p2p_b_ll(R, par, pv->rank), s, (unsigned)seq);
     } else {
-      *nrm2 = s;
-      if (do_step) gmres_step_dev(ncol - 1, S, h, gv, beta, tailc, res_hist);
+      U.S->nrm2_live = s;
+      if (mode == 0) gmres_step_dev(jc, U.S, hcol, U.gv, U.beta, U.tailc, U.res_hist, U.qs);
     }
   }
 }
@@ -909,26 +975,13 @@ __global__ void __launch_bounds__(256) k_sumsq(size_t n, const f64* __restrict__
   if (threadIdx.x == 0) part[blockIdx.x] = r;
 }
 
-// v *= *scale
-__global__ void k_scale(size_t n, f64* __restrict__ v, const f64* __restrict__ scale) {
-  const f64 s = *scale;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) v[i] *= s;
-}
-
-// gather the compact live part out of a 6N-layout vector (u at [0,3n_own), p at [poff, poff+n_own))
+// gather the live part of an ABI-layout vector (u at v[3i + c], p at v[poff + i]) into the interleaved layout out[4i + c]
 __global__ void k_pack_live(int n_own, const f64* __restrict__ v, size_t poff, f64* __restrict__ out) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t nu = (size_t)3 * n_own;
-  if (i < nu) out[i] = v[i];
-  else if (i < nu + n_own) out[i] = v[poff + (i - nu)];
-}
-
-// x(6N layout) += d(compact live)
-__global__ void k_add_live(int n_own, const f64* __restrict__ d, f64* __restrict__ x, size_t poff) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t nu = (size_t)3 * n_own;
-  if (i < nu) x[i] += d[i];
-  else if (i < nu + n_own) x[poff + (i - nu)] += d[i];
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)4 * n_own) return;
+  const size_t i = t >> 2;
+  const int c = (int)(t & 3);
+  out[t] = c < 3 ? v[i * 3 + c] : v[poff + i];
 }
 
 // x_tail += coef * b_tail
@@ -968,18 +1021,19 @@ __global__ void k_final_sum(const f64* __restrict__ part, f64* __restrict__ out)
 }
 
 // start of a solve: beta[0] = ||r0|| including the dead tail; tailc[0] = 1/beta0; inv_norm = 1/beta0
-__global__ void k_gmres_begin(GmresScalars* S, f64* beta, f64* tailc, f64* res_hist) {
+__global__ void k_gmres_begin(GmresScalars* S, f64* beta, f64* tailc, f64* res_hist, f64* qs) {
   const f64 n0 = sqrt(S->nrm2_live + S->tail2);
   S->rnrm_init = n0;
   beta[0] = n0;
   res_hist[0] = n0;
   S->inv_norm = 1.0 / n0;
+  qs[0] = 1.0 / n0;
   tailc[0] = 1.0 / n0;
 }
 
 // one Arnoldi step's scalar work (krylov.c:229-277 + krylov_util.cu:5-19) for column `it`:
 //   hcol[0..it] holds h = Q^T w (already reduced), S->nrm2_live the sum of squares of the updated live w.
-__device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist) {
+__device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist, f64* qs) {
   // dead tail: every basis vector's rows [4N,6N) equal tailc[j] * b_tail (D4): w_tail = -sum_j h_j tailc[j] b_tail
   f64 cw = 0.0;
   for (int j = 0; j <= it; j++) cw -= hcol[j] * tailc[j];
@@ -987,6 +1041,7 @@ __device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64*
   hcol[it + 1] = nrm;
   const f64 inv = 1.0 / nrm;
   S->inv_norm = inv;
+  qs[it + 1] = inv;             // scale of the (unnormalised) column it + 1
   tailc[it + 1] = cw * inv;
   f64 xx = hcol[0];
   for (int i = 0; i < it; i++) {  // cublasDrot, n = 1 (krylov.c:258-263); the running entry stays in a register so that
@@ -1006,12 +1061,12 @@ __device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64*
   res_hist[it + 1] = fabs(beta[it + 1]);
 }
 
-__global__ void k_gmres_step(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist) {
-  gmres_step_dev(it, S, hcol, gv, beta, tailc, res_hist);
+__global__ void k_gmres_step(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist, f64* qs) {
+  gmres_step_dev(it, S, hcol, gv, beta, tailc, res_hist, qs);
 }
 
 // peer-memory mode: fused all-reduce of ||w||^2 (rank order) + the scalar Arnoldi/Givens step; one warp
-__global__ void k_gmres_step_peer(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist,
+__global__ void k_gmres_step_peer(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist, f64* qs,
                                   const P2PView* __restrict__ pv, unsigned long long seq) {
   const int R = pv->nranks, par = (int)(seq & 1ull);
   __shared__ f64 s_part[P2P_MAXR];
@@ -1021,7 +1076,7 @@ __global__ void k_gmres_step_peer(int it, GmresScalars* S, f64* hcol, f64* gv, f
     f64 s = 0.0;
     for (int r = 0; r < R; r++) s += s_part[r];
     S->nrm2_live = s;
-    gmres_step_dev(it, S, hcol, gv, beta, tailc, res_hist);
+    gmres_step_dev(it, S, hcol, gv, beta, tailc, res_hist, qs);
   }
 }
 
@@ -1029,7 +1084,7 @@ __global__ void k_gmres_step_peer(int it, GmresScalars* S, f64* hcol, f64* gv, f
 // One block of 128 threads (m <= 127): H is staged in shared memory, thread i owns the right-hand side entry i, the
 // column-oriented sweep needs one broadcast + one FMA per unknown instead of a serial O(m^2) chain of dependent loads.
 __global__ void __launch_bounds__(128) k_gmres_trsv(int m, const f64* __restrict__ H, int ldh, f64* beta, const f64* tailc,
-                                                    f64* tail_coef) {
+                                                    f64* tail_coef, const f64* __restrict__ qs, f64* __restrict__ ycoef) {
   extern __shared__ f64 hs[];   // [m][m] column-major copy of the triangle
   __shared__ f64 ycur;
   __shared__ f64 red[4];
@@ -1046,7 +1101,10 @@ __global__ void __launch_bounds__(128) k_gmres_trsv(int m, const f64* __restrict
     if (i < j) b -= hs[j * m + i] * ycur;
     __syncthreads();
   }
-  if (i < m) beta[i] = b;
+  if (i < m) {
+    beta[i] = b;
+    ycoef[i] = b * qs[i];   // coefficient of the stored (unnormalised) column i in the solution combination
+  }
   f64 tc = i < m ? tailc[i] * b : 0.0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tc += __shfl_xor_sync(FULLM, tc, o);
@@ -1064,6 +1122,7 @@ struct dfb_gmres {
   int n_own = 0;  // rows reduced in the inner products (== N on a single GPU)
   f64 *Q = nullptr, *H = nullptr, *gv = nullptr, *beta = nullptr, *tailc = nullptr, *res_hist = nullptr;
   f64 *z = nullptr, *t = nullptr, *part = nullptr, *dinv00 = nullptr, *dinv11 = nullptr, *tail_coef = nullptr;
+  f64 *qs = nullptr, *draw = nullptr, *ycoef = nullptr, *pcrec = nullptr;   // column scales, raw dots, combination coefficients, packed P^-1
   GmresScalars* S = nullptr;
   unsigned* ctr = nullptr;  // [2] last-block election counters (multi-dot, update)
   size_t bytes = 0;
@@ -1108,7 +1167,9 @@ int dfb_gmres_create(dfb_gmres** out, int N, int maxit) {
       {&w->Q, nl * ((size_t)maxit + 1)}, {&w->H, (size_t)w->ldh * maxit}, {&w->gv, (size_t)2 * maxit},
       {&w->beta, (size_t)maxit + 1},    {&w->tailc, (size_t)maxit + 1},  {&w->res_hist, (size_t)maxit + 1},
       {&w->z, (size_t)6 * N},           {&w->t, (size_t)6 * N},          {&w->part, (size_t)NCHUNK * (maxit + 2) + UCHUNK},
-      {&w->dinv00, (size_t)9 * N},      {&w->dinv11, (size_t)N},         {&w->tail_coef, 8}};
+      {&w->dinv00, (size_t)9 * N},      {&w->dinv11, (size_t)N},         {&w->tail_coef, 8},
+      {&w->qs, (size_t)maxit + 2},      {&w->draw, (size_t)maxit + 2},   {&w->ycoef, (size_t)maxit + 2},
+      {&w->pcrec, (size_t)PCREC * N}};
   for (auto& a : allocs) {
     if (cudaMalloc(a.p, a.n * sizeof(f64)) != cudaSuccess) {
       set_error("dfb_gmres_create: cudaMalloc of %zu bytes failed", a.n * sizeof(f64));
@@ -1130,6 +1191,7 @@ void dfb_gmres_destroy(dfb_gmres* w) {
   if (!w) return;
   cudaFree(w->Q); cudaFree(w->H); cudaFree(w->gv); cudaFree(w->beta); cudaFree(w->tailc); cudaFree(w->res_hist);
   cudaFree(w->z); cudaFree(w->t); cudaFree(w->part); cudaFree(w->dinv00); cudaFree(w->dinv11); cudaFree(w->tail_coef);
+  cudaFree(w->qs); cudaFree(w->draw); cudaFree(w->ycoef); cudaFree(w->pcrec);
   cudaFree(w->S); cudaFree(w->ctr);
   delete w;
 }
@@ -1169,7 +1231,6 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   const size_t nl = (size_t)4 * n_own;          // compact live length
   const size_t ldq = nl;
   const size_t poffN = (size_t)3 * N;           // p offset in the 6N / local layout
-  const size_t poffC = (size_t)3 * n_own;       // p offset in the compact layout
   const size_t tail_n = (size_t)2 * N;
   f64* Q = W->Q;
 #define QCOL(c) (Q + (size_t)(c)*ldq)
@@ -1177,23 +1238,12 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   const int vgrid = ceil_div((i64)nl, 256);
   const int mgrid = std::min(NCHUNK, ceil_div((i64)(nl / 2), 256));   // row chunks of the multi-dot
   // update kernel: one resident wave (4 blocks per SM; measured 27.4 us vs 30.4 us for one row pair per thread)
-  const int ugrid = std::min(std::min(UCHUNK, 4 * num_sms()), ceil_div((i64)(nl / 2) * USPLIT, 256));
+  const int ugrid = std::min(std::min(UCHUNK, 4 * num_sms()), ceil_div((i64)(nl / 2), 256));
   const int cgrid = std::min(1184, ceil_div((i64)(nl / 2), 256));              // blocks of the combine kernel
-  // y(compact) = beta*y + alpha * A x(local layout): interior rows overlap the ghost exchange of x
   const P2PHandle* ph = W->parallel ? static_cast<const P2PHandle*>(W->par.p2p) : nullptr;
   const P2PView* pv = ph ? ph->dev : nullptr;
-  f64* const zvec = ph ? ph->host.z_local : W->z;   // peer-memory mode: z lives in the IPC-shared region
-  auto matvec = [&](f64 alpha, f64* x, f64 beta, f64* y) -> int {
-    if (W->parallel) {
-      DFB_CHECK(W->par.halo_begin(x, st, W->par.user));
-      DFB_CHECK(launch_spmv(0, W->n_interior, rp, ci, A00, A01, A10, A11, alpha, x, poffN, beta, y, poffC, st));
-      DFB_CHECK(W->par.halo_end(x, st, W->par.user));
-      DFB_CHECK(launch_spmv(W->n_interior, n_own, rp, ci, A00, A01, A10, A11, alpha, x, poffN, beta, y, poffC, st));
-    } else {
-      DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, alpha, x, poffN, beta, y, poffC, st));
-    }
-    return DFB_OK;
-  };
+  f64* const zvec = ph ? ph->host.z_local : W->z;   // peer-memory mode: z lives in the IPC-shared region (interleaved, 4 N_local)
+  if (W->parallel && !pv && !W->par.halo_begin_aos) { set_error("dfb_gmres_solve: the NCCL path needs dfb_parallel_ops.halo_begin_aos"); return DFB_ERR_ARG; }
   if ((!ext_dinv00) != (!ext_dinv11)) { set_error("dfb_gmres_solve_pc: pass both preconditioner arrays or neither"); return DFB_ERR_ARG; }
   const f64 *dinv00 = W->dinv00, *dinv11 = W->dinv11;
   if (ext_dinv00) {  // the caller has run PCSetup already (drop-in layer: the PC tree owns the arrays)
@@ -1202,11 +1252,20 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     k_pc_setup<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, rp, ci, A00, A11, W->dinv00, W->dinv11);
     DFB_LAUNCH_CHECK();
   }
+  k_pc_pack<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, dinv00, dinv11, W->pcrec);
+  DFB_LAUNCH_CHECK();
   DFB_CUDA(cudaMemsetAsync(W->H, 0, sizeof(f64) * (size_t)ldh * maxit, st));
-  // r0 = b - A x  (krylov.c:114-118)
+  // r0 = b - A x  (krylov.c:114-118): x in the ABI layout (its ghosts refreshed by the callbacks), r0 interleaved
   k_pack_live<<<vgrid, 256, 0, st>>>(n_own, d_b, poffN, QCOL(0));
   DFB_LAUNCH_CHECK();
-  DFB_CHECK(matvec(-1.0, d_x, 1.0, QCOL(0)));
+  if (W->parallel) {
+    DFB_CHECK(W->par.halo_begin(d_x, st, W->par.user));
+    DFB_CHECK(launch_spmv(0, W->n_interior, rp, ci, A00, A01, A10, A11, -1.0, d_x, poffN, 1.0, QCOL(0), 0, st, LAY_YAOS));
+    DFB_CHECK(W->par.halo_end(d_x, st, W->par.user));
+    DFB_CHECK(launch_spmv(W->n_interior, n_own, rp, ci, A00, A01, A10, A11, -1.0, d_x, poffN, 1.0, QCOL(0), 0, st, LAY_YAOS));
+  } else {
+    DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, -1.0, d_x, poffN, 1.0, QCOL(0), 0, st, LAY_YAOS));
+  }
   k_sumsq<<<NCHUNK, 256, 0, st>>>(nl, QCOL(0), W->part);
   DFB_LAUNCH_CHECK();
   k_final_sum<<<1, 32, 0, st>>>(W->part, &W->S->nrm2_live);
@@ -1219,9 +1278,13 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   k_final_sum<<<1, 32, 0, st>>>(W->part + NCHUNK, &W->S->tail2);
   DFB_LAUNCH_CHECK();
   if (W->parallel) DFB_CHECK(W->par.allreduce(&W->S->nrm2_live, 2, st, W->par.user));
-  k_gmres_begin<<<1, 1, 0, st>>>(W->S, W->beta, W->tailc, W->res_hist);
+  k_gmres_begin<<<1, 1, 0, st>>>(W->S, W->beta, W->tailc, W->res_hist, W->qs);
   DFB_LAUNCH_CHECK();
   DFB_CUDA(cudaMemsetAsync(W->ctr, 0, 2 * sizeof(unsigned), st));
+  // z~_0 = P^-1 r0 (+ its halo); every later z~ leaves the update kernel
+  unsigned long long hseq = ph ? ++*ph->hseq : 0ull;
+  k_pc_apply_aos<<<ceil_div((i64)2 * n_own, 256), 256, 0, st>>>(n_own, W->pcrec, QCOL(0), zvec, pv, hseq);
+  DFB_LAUNCH_CHECK();
 
   int iter = 0;
   bool converged = false;
@@ -1229,61 +1292,54 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   f64 rnrm_init = 0.0;
   std::vector<f64> hist((size_t)maxit + 1, 0.0);
   SolveProfiler prof;
+  const UpdateScalars US = {W->S, W->qs, W->gv, W->beta, W->tailc, W->res_hist};
   unsigned long long pending_seq = 0;   // peer-memory mode: norm reduction + Givens step of the previous iteration still to run
   while (!converged && iter < maxit) {
-    // q_iter = w / ||w|| written back in place, z = P^-1 q_iter (local layout); then w = A z
+    // w_raw = A z~_iter into column iter + 1 (no scaling: the update applies s_iter)
     f64* w = QCOL(iter + 1);
-    if (pv) {
-      // one kernel: [norm all-reduce + Givens step of iteration iter-1] + scale + P^-1 + [halo push]; then ONE mat-vec launch
-      // whose boundary-row blocks (scheduled last) wait for the neighbours' halo flags
-      const unsigned long long hseq = ++*ph->hseq;
-      prof.begin("scale_pc_apply", st);
-      k_scale_pc_apply_peer<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, dinv00, dinv11, QCOL(iter), poffC, zvec, poffN, pv, pending_seq,
-                                                                  hseq, iter - 1, W->S, iter ? HCOL(iter - 1) : HCOL(0), W->gv, W->beta,
-                                                                  W->tailc, W->res_hist);
-      DFB_LAUNCH_CHECK();
-      prof.end(st);
-      pending_seq = 0;
-      prof.begin("spmv", st);
-      DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, poffN, 0.0, w, poffC, st, pv, hseq, W->n_interior));
-      prof.end(st);
+    prof.begin("spmv", st);
+    if (pv && options().spmv_peer_split) {   // interior rows by the plain kernel, the boundary rows (which wait for the halo) after them
+      DFB_CHECK(launch_spmv(0, W->n_interior, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, st, LAY_XAOS | LAY_YAOS));
+      DFB_CHECK(launch_spmv(W->n_interior, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, st, LAY_XAOS | LAY_YAOS, pv, hseq, W->n_interior));
+    } else if (pv) {   // ONE launch whose boundary-row blocks (scheduled last) wait for the neighbours' halo flags
+      DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, st, LAY_XAOS | LAY_YAOS, pv, hseq, W->n_interior));
+    } else if (W->parallel) {
+      DFB_CHECK(W->par.halo_begin_aos(zvec, st, W->par.user));
+      DFB_CHECK(launch_spmv(0, W->n_interior, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, st, LAY_XAOS | LAY_YAOS));
+      DFB_CHECK(W->par.halo_end(zvec, st, W->par.user));
+      DFB_CHECK(launch_spmv(W->n_interior, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, st, LAY_XAOS | LAY_YAOS));
     } else {
-      prof.begin("scale_pc_apply", st);
-      k_scale_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, &W->S->inv_norm, dinv00, dinv11, QCOL(iter), poffC,
-                                                            zvec, poffN);
-      DFB_LAUNCH_CHECK();
-      prof.end(st);
-      prof.begin("spmv", st);
-      DFB_CHECK(matvec(1.0, zvec, 0.0, w));
-      prof.end(st);
+      DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, st, LAY_XAOS | LAY_YAOS));
     }
-    // h = Q^T w  (krylov.c:166-174)
+    prof.end(st);
+    // raw dots d = Q^T w_raw  (krylov.c:166-174)
     const int ncol = iter + 1;
     const unsigned long long seq = pv ? ++*ph->seq : 0ull;
     prof.begin("multidot", st);
     const int ny = ceil_div(ncol, JT);
     const int mg = std::max(1, std::min(mgrid, (4 * num_sms()) / ny));   // one resident wave of (row chunk, column group) blocks
-    k_multidot<<<dim3(mg, ny), 256, 0, st>>>(nl, Q, ldq, ncol, w, W->part, HCOL(iter), W->ctr, pv, seq);
+    k_multidot<<<dim3(mg, ny), 256, 0, st>>>(nl, Q, ldq, ncol, w, W->part, W->draw, W->ctr, pv, seq);
     DFB_LAUNCH_CHECK();
     prof.end(st);
     if (W->parallel && !pv) {
-      prof.begin("allreduce h", st);
-      DFB_CHECK(W->par.allreduce(HCOL(iter), ncol, st, W->par.user));
+      prof.begin("allreduce d", st);
+      DFB_CHECK(W->par.allreduce(W->draw, ncol, st, W->par.user));
       prof.end(st);
     }
-    // w -= Q h, fused with ||w||^2 and (single GPU) the scalar Givens step  (krylov.c:176-183, 229-277)
+    // update + norm + P^-1 (+ Givens step on one GPU; + the fused collectives in peer-memory mode)  (krylov.c:176-183, 229-277)
     prof.begin("update", st);
-    k_update<<<ugrid, 256, 0, st>>>(nl, Q, ldq, ncol, HCOL(iter), w, W->part, &W->S->nrm2_live, W->ctr + 1, W->parallel ? 0 : 1,
-                                    W->S, W->gv, W->beta, W->tailc, W->res_hist, pv, seq);
+    if (ph) hseq = ++*ph->hseq;   // the halo of z~_{iter+1} leaves from this kernel
+    k_update<<<ugrid, 256, 0, st>>>(nl, Q, ldq, ncol, W->draw, HCOL(iter), iter ? HCOL(iter - 1) : HCOL(0), w, W->part, W->ctr + 1,
+                                    pv ? 2 : (W->parallel ? 1 : 0), US, W->pcrec, zvec, pv, seq, pending_seq, hseq);
     DFB_LAUNCH_CHECK();
     prof.end(st);
     if (pv) {
-      // the norm reduction + Givens step are folded into the NEXT iteration's first kernel; they run on their own only
-      // when the host needs the residual now (the every-20th test) or the loop ends
+      // the norm reduction + Givens step of this iteration are folded into the NEXT update's prologue; they run on their own
+      // only when the host needs the residual now (the every-20th test) or the loop ends
       pending_seq = seq;
       if ((iter + 1) % 20 == 0 || iter + 1 == maxit) {
         prof.begin("step (peer sum)", st);
-        k_gmres_step_peer<<<1, 32, 0, st>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist, pv, seq);
+        k_gmres_step_peer<<<1, 32, 0, st>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist, W->qs, pv, seq);
         DFB_LAUNCH_CHECK();
         prof.end(st);
         pending_seq = 0;
@@ -1291,7 +1347,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     } else if (W->parallel) {
       prof.begin("allreduce nrm+step", st);
       DFB_CHECK(W->par.allreduce(&W->S->nrm2_live, 1, st, W->par.user));
-      k_gmres_step<<<1, 1, 0, st>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist);
+      k_gmres_step<<<1, 1, 0, st>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist, W->qs);
       DFB_LAUNCH_CHECK();
       prof.end(st);
     }
@@ -1313,14 +1369,12 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
       DFB_CUDA(cudaFuncSetAttribute(k_gmres_trsv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(f64) * 127 * 127)));
       trsv_attr = true;
     }
-    k_gmres_trsv<<<1, 128, sizeof(f64) * (size_t)iter * iter, st>>>(iter, W->H, ldh, W->beta, W->tailc, W->tail_coef);
+    k_gmres_trsv<<<1, 128, sizeof(f64) * (size_t)iter * iter, st>>>(iter, W->H, ldh, W->beta, W->tailc, W->tail_coef, W->qs, W->ycoef);
     DFB_LAUNCH_CHECK();
-    k_combine<<<cgrid, 256, 0, st>>>(nl, Q, ldq, iter, W->beta, W->t);
+    k_combine<<<cgrid, 256, 0, st>>>(nl, Q, ldq, iter, W->ycoef, W->t);
     DFB_LAUNCH_CHECK();
-    // P^-1 on the combination, written compactly into z, then x += z (krylov.c:313-319)
-    k_pc_apply<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, dinv00, dinv11, W->t, poffC, W->z, poffC, 0, 0, 0);   // W->z: private scratch
-    DFB_LAUNCH_CHECK();
-    k_add_live<<<vgrid, 256, 0, st>>>(n_own, W->z, d_x, poffN);
+    // x += P^-1 (combination)  (krylov.c:313-319)
+    k_pc_add_live<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, W->pcrec, W->t, d_x, poffN);
     DFB_LAUNCH_CHECK();
     k_axpy_dev<<<ceil_div((i64)tail_n, 256), 256, 0, st>>>(tail_n, W->tail_coef, d_b + (size_t)4 * N, d_x + (size_t)4 * N);
     DFB_LAUNCH_CHECK();

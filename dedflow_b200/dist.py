@@ -150,7 +150,7 @@ def partition(mesh, npart: np.ndarray, rank: int, world: int, weak_group: int = 
 # ----------------------------------------------------------------------------------------------------------------
 class ParallelOps(C.Structure):
     _fields_ = [("n_own", C.c_int), ("n_interior", C.c_int), ("allreduce", C.c_void_p), ("halo_begin", C.c_void_p),
-                ("halo_end", C.c_void_p), ("user", C.c_void_p), ("p2p", C.c_void_p)]
+                ("halo_end", C.c_void_p), ("user", C.c_void_p), ("p2p", C.c_void_p), ("halo_begin_aos", C.c_void_p)]
 
 
 class DistFlowSystem:
@@ -215,7 +215,7 @@ class DistFlowSystem:
         self.gmres = ws
         fn = lambda name: C.cast(getattr(L, name), C.c_void_p).value
         self.ops = ParallelOps(self.n_own, self.n_int, fn("dfb_comm_allreduce"), fn("dfb_comm_halo_begin"),
-                               fn("dfb_comm_halo_end"), comm.value, self.p2p)
+                               fn("dfb_comm_halo_end"), comm.value, self.p2p, fn("dfb_comm_halo_begin_aos"))
         _lib.check(L.dfb_gmres_set_parallel(ws, C.byref(self.ops)), "dfb_gmres_set_parallel")
 
     def _connect_peer_memory(self, dist):

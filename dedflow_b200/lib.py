@@ -55,6 +55,7 @@ _SIGS = {
     "dfb_comm_set_halo": (ci, [vp, ci, ci, vp, vp, vp, vp, vp]),
     "dfb_comm_allreduce": (ci, [vp, ci, vp, vp]),
     "dfb_comm_halo_begin": (ci, [vp, vp, vp]),
+    "dfb_comm_halo_begin_aos": (ci, [vp, vp, vp]),
     "dfb_comm_halo_end": (ci, [vp, vp, vp]),
     "dfb_comm_halo": (ci, [vp, vp, vp]),
     "dfb_genalpha_stage": (ci, [ci, vp, vp, vp, vp, vp, vp]),

@@ -168,6 +168,9 @@ typedef struct dfb_parallel_ops {
    * summed in rank order): no NCCL call and no extra launch per reduction.  The callbacks above are still used outside
    * the iteration loop (initial residual, final ghost refresh). */
   const void* p2p;
+  /* Needed when p2p is NULL (NCCL path): like halo_begin, for a vector in the solver's interleaved layout x[4*node + c]
+   * (c = 0..2 velocity, 3 pressure; 4 * num_local_nodes doubles).  halo_end is shared. */
+  int (*halo_begin_aos)(double* d_x4, void* stream, void* user);
 } dfb_parallel_ops;
 int dfb_gmres_set_parallel(dfb_gmres* ws, const dfb_parallel_ops* ops);
 /* Solve A x = b (x in/out, b in; both 6N device vectors).  Convergence is tested only when (iter+1)%20==0 against
@@ -223,6 +226,7 @@ int dfb_comm_set_halo(dfb_comm* comm, int num_local_nodes, int n_neighbors, cons
 int dfb_comm_allreduce(double* d_buf, int count, void* stream, void* user);
 int dfb_comm_halo_begin(double* d_x, void* stream, void* user);
 int dfb_comm_halo_end(double* d_x, void* stream, void* user);
+int dfb_comm_halo_begin_aos(double* d_x4, void* stream, void* user);
 /* blocking convenience: refresh the ghosts of a 6N-layout vector */
 int dfb_comm_halo(dfb_comm* comm, double* d_x, void* stream);
 /* Peer-memory (CUDA IPC over NVLink) mode, one node only.  (1) every rank allocates its shared region (mailbox + the
