@@ -149,6 +149,10 @@ struct P2PView {
   // at most ~timeout per kernel in flight, never a GPU that has to be reset.
   unsigned* err;
   unsigned long long timeout_ns;
+  // {all-reduce sequence, halo sequence} at the start of the current solve (device memory, set by the host once per solve):
+  // the kernels of a solve receive OFFSETS from these (fixed for a given iteration index, so the launches can be replayed
+  // from a CUDA graph) and form the tags as base + offset.
+  const unsigned long long* seq_base;
 };
 
 // what dfb_comm_p2p_view() returns.  The sequence counters of the fused collectives belong to the COMMUNICATOR (one owner per
@@ -160,6 +164,7 @@ struct P2PHandle {
   unsigned long long* seq;    // all-reduce sequence (multi-dot / norm slots)
   unsigned long long* hseq;   // halo sequence
   unsigned* d_err;            // device error word (== host.err)
+  unsigned long long* d_seq_base;   // device copy of {seq, hseq} at the start of the running solve (== host.seq_base)
 };
 
 __host__ __device__ inline size_t p2p_a_ll(int R, int par, int r, int j) { return (((size_t)par * R + r) * P2P_ACAP + j) * 2; }

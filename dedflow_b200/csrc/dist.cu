@@ -126,6 +126,7 @@ struct dfb_comm {
   unsigned* d_push_ctr = nullptr;
   unsigned* d_err = nullptr;            // raised by a kernel whose bounded wait ran out (common.cuh p2p_give_up)
   unsigned long long seq = 0, hseq = 0; // sequence counters of the fused collectives: ONE owner per communicator
+  unsigned long long* d_seq_base = nullptr;   // their values at the start of the running solve, on the device
   P2PView* d_view = nullptr;
   P2PView h_view;
   P2PHandle handle;
@@ -163,7 +164,7 @@ void dfb_comm_destroy(dfb_comm* c) {
   for (int r = 0; r < c->nranks && r < P2P_MAXR; r++)
     if (c->peer_base[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_base[r]);
   cudaFree(c->d_tgt_ptr); cudaFree(c->d_tgt_q); cudaFree(c->d_tgt_rid);
-  cudaFree(c->shared); cudaFree(c->d_remote_nodes); cudaFree(c->d_push_ctr); cudaFree(c->d_err); cudaFree(c->d_view);
+  cudaFree(c->shared); cudaFree(c->d_remote_nodes); cudaFree(c->d_push_ctr); cudaFree(c->d_err); cudaFree(c->d_seq_base); cudaFree(c->d_view);
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
   if (c->ev_done) cudaEventDestroy(c->ev_done);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
@@ -333,6 +334,11 @@ int dfb_comm_p2p_connect(dfb_comm* c, const void* handles, const int* h_remote_n
     DFB_CUDA(cudaMemset(c->d_err, 0, sizeof(unsigned)));
   }
   v.err = c->d_err;
+  if (!c->d_seq_base) {
+    DFB_CUDA(cudaMalloc(&c->d_seq_base, 2 * sizeof(unsigned long long)));
+    DFB_CUDA(cudaMemset(c->d_seq_base, 0, 2 * sizeof(unsigned long long)));
+  }
+  v.seq_base = c->d_seq_base;
   {   // wait budget of one poll loop (default 10 s; DFB_P2P_TIMEOUT_MS overrides, tests use a short one)
     const char* e = getenv("DFB_P2P_TIMEOUT_MS");
     const double ms = e ? atof(e) : 10000.0;
@@ -352,6 +358,7 @@ const void* dfb_comm_p2p_view(dfb_comm* c) {
   c->handle.seq = &c->seq;
   c->handle.hseq = &c->hseq;
   c->handle.d_err = c->d_err;
+  c->handle.d_seq_base = c->d_seq_base;
   return &c->handle;
 }
 

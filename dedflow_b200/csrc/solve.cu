@@ -90,7 +90,13 @@ struct GmresScalars {
   f64 cw;          // peer-memory mode: dead-tail coefficient of the current w, -sum_j h_j tailc_j (set by k_update)
 };
 
-__device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist, f64* qs);
+struct UpdateScalars {   // device arrays of the recurrence (all persistent in the workspace)
+  GmresScalars* S;
+  f64 *qs, *gv, *beta, *tailc, *res_hist;
+};
+__device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist, f64* qs,
+                               const f64* h_in, const f64* gv_in, const f64* tc_in);
+__device__ __forceinline__ void gmres_step_stage(int it, const f64* hcol, const f64* gv, const f64* tailc, f64* h_s, f64* gv_s, f64* tc_s);
 
 // ------------------------------------------------------------------------------------------------------------
 // SpMV.  Row i of the output: u -> y[3*i + ii], p -> y[y_poff + i]; input x: u -> x[3*c + l], p -> x[x_poff + c].
@@ -251,12 +257,14 @@ __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int
                                                  const f64* __restrict__ A00, const f64* __restrict__ A01,
                                                  const f64* __restrict__ A10, const f64* __restrict__ A11, f64 alpha,
                                                  const f64* __restrict__ x, size_t x_poff, f64 beta, f64* __restrict__ y,
-                                                 size_t y_poff, const P2PView* __restrict__ pv, unsigned long long hseq,
-                                                 int n_interior) {
+                                                 size_t y_poff, const P2PView* __restrict__ pv, unsigned hoff, int n_interior) {
+  bool halo_block = false;   // block-uniform: this block owns boundary rows (they reference ghost columns)
   if (PEER) {
     const int last_row = row0 + (int)((((size_t)blockIdx.x + 1) * blockDim.x - 1) / G);
-    if (last_row >= n_interior) {   // block-uniform
-      if ((int)threadIdx.x < pv->n_nbr) p2p_wait(pv, pv->mbox_local + p2p_h_flag(pv->nranks, pv->nbr[threadIdx.x]), hseq);
+    halo_block = last_row >= n_interior;
+    if (halo_block) {
+      if ((int)threadIdx.x < pv->n_nbr)
+        p2p_wait(pv, pv->mbox_local + p2p_h_flag(pv->nranks, pv->nbr[threadIdx.x]), pv->seq_base[1] + hoff);
       __syncthreads();
     }
   }
@@ -272,8 +280,12 @@ __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int
     len = __ldg(row_ptr + row + 1) - start;
   }
   f64 y0, y1, y2, yp;
-  spmv_row<G, PEER, false, AOSX>(A00 + (size_t)start * 9, A01 + (size_t)start * 3, A10 + (size_t)start * 3, A11 + start,
-                                 col_ind + start, len, lane, gmask, x, x_poff, n_rows, y0, y1, y2, yp);
+  if (PEER && halo_block)   // ghost columns are read through L2; interior blocks run exactly the single-GPU row code
+    spmv_row<G, true, false, AOSX>(A00 + (size_t)start * 9, A01 + (size_t)start * 3, A10 + (size_t)start * 3, A11 + start,
+                                   col_ind + start, len, lane, gmask, x, x_poff, n_rows, y0, y1, y2, yp);
+  else
+    spmv_row<G, false, false, AOSX>(A00 + (size_t)start * 9, A01 + (size_t)start * 3, A10 + (size_t)start * 3, A11 + start,
+                                    col_ind + start, len, lane, gmask, x, x_poff, n_rows, y0, y1, y2, yp);
   if (live && lane == 0) spmv_store<AOSY>(y, y_poff, row, alpha, beta, y0, y1, y2, yp);
 }
 
@@ -444,7 +456,7 @@ static bool spmv_tma_on() { return options().spmv_tma != 0; }   // 0 selects the
 enum { LAY_ABI = 0, LAY_XAOS = 1, LAY_YAOS = 2 };
 int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, const f64* A00, const f64* A01, const f64* A10,
                 const f64* A11, f64 alpha, const f64* x, size_t x_poff, f64 beta, f64* y, size_t y_poff, cudaStream_t st,
-                int layout = LAY_ABI, const P2PView* pv = nullptr, unsigned long long hseq = 0, int n_interior = 0) {
+                int layout = LAY_ABI, const P2PView* pv = nullptr, unsigned hoff = 0, int n_interior = 0) {
   if (row1 <= row0) return DFB_OK;
   const i64 rows = row1 - row0;
   if (pv && layout != (LAY_XAOS | LAY_YAOS)) { set_error("launch_spmv: the peer-memory mat-vec runs on interleaved vectors only"); return DFB_ERR_ARG; }
@@ -473,17 +485,17 @@ int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, cons
   const int grid8 = ceil_div(rows * 8, 256);
   if (pv) {
     k_spmv_fs<8, true, true, true><<<grid8, 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x, x_poff, beta, y,
-                                                         y_poff, pv, hseq, n_interior);
+                                                         y_poff, pv, hoff, n_interior);
   } else if (layout == LAY_YAOS) {
     k_spmv_fs<8, false, false, true><<<grid8, 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x, x_poff, beta, y,
-                                                           y_poff, nullptr, 0ull, 0);
+                                                           y_poff, nullptr, 0u, 0);
   } else if (layout == (LAY_XAOS | LAY_YAOS)) {
     k_spmv_fs<8, false, true, true><<<grid8, 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x, x_poff, beta, y,
-                                                          y_poff, nullptr, 0ull, 0);
+                                                          y_poff, nullptr, 0u, 0);
   } else if (layout == LAY_ABI) {
 #define DFB_SPMV(G)                                                                                                              \
   k_spmv_fs<G, false, false, false><<<ceil_div(rows * G, 256), 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11,   \
-                                                                             alpha, x, x_poff, beta, y, y_poff, nullptr, 0ull, 0)
+                                                                             alpha, x, x_poff, beta, y, y_poff, nullptr, 0u, 0)
     switch (spmv_group()) {
       case 4: DFB_SPMV(4); break;
       case 32: DFB_SPMV(32); break;
@@ -587,19 +599,21 @@ __device__ __forceinline__ double2 pc_half(const f64* __restrict__ rec, int half
   return make_double2(a.x * x0 + a.y * x1 + b.x * x2, xp * b.y);
 }
 
-// halo push of one half node record into the neighbours' z (peer-memory mode): node i is boundary-owned
-__device__ __forceinline__ void push_half(const P2PView* __restrict__ pv, int i, int half, double2 v) {
-  const int b = i - pv->tgt_base;
-  if (b < 0 || b >= pv->tgt_n) return;
+// halo push of one half node record into the neighbours' z (peer-memory mode) if node i is boundary-owned; returns whether it
+// stored anything.  The caller issues ONE __threadfence_system() after its last push (before the flag election below): a fence
+// per push would stall the warp for an NVLink round trip every trip.
+__device__ __forceinline__ bool push_half(const P2PView* __restrict__ pv, int tgt_base, int tgt_n, int i, int half, double2 v) {
+  const int b = i - tgt_base;
+  if (b < 0 || b >= tgt_n) return false;
   for (int t = pv->tgt_ptr[b]; t < pv->tgt_ptr[b + 1]; t++) {
     f64* zr = pv->z_peer[pv->nbr[pv->tgt_q[t]]];
     *reinterpret_cast<double2*>(zr + (size_t)pv->tgt_rid[t] * 4 + 2 * half) = v;
   }
-  __threadfence_system();
+  return true;
 }
 
 // raise this mat-vec's halo flag on every neighbour once the whole grid has pushed (last-block election on pv->push_ctr)
-__device__ __forceinline__ void push_flag(const P2PView* __restrict__ pv, unsigned long long hseq) {
+__device__ __forceinline__ void push_flag(const P2PView* __restrict__ pv, unsigned hoff) {
   __shared__ bool push_last;
   if (pv->n_nbr == 0) return;
   __syncthreads();
@@ -612,14 +626,14 @@ __device__ __forceinline__ void push_flag(const P2PView* __restrict__ pv, unsign
   if (threadIdx.x == 0) *pv->push_ctr = 0u;
   if ((int)threadIdx.x < pv->n_nbr) {
     __threadfence_system();
-    p2p_signal(pv->mbox_peer[pv->nbr[threadIdx.x]] + p2p_h_flag(pv->nranks, pv->rank), hseq);
+    p2p_signal(pv->mbox_peer[pv->nbr[threadIdx.x]] + p2p_h_flag(pv->nranks, pv->rank), pv->seq_base[1] + hoff);
   }
 }
 
 // z (interleaved, local numbering) = P^-1 w (interleaved, owned nodes): the first basis vector of a solve (every later one
 // leaves the update kernel already preconditioned).  One thread per half node.  pv != NULL: + halo push and flag.
 __global__ void __launch_bounds__(256) k_pc_apply_aos(int n, const f64* __restrict__ rec, const f64* __restrict__ w, f64* __restrict__ z,
-                                                      const P2PView* __restrict__ pv, unsigned long long hseq) {
+                                                      const P2PView* __restrict__ pv, unsigned hoff) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int i = (int)(t >> 1), half = (int)(t & 1);
   if (i < n) {
@@ -627,9 +641,9 @@ __global__ void __launch_bounds__(256) k_pc_apply_aos(int n, const f64* __restri
     const double2 lo = w2[0], hi = w2[1];
     const double2 v = pc_half(rec + (size_t)i * PCREC, half, lo.x, lo.y, hi.x, hi.y);
     reinterpret_cast<double2*>(z)[t] = v;
-    if (pv) push_half(pv, i, half, v);
+    if (pv && push_half(pv, pv->tgt_base, pv->tgt_n, i, half, v)) __threadfence_system();
   }
-  if (pv) push_flag(pv, hseq);
+  if (pv) push_flag(pv, hoff);
 }
 
 // x (ABI layout, 6N) += P^-1 t (interleaved, owned nodes)   (krylov.c:313-319: the preconditioner on the combination)
@@ -733,9 +747,11 @@ __device__ __forceinline__ void md_accum(const double2* __restrict__ q2, const d
 // starts 32-byte aligned.
 __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restrict__ Q, size_t ldq, int ncol,
                                                   const f64* __restrict__ w, f64* part, f64* __restrict__ h,
-                                                  unsigned* ctr, const P2PView* __restrict__ pv, unsigned long long seq) {
+                                                  unsigned* ctr, const P2PView* __restrict__ pv, unsigned soff, unsigned soff_prev,
+                                                  UpdateScalars U, f64* hcol_prev) {
   __shared__ f64 smj[8][JT];
   __shared__ f64 hsum[P2P_ACAP];
+  __shared__ f64 h_s[128], gv_s[256], tc_s[128];   // staged inputs of the previous step's Givens update (peer-memory mode)
   const int ngrp = gridDim.y, gbase = ncol / ngrp, grem = ncol - gbase * ngrp;
   const int j0 = blockIdx.y * gbase + min((int)blockIdx.y, grem);
   const int nj = gbase + ((int)blockIdx.y < grem ? 1 : 0);
@@ -784,12 +800,37 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
       if (pv) hsum[j] = s; else h[j] = s;
     }
   }
-  if (pv) {   // publish this rank's partial to every rank (itself included); k_update sums them in rank order
+  if (pv) {
+    // Peer-memory mode: the whole all-reduce finishes HERE, in one block per GPU -- publish this rank's partial to every rank
+    // (itself included), wait for every rank's partial in our own mailbox, sum in rank order (bit-identical on all ranks) and
+    // leave the result in global memory for the update kernel, whose ~600 blocks then read it like on one GPU.  (Every block
+    // of the update polling the mailbox itself -- tens of thousands of uncached loads on a dozen lines -- measured +11 us.)
     __syncthreads();
+    const unsigned long long seq = pv->seq_base[0] + soff;
     const int R = pv->nranks, par = (int)(seq & 1ull);
     for (int t = threadIdx.x; t < R * ncol; t += 256) {
       const int r = t / ncol, j = t - r * ncol;
       ll_store(pv->mbox_peer[r] + p2p_a_ll(R, par, pv->rank, j), hsum[j], (unsigned)seq);
+    }
+    // meanwhile: the norm of the newest column (published at the end of the previous update, long since arrived) and the
+    // scalar Givens step of the previous iteration, which nothing has needed until now
+    if (soff_prev) {
+      const int itp = ncol - 2;   // the previous iteration
+      gmres_step_stage(itp, hcol_prev, U.gv, U.tailc, h_s, gv_s, tc_s);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned long long sp = pv->seq_base[0] + soff_prev;
+        const int parp = (int)(sp & 1ull);
+        f64 nrm2 = 0.0;
+        for (int r = 0; r < R; r++) nrm2 += ll_load(pv, pv->mbox_local + p2p_b_ll(R, parp, r), (unsigned)sp);
+        U.S->nrm2_live = nrm2;
+        gmres_step_dev(itp, U.S, hcol_prev, U.gv, U.beta, U.tailc, U.res_hist, U.qs, h_s, gv_s, tc_s);
+      }
+    }
+    for (int j = threadIdx.x; j < ncol; j += 256) {
+      f64 d = 0.0;
+      for (int r = 0; r < R; r++) d += ll_load(pv, pv->mbox_local + p2p_a_ll(R, par, r, j), (unsigned)seq);
+      h[j] = d;
     }
   }
   if (threadIdx.x == 0) *ctr = 0u;
@@ -808,54 +849,31 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
 #ifndef UPDATE_LD
 #define UPDATE_LD __ldcs
 #endif
-struct UpdateScalars {   // device arrays of the recurrence (all persistent in the workspace)
-  GmresScalars* S;
-  f64 *qs, *gv, *beta, *tailc, *res_hist;
-};
 __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict__ Q, size_t ldq, int ncol, const f64* __restrict__ draw,
                                                 f64* hcol, f64* hcol_prev, f64* __restrict__ w, f64* part, unsigned* ctr, int mode,
                                                 UpdateScalars U, const f64* __restrict__ pcrec, f64* __restrict__ z,
-                                                const P2PView* __restrict__ pv, unsigned long long seq, unsigned long long seq_prev,
-                                                unsigned long long hseq) {
+                                                const P2PView* __restrict__ pv, unsigned soff, unsigned hoff) {
   __shared__ f64 sh[128];    // c_i = h_i s_i: coefficient of the stored (unnormalised) column i
   __shared__ f64 shh[128];   // h_i: the Hessenberg column
   __shared__ f64 sm[8];
   __shared__ f64 s_sj, s_tcj;
+  __shared__ f64 sgv[256], stc[128];   // staged inputs of the scalar Givens step (gmres_step_dev)
   const int jc = ncol - 1;   // index of the newest column w~_j (the one A z~ was formed from)
-  if (threadIdx.x == 0) {
-    f64 sj = U.qs[jc], tcj = U.tailc[jc];
-    if (pv && seq_prev) {   // the norm of w~_j is still in the mailbox: sum the ranks' partials in rank order
-      const int R = pv->nranks, par = (int)(seq_prev & 1ull);
-      f64 nrm2 = 0.0;
-      for (int r = 0; r < R; r++) nrm2 += ll_load(pv, pv->mbox_local + p2p_b_ll(R, par, r), (unsigned)seq_prev);
-      const f64 cw = U.S->cw;
-      sj = 1.0 / sqrt(nrm2 + cw * cw * U.S->tail2);   // same expressions as gmres_step_dev: identical on every block and rank
-      tcj = cw * sj;
-      if (blockIdx.x == 0) {
-        U.S->nrm2_live = nrm2;
-        gmres_step_dev(jc - 1, U.S, hcol_prev, U.gv, U.beta, U.tailc, U.res_hist, U.qs);
-      }
-    }
-    s_sj = sj;
-    s_tcj = tcj;
+  const unsigned long long seq = pv ? pv->seq_base[0] + soff : 0ull;
+  if (threadIdx.x == 0) {   // scale and dead-tail coefficient of the newest column: written by the previous step's Givens update
+    s_sj = U.qs[jc];
+    s_tcj = U.tailc[jc];
   }
   __syncthreads();
   {
     const f64 sj = s_sj;
     for (int i = threadIdx.x; i < ncol; i += 256) {
-      f64 d;
-      if (pv) {   // fused all-reduce of the raw dots: every rank's partial was stored into OUR mailbox, summed in rank order
-        const int R = pv->nranks, par = (int)(seq & 1ull);
-        d = 0.0;
-        for (int r = 0; r < R; r++) d += ll_load(pv, pv->mbox_local + p2p_a_ll(R, par, r, i), (unsigned)seq);
-      } else {
-        d = draw[i];
-      }
-      const f64 si = i == jc ? sj : U.qs[i];
+      const f64 d = draw[i];   // raw dots, all-reduced (peer mode: by the multi-dot's last block)
+      const f64 si = U.qs[i];
       const f64 h = si * sj * d;
       shh[i] = h;
       sh[i] = h * si;
-      if (pv && blockIdx.x == 0) hcol[i] = h;   // the next kernel's Givens step reads the column from global memory
+      if (pv && blockIdx.x == 0) hcol[i] = h;   // the next multi-dot's Givens step reads the column from global memory
     }
   }
   __syncthreads();
@@ -867,6 +885,8 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
   const int lane = threadIdx.x & 31;
   const size_t warp0 = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5, nwarp = ((size_t)gridDim.x * 256) >> 5;
   f64 ss = 0.0;
+  bool pushed = false;
+  const int tgt_base = pv ? pv->tgt_base : 0, tgt_n = pv ? pv->tgt_n : 0;
   // The multi-dot has just swept the rows in ASCENDING order, so the highest rows of every column are what the 126 MB L2
   // still holds: sweep DESCENDING here (and leave the lowest rows behind for the next multi-dot's ascending sweep).
   const bool reverse = UPDATE_REVERSE;
@@ -909,31 +929,35 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
       const double2 v = half == 0 ? pc_half(pcrec + (size_t)node * PCREC, 0, wn.x, wn.y, ox, oy)
                                   : pc_half(pcrec + (size_t)node * PCREC, 1, ox, oy, wn.x, wn.y);
       z2[i] = v;
-      if (pv) push_half(pv, node, half, v);
+      if (pv) pushed |= push_half(pv, tgt_base, tgt_n, node, half, v);
     }
   }
-  if (pv) push_flag(pv, hseq);
+  if (pv) {
+    if (pushed) __threadfence_system();   // this thread's halo stores are visible on the peers before the block joins the election
+    push_flag(pv, hoff);
+  }
   f64 r = block_sum_256(ss, sm);
   if (threadIdx.x == 0) part[blockIdx.x] = r;
   if (!last_block(ctr, gridDim.x)) return;
   f64 s = 0.0;
   for (int c = threadIdx.x; c < (int)gridDim.x; c += 256) s += __ldcg(part + c);
   s = block_sum_256(s, sm);
-  if (!pv)
-    for (int i = threadIdx.x; i < ncol; i += 256) hcol[i] = shh[i];
+  // inputs of the scalar tail below from shared memory (h itself is in shh already)
+  gmres_step_stage(jc, nullptr, U.gv, U.tailc, nullptr, sgv, stc);
   __syncthreads();
   if (threadIdx.x == 0) {
     *ctr = 0u;
     if (pv) {   // publish the partial sum of squares; the next update (or the step kernel) sums the ranks
       const int R = pv->nranks, par = (int)(seq & 1ull);
       f64 cw = 0.0;
-      for (int i = 0; i < ncol; i++) cw -= shh[i] * (i == jc ? s_tcj : U.tailc[i]);   // same expression and order as gmres_step_dev
+      for (int i = 0; i < ncol; i++) cw -= shh[i] * stc[i];   // same expression and order as gmres_step_dev
       U.S->cw = cw;
       __threadfence();   // S->cw before the norm becomes visible anywhere
       for (int rr = 0; rr < R; rr++) ll_store(pv->mbox_peer[rr] + p2p_b_ll(R, par, pv->rank), s, (unsigned)seq);
     } else {
       U.S->nrm2_live = s;
-      if (mode == 0) gmres_step_dev(jc, U.S, hcol, U.gv, U.beta, U.tailc, U.res_hist, U.qs);
+      if (mode == 0) gmres_step_dev(jc, U.S, hcol, U.gv, U.beta, U.tailc, U.res_hist, U.qs, shh, sgv, stc);
+      else for (int i = 0; i < ncol; i++) hcol[i] = shh[i];   // NCCL path: k_gmres_step reads the column from global memory
     }
   }
 }
@@ -1020,6 +1044,11 @@ __global__ void k_final_sum(const f64* __restrict__ part, f64* __restrict__ out)
   if (threadIdx.x == 0) *out = s;
 }
 
+__global__ void k_set_seq_base(unsigned long long* base, unsigned long long seq, unsigned long long hseq) {
+  base[0] = seq;
+  base[1] = hseq;
+}
+
 // start of a solve: beta[0] = ||r0|| including the dead tail; tailc[0] = 1/beta0; inv_norm = 1/beta0
 __global__ void k_gmres_begin(GmresScalars* S, f64* beta, f64* tailc, f64* res_hist, f64* qs) {
   const f64 n0 = sqrt(S->nrm2_live + S->tail2);
@@ -1033,19 +1062,22 @@ __global__ void k_gmres_begin(GmresScalars* S, f64* beta, f64* tailc, f64* res_h
 
 // one Arnoldi step's scalar work (krylov.c:229-277 + krylov_util.cu:5-19) for column `it`:
 //   hcol[0..it] holds h = Q^T w (already reduced), S->nrm2_live the sum of squares of the updated live w.
-__device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist, f64* qs) {
+// The recurrence reads its inputs -- h_in[0..it], gv_in[0..2 it), tc_in[0..it] -- from SHARED memory, where the calling block
+// has staged them with coalesced loads: one thread walking them in global memory pays an L2 round trip per entry (~0.3 us each,
+// 40 entries deep at the end of a solve), on the critical path of every Arnoldi step.  Outputs go to the global arrays.
+__device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist, f64* qs,
+                               const f64* h_in, const f64* gv_in, const f64* tc_in) {
   // dead tail: every basis vector's rows [4N,6N) equal tailc[j] * b_tail (D4): w_tail = -sum_j h_j tailc[j] b_tail
   f64 cw = 0.0;
-  for (int j = 0; j <= it; j++) cw -= hcol[j] * tailc[j];
+  for (int j = 0; j <= it; j++) cw -= h_in[j] * tc_in[j];
   const f64 nrm = sqrt(S->nrm2_live + cw * cw * S->tail2);
-  hcol[it + 1] = nrm;
   const f64 inv = 1.0 / nrm;
   S->inv_norm = inv;
   qs[it + 1] = inv;             // scale of the (unnormalised) column it + 1
   tailc[it + 1] = cw * inv;
-  f64 xx = hcol[0];
-  for (int i = 0; i < it; i++) {  // cublasDrot, n = 1 (krylov.c:258-263); the running entry stays in a register so that
-    const f64 c = gv[2 * i], s = gv[2 * i + 1], yy = hcol[i + 1];   // no load waits for a previous store
+  f64 xx = h_in[0];
+  for (int i = 0; i < it; i++) {  // cublasDrot, n = 1 (krylov.c:258-263); the running entry stays in a register
+    const f64 c = gv_in[2 * i], s = gv_in[2 * i + 1], yy = h_in[i + 1];
     hcol[i] = c * xx + s * yy;
     xx = c * yy - s * xx;
   }
@@ -1061,22 +1093,38 @@ __device__ void gmres_step_dev(int it, GmresScalars* S, f64* hcol, f64* gv, f64*
   res_hist[it + 1] = fabs(beta[it + 1]);
 }
 
-__global__ void k_gmres_step(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist, f64* qs) {
-  gmres_step_dev(it, S, hcol, gv, beta, tailc, res_hist, qs);
+// stage the inputs of step `it` (block-cooperative; the caller synchronises before thread 0 runs the step)
+__device__ __forceinline__ void gmres_step_stage(int it, const f64* hcol, const f64* gv, const f64* tailc, f64* h_s, f64* gv_s, f64* tc_s) {
+  for (int i = threadIdx.x; i <= it; i += blockDim.x) {
+    if (hcol) h_s[i] = hcol[i];
+    tc_s[i] = tailc[i];
+  }
+  for (int i = threadIdx.x; i < 2 * it; i += blockDim.x) gv_s[i] = gv[i];
+}
+
+__global__ void __launch_bounds__(128) k_gmres_step(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist,
+                                                    f64* qs) {
+  __shared__ f64 h_s[128], gv_s[256], tc_s[128];
+  gmres_step_stage(it, hcol, gv, tailc, h_s, gv_s, tc_s);
+  __syncthreads();
+  if (threadIdx.x == 0) gmres_step_dev(it, S, hcol, gv, beta, tailc, res_hist, qs, h_s, gv_s, tc_s);
 }
 
 // peer-memory mode: fused all-reduce of ||w||^2 (rank order) + the scalar Arnoldi/Givens step; one warp
 __global__ void k_gmres_step_peer(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist, f64* qs,
-                                  const P2PView* __restrict__ pv, unsigned long long seq) {
+                                  const P2PView* __restrict__ pv, unsigned soff) {
+  const unsigned long long seq = pv->seq_base[0] + soff;
   const int R = pv->nranks, par = (int)(seq & 1ull);
   __shared__ f64 s_part[P2P_MAXR];
+  __shared__ f64 h_s[128], gv_s[256], tc_s[128];
+  gmres_step_stage(it, hcol, gv, tailc, h_s, gv_s, tc_s);
   if ((int)threadIdx.x < R) s_part[threadIdx.x] = ll_load(pv, pv->mbox_local + p2p_b_ll(R, par, threadIdx.x), (unsigned)seq);
   __syncthreads();
   if (threadIdx.x == 0) {
     f64 s = 0.0;
     for (int r = 0; r < R; r++) s += s_part[r];
     S->nrm2_live = s;
-    gmres_step_dev(it, S, hcol, gv, beta, tailc, res_hist, qs);
+    gmres_step_dev(it, S, hcol, gv, beta, tailc, res_hist, qs, h_s, gv_s, tc_s);
   }
 }
 
@@ -1130,6 +1178,22 @@ struct dfb_gmres {
   dfb_parallel_ops par = {0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool parallel = false;
   std::string last_profile;   // per-kernel event times of the last solve (DFB_PROFILE != 0), see dfb_gmres_profile
+  // CUDA graphs of the 20-iteration chunks between two convergence tests (one GPU), valid for one set of matrix pointers
+  struct GraphKey {
+    const void *rp, *ci, *a00, *a01, *a10, *a11, *pv;
+    int n_own, n_interior, split;
+    bool operator==(const GraphKey& o) const {
+      return rp == o.rp && ci == o.ci && a00 == o.a00 && a01 == o.a01 && a10 == o.a10 && a11 == o.a11 && pv == o.pv && n_own == o.n_own &&
+             n_interior == o.n_interior && split == o.split;
+    }
+  };
+  GraphKey gkey = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0};
+  std::vector<cudaGraphExec_t> gexec;
+  cudaStream_t cap_stream = nullptr;
+  void drop_graphs() {
+    for (auto g : gexec) if (g) cudaGraphExecDestroy(g);
+    gexec.clear();
+  }
 };
 
 extern "C" {
@@ -1193,6 +1257,8 @@ void dfb_gmres_destroy(dfb_gmres* w) {
   cudaFree(w->z); cudaFree(w->t); cudaFree(w->part); cudaFree(w->dinv00); cudaFree(w->dinv11); cudaFree(w->tail_coef);
   cudaFree(w->qs); cudaFree(w->draw); cudaFree(w->ycoef); cudaFree(w->pcrec);
   cudaFree(w->S); cudaFree(w->ctr);
+  w->drop_graphs();
+  if (w->cap_stream) cudaStreamDestroy(w->cap_stream);
   delete w;
 }
 
@@ -1282,8 +1348,13 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   DFB_LAUNCH_CHECK();
   DFB_CUDA(cudaMemsetAsync(W->ctr, 0, 2 * sizeof(unsigned), st));
   // z~_0 = P^-1 r0 (+ its halo); every later z~ leaves the update kernel
-  unsigned long long hseq = ph ? ++*ph->hseq : 0ull;
-  k_pc_apply_aos<<<ceil_div((i64)2 * n_own, 256), 256, 0, st>>>(n_own, W->pcrec, QCOL(0), zvec, pv, hseq);
+  // Peer-memory mode: the tags of this solve's fused collectives are {base + offset}; the base goes to the device once, the
+  // offsets are fixed per iteration index (all-reduce: iteration + 1; halo of z~_j: j + 1), so the launches replay from graphs.
+  if (ph) {
+    k_set_seq_base<<<1, 1, 0, st>>>(ph->d_seq_base, *ph->seq, *ph->hseq);
+    DFB_LAUNCH_CHECK();
+  }
+  k_pc_apply_aos<<<ceil_div((i64)2 * n_own, 256), 256, 0, st>>>(n_own, W->pcrec, QCOL(0), zvec, pv, 1u);
   DFB_LAUNCH_CHECK();
 
   int iter = 0;
@@ -1293,74 +1364,114 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   std::vector<f64> hist((size_t)maxit + 1, 0.0);
   SolveProfiler prof;
   const UpdateScalars US = {W->S, W->qs, W->gv, W->beta, W->tailc, W->res_hist};
-  unsigned long long pending_seq = 0;   // peer-memory mode: norm reduction + Givens step of the previous iteration still to run
-  while (!converged && iter < maxit) {
+  // one Arnoldi step = three launches on stream `s` (+ the standalone collectives of the NCCL path)
+  auto arnoldi_step = [&](int iter, cudaStream_t s) -> int {
     // w_raw = A z~_iter into column iter + 1 (no scaling: the update applies s_iter)
     f64* w = QCOL(iter + 1);
-    prof.begin("spmv", st);
+    prof.begin("spmv", s);
     if (pv && options().spmv_peer_split) {   // interior rows by the plain kernel, the boundary rows (which wait for the halo) after them
-      DFB_CHECK(launch_spmv(0, W->n_interior, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, st, LAY_XAOS | LAY_YAOS));
-      DFB_CHECK(launch_spmv(W->n_interior, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, st, LAY_XAOS | LAY_YAOS, pv, hseq, W->n_interior));
+      DFB_CHECK(launch_spmv(0, W->n_interior, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, s, LAY_XAOS | LAY_YAOS));
+      DFB_CHECK(launch_spmv(W->n_interior, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, s, LAY_XAOS | LAY_YAOS, pv, (unsigned)iter + 1u, W->n_interior));
     } else if (pv) {   // ONE launch whose boundary-row blocks (scheduled last) wait for the neighbours' halo flags
-      DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, st, LAY_XAOS | LAY_YAOS, pv, hseq, W->n_interior));
+      DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, s, LAY_XAOS | LAY_YAOS, pv, (unsigned)iter + 1u, W->n_interior));
     } else if (W->parallel) {
-      DFB_CHECK(W->par.halo_begin_aos(zvec, st, W->par.user));
-      DFB_CHECK(launch_spmv(0, W->n_interior, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, st, LAY_XAOS | LAY_YAOS));
-      DFB_CHECK(W->par.halo_end(zvec, st, W->par.user));
-      DFB_CHECK(launch_spmv(W->n_interior, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, st, LAY_XAOS | LAY_YAOS));
+      DFB_CHECK(W->par.halo_begin_aos(zvec, s, W->par.user));
+      DFB_CHECK(launch_spmv(0, W->n_interior, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, s, LAY_XAOS | LAY_YAOS));
+      DFB_CHECK(W->par.halo_end(zvec, s, W->par.user));
+      DFB_CHECK(launch_spmv(W->n_interior, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, s, LAY_XAOS | LAY_YAOS));
     } else {
-      DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, st, LAY_XAOS | LAY_YAOS));
+      DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, s, LAY_XAOS | LAY_YAOS));
     }
-    prof.end(st);
+    prof.end(s);
     // raw dots d = Q^T w_raw  (krylov.c:166-174)
     const int ncol = iter + 1;
-    const unsigned long long seq = pv ? ++*ph->seq : 0ull;
-    prof.begin("multidot", st);
+    const unsigned soff = pv ? (unsigned)iter + 1u : 0u;
+    // peer-memory mode: the norm + Givens step of the previous iteration is still pending unless it closed a 20-iteration chunk
+    const unsigned soff_prev = (pv && iter > 0 && iter % 20 != 0) ? (unsigned)iter : 0u;
+    prof.begin("multidot", s);
     const int ny = ceil_div(ncol, JT);
     const int mg = std::max(1, std::min(mgrid, (4 * num_sms()) / ny));   // one resident wave of (row chunk, column group) blocks
-    k_multidot<<<dim3(mg, ny), 256, 0, st>>>(nl, Q, ldq, ncol, w, W->part, W->draw, W->ctr, pv, seq);
+    k_multidot<<<dim3(mg, ny), 256, 0, s>>>(nl, Q, ldq, ncol, w, W->part, W->draw, W->ctr, pv, soff, soff_prev, US,
+                                            iter ? HCOL(iter - 1) : HCOL(0));
     DFB_LAUNCH_CHECK();
-    prof.end(st);
+    prof.end(s);
     if (W->parallel && !pv) {
-      prof.begin("allreduce d", st);
-      DFB_CHECK(W->par.allreduce(W->draw, ncol, st, W->par.user));
-      prof.end(st);
+      prof.begin("allreduce d", s);
+      DFB_CHECK(W->par.allreduce(W->draw, ncol, s, W->par.user));
+      prof.end(s);
     }
     // update + norm + P^-1 (+ Givens step on one GPU; + the fused collectives in peer-memory mode)  (krylov.c:176-183, 229-277)
-    prof.begin("update", st);
-    if (ph) hseq = ++*ph->hseq;   // the halo of z~_{iter+1} leaves from this kernel
-    k_update<<<ugrid, 256, 0, st>>>(nl, Q, ldq, ncol, W->draw, HCOL(iter), iter ? HCOL(iter - 1) : HCOL(0), w, W->part, W->ctr + 1,
-                                    pv ? 2 : (W->parallel ? 1 : 0), US, W->pcrec, zvec, pv, seq, pending_seq, hseq);
+    prof.begin("update", s);
+    k_update<<<ugrid, 256, 0, s>>>(nl, Q, ldq, ncol, W->draw, HCOL(iter), iter ? HCOL(iter - 1) : HCOL(0), w, W->part, W->ctr + 1,
+                                   pv ? 2 : (W->parallel ? 1 : 0), US, W->pcrec, zvec, pv, soff,
+                                   (unsigned)iter + 2u /* the halo of z~_{iter+1} leaves from this kernel */);
     DFB_LAUNCH_CHECK();
-    prof.end(st);
+    prof.end(s);
     if (pv) {
       // the norm reduction + Givens step of this iteration are folded into the NEXT update's prologue; they run on their own
       // only when the host needs the residual now (the every-20th test) or the loop ends
-      pending_seq = seq;
       if ((iter + 1) % 20 == 0 || iter + 1 == maxit) {
-        prof.begin("step (peer sum)", st);
-        k_gmres_step_peer<<<1, 32, 0, st>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist, W->qs, pv, seq);
+        prof.begin("step (peer sum)", s);
+        k_gmres_step_peer<<<1, 128, 0, s>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist, W->qs, pv, soff);
         DFB_LAUNCH_CHECK();
-        prof.end(st);
-        pending_seq = 0;
+        prof.end(s);
       }
     } else if (W->parallel) {
-      prof.begin("allreduce nrm+step", st);
-      DFB_CHECK(W->par.allreduce(&W->S->nrm2_live, 1, st, W->par.user));
-      k_gmres_step<<<1, 1, 0, st>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist, W->qs);
+      prof.begin("allreduce nrm+step", s);
+      DFB_CHECK(W->par.allreduce(&W->S->nrm2_live, 1, s, W->par.user));
+      k_gmres_step<<<1, 128, 0, s>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist, W->qs);
       DFB_LAUNCH_CHECK();
-      prof.end(st);
+      prof.end(s);
     }
-    if ((iter + 1) % 20 == 0) {  // the reference's only convergence test (krylov.c:281-290)
-      DFB_CUDA(cudaMemcpyAsync(hist.data(), W->res_hist, sizeof(f64) * ((size_t)iter + 2), cudaMemcpyDeviceToHost, st));
-      if (ph) DFB_CUDA(cudaMemcpyAsync(&peer_err, ph->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-      DFB_CUDA(cudaStreamSynchronize(st));
-      if (peer_err) break;
-      rnrm_init = hist[0];
-      const f64 rnrm = hist[iter + 1];
-      if (rnrm < atol || rnrm < (rnrm_init + 1e-16) * rtol) converged = true;
+    return DFB_OK;
+  };
+  // the reference's only convergence test, after every 20th iteration (krylov.c:281-290)
+  auto convergence_test = [&](int done) -> int {
+    DFB_CUDA(cudaMemcpyAsync(hist.data(), W->res_hist, sizeof(f64) * ((size_t)done + 1), cudaMemcpyDeviceToHost, st));
+    if (ph) DFB_CUDA(cudaMemcpyAsync(&peer_err, ph->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    DFB_CUDA(cudaStreamSynchronize(st));
+    if (peer_err) return DFB_OK;
+    rnrm_init = hist[0];
+    const f64 rnrm = hist[done];
+    if (rnrm < atol || rnrm < (rnrm_init + 1e-16) * rtol) converged = true;
+    return DFB_OK;
+  };
+  // One GPU: the 20 iterations between two convergence tests (60 launches with fixed arguments for a given workspace and
+  // matrix) are captured once into a CUDA graph per chunk and replayed -- the launch gaps shrink, the host does one call.
+  const bool use_graph = (!W->parallel || pv) && !prof.on && options().graph != 0;
+  const dfb_gmres::GraphKey gkey = {rp, ci, A00, A01, A10, A11, pv, n_own, W->n_interior, options().spmv_peer_split};
+  while (!converged && iter < maxit && !peer_err) {
+    if (use_graph && iter % 20 == 0 && iter + 20 <= maxit) {
+      const size_t chunk = (size_t)iter / 20;
+      if (!(W->gkey == gkey)) { W->drop_graphs(); W->gkey = gkey; }
+      if (W->gexec.size() <= chunk) W->gexec.resize(chunk + 1, nullptr);
+      if (!W->gexec[chunk]) {
+        if (!W->cap_stream) DFB_CUDA(cudaStreamCreateWithFlags(&W->cap_stream, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        DFB_CUDA(cudaStreamBeginCapture(W->cap_stream, cudaStreamCaptureModeThreadLocal));
+        int rc = DFB_OK;
+        for (int k = 0; k < 20 && rc == DFB_OK; k++) rc = arnoldi_step(iter + k, W->cap_stream);
+        const cudaError_t ce = cudaStreamEndCapture(W->cap_stream, &graph);
+        if (rc != DFB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        DFB_CUDA(ce);
+        const cudaError_t ie = cudaGraphInstantiate(&W->gexec[chunk], graph, 0);
+        cudaGraphDestroy(graph);
+        DFB_CUDA(ie);
+      } else {
+        count_launch(pv ? (options().spmv_peer_split ? 81 : 61) : 60);
+      }
+      DFB_CUDA(cudaGraphLaunch(W->gexec[chunk], st));
+      iter += 20;
+      DFB_CHECK(convergence_test(iter));
+      continue;
     }
+    DFB_CHECK(arnoldi_step(iter, st));
     iter++;
+    if (iter % 20 == 0) DFB_CHECK(convergence_test(iter));
+  }
+  if (ph) {   // identical control flow on every rank: the communicator's counters advance by what this solve used
+    *ph->seq += (unsigned long long)iter;
+    *ph->hseq += (unsigned long long)iter + 1ull;
   }
   if (iter && !peer_err) {
     prof.begin("trsv..axpy", st);
