@@ -65,7 +65,10 @@ def mesh_datasets(mesh, group: str = "mesh") -> dict:
     forn = np.asarray(mesh.bound_forn, np.int64)
     # boundary triangles: the three vertices of the element that are not the opposite vertex forn (mesh_convert.py:80-98)
     ien = np.asarray(mesh.ien, np.int64)
-    tri = np.stack([np.delete(ien[e], o) for e, o in zip(f2e, forn)]) if f2e.size else np.zeros((0, 3), np.int64)
+    if getattr(mesh, "bound_ien", None) is not None:
+        tri = np.asarray(mesh.bound_ien, np.int64).reshape(-1, 3)
+    else:
+        tri = np.stack([np.delete(ien[e], o) for e, o in zip(f2e, forn)]) if f2e.size else np.zeros((0, 3), np.int64)
     d = {f"{group}/xg": np.asarray(mesh.xg, np.float64).reshape(-1),
          f"{group}/ien/tet": ien.reshape(-1),
          f"{group}/bound/node_offset": np.asarray(mesh.bound_node_offset, np.int64),

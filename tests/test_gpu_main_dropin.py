@@ -1,0 +1,108 @@
+"""The reference's OWN driver as the drop-in test (pytest -m gpu).  `/root/reference/src/main.c` is compiled UNMODIFIED by
+oracle/ref/Makefile into two executables that differ only in their link line:
+
+    oracle/_ref/dedflow_main_ref    main.c + the reference's own CUDA objects
+    oracle/_ref/dedflow_main_b200   main.c + Mesh.c MeshData.c common.c alloc.c Particle.c Field.c Array.c + -ldedflow_b200
+
+Both read the synthetic box mesh from `box.h5` (schema of tools/mesh_convert.py:116-126, written by dedflow_b200/h5flat.py)
+through Mesh3DCreateH5 (Mesh.c:12-104), run main()'s time loop (main.c:537-592: predictor, Newton iterations with reassembly
+of F and J, corrector) and write `sol.10.h5`.  main() runs 4000 steps, so each program is stopped (its own PID) once the
+banner of step 11 shows that step 10 and its solution file are complete.  Compared: every printed Newton norm (%.17e), every
+printed GMRES residual line, and every dataset of sol.0.h5 / sol.10.h5 -- BASELINE configs[4] in miniature, held by the reference."""
+import re
+import subprocess
+import time
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from dedflow_b200 import boxmesh, h5flat
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+REF_EXE = ROOT / "oracle" / "_ref" / "dedflow_main_ref"
+OUR_EXE = ROOT / "oracle" / "_ref" / "dedflow_main_b200"
+
+NEWTON = re.compile(r"^Newton (\d+)\) abs = (\S+) rel")
+GMRES = re.compile(r"^\s*(\d+)\) abs = (\S+) \(tol")
+
+
+def run_until_step(exe: Path, cwd: Path, step: int, timeout: float = 600.0) -> str:
+    """start the program, wait for the banner of `step`, stop it (exact PID), return what it printed before that banner"""
+    log = cwd / "stdout.log"
+    with open(log, "wb") as out:
+        proc = subprocess.Popen([str(exe)], cwd=str(cwd), stdout=out, stderr=subprocess.STDOUT)
+        t0 = time.time()
+        try:
+            while True:
+                text = log.read_text(errors="replace")
+                if f"# Step {step}\n" in text:
+                    break
+                if proc.poll() is not None:
+                    pytest.fail(f"{exe.name} exited with {proc.returncode} before step {step}:\n{text[-2000:]}")
+                if time.time() - t0 > timeout:
+                    pytest.fail(f"{exe.name}: step {step} not reached in {timeout} s:\n{text[-2000:]}")
+                time.sleep(0.05)
+        finally:
+            proc.kill()
+            proc.wait()
+    text = log.read_text(errors="replace")
+    return text[:text.index(f"# Step {step}\n")]
+
+
+def parse(text: str):
+    steps, cur = [], None
+    for line in text.splitlines():
+        if line.startswith("# Step "):
+            cur = {"newton": [], "gmres": []}
+            steps.append(cur)
+        elif cur is not None:
+            m = NEWTON.match(line)
+            if m:
+                cur["newton"].append((int(m.group(1)), float(m.group(2))))
+                continue
+            m = GMRES.match(line)
+            if m:
+                cur["gmres"].append((int(m.group(1)), float(m.group(2))))
+    return steps
+
+
+def test_unmodified_main_links_against_the_product_and_matches_the_reference(tmp_path):
+    for exe in (REF_EXE, OUR_EXE):
+        if not exe.exists():
+            pytest.fail(f"{exe} is missing: run __graft_entry__.build() where /root/reference exists")
+    # the drop-in executable holds none of the hot path itself: those symbols resolve into libdedflow_b200.so
+    undefined = subprocess.run(["nm", "-D", "--undefined-only", str(OUR_EXE)], capture_output=True, text=True).stdout
+    for sym in ("CSRAttrCreate", "ColorMeshTet", "AssembleSystemTet", "AssembleSystemTetFace", "KrylovSolve", "DirichletApplyMat",
+                "MatrixCreateTypeFS", "KrylovCreateGMRES"):
+        assert re.search(rf"\bU {sym}\b", undefined), sym
+    mesh = boxmesh.make_box(12)
+    N = mesh.num_node
+    outs, files = {}, {}
+    for name, exe in (("ref", REF_EXE), ("b200", OUR_EXE)):
+        d = tmp_path / name
+        d.mkdir()
+        h5flat.write_mesh(d / "box.h5", mesh)
+        outs[name] = parse(run_until_step(exe, d, 11))
+        files[name] = {f: h5flat.read(d / f) for f in ("sol.0.h5", "sol.10.h5")}
+    ref, ours = outs["ref"], outs["b200"]
+    assert len(ref) == len(ours) == 10
+    scale = max(v for _, v in ref[0]["newton"])
+    for s, (r, o) in enumerate(zip(ref, ours)):
+        assert [k for k, _ in r["newton"]] == [k for k, _ in o["newton"]], f"step {s + 1}: different Newton iteration count"
+        for (k, a), (_, b) in zip(r["newton"], o["newton"]):
+            assert abs(a - b) <= 1e-8 * max(scale, abs(a)), (s + 1, k, a, b)
+        assert [k for k, _ in r["gmres"]] == [k for k, _ in o["gmres"]], f"step {s + 1}: different GMRES iteration counts"
+        for (k, a), (_, b) in zip(r["gmres"], o["gmres"]):
+            assert abs(a - b) <= 2e-4 * abs(a) + 1e-300, (s + 1, k, a, b)          # 5 printed digits
+    # solution files: the initial condition bit for bit, the state after 10 steps to the time-step parity bar
+    for f in ("sol.0.h5", "sol.10.h5"):
+        assert sorted(files["ref"][f]) == sorted(files["b200"][f])
+    for k, v in files["ref"]["sol.0.h5"].items():
+        assert np.array_equal(v, files["b200"]["sol.0.h5"][k]), k
+    assert sorted(files["ref"]["sol.10.h5"]) == ["T", "dT", "dphi", "du", "p", "phi", "u"]
+    for k, v in files["ref"]["sol.10.h5"].items():
+        w = files["b200"]["sol.10.h5"][k]
+        assert v.shape == w.shape and v.size in (N, 3 * N)
+        assert np.abs(v - w).max() <= 1e-7 * max(np.abs(v).max(), 1e-12), k
