@@ -599,6 +599,7 @@ def main():
     ap.add_argument("--timesteps", type=int, default=0,
                     help="run BASELINE configs[4] instead: this many time steps with Newton reassembly (see run_timesteps)")
     ap.add_argument("--fixed-m", action="store_true", help="N > 1: keep --m (strong scaling) instead of growing the mesh with N")
+    ap.add_argument("--owner", default="slab", choices=["slab", "rcb"], help="N > 1: node ownership (z-slabs or coordinate bisection)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling blocks (16M-tet mesh; 64M at 8 GPUs)")
     ap.add_argument("--strong64", action="store_true", help="N = 1: also run the 64M-tet mesh on one GPU (about a minute)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the embedded parity check against the oracle")

@@ -37,6 +37,34 @@ def slab_owner(mesh, world: int) -> np.ndarray:
     return plane_owner[k]
 
 
+def coordinate_owner(mesh, world: int) -> np.ndarray:
+    """Owner of every node by recursive coordinate bisection of the node coordinates: works for ANY mesh and node numbering
+    (unstructured, renumbered), unlike slab_owner.  The node set is cut along its longest extent into two parts whose sizes
+    are proportional to the ranks they receive (world need not be a power of two); ties are broken by the other two
+    coordinates, then by node id: deterministic, and the same geometric parts whatever the numbering.  Compact parts with small surfaces are what the reference's METIS_PartMeshNodal call is after
+    (src/partition.c:16-77; METIS itself is not available here)."""
+    xg = np.asarray(mesh.xg, np.float64).reshape(-1, 3)
+    owner = np.zeros(xg.shape[0], np.int32)
+    stack = [(np.arange(xg.shape[0]), 0, world)]
+    while stack:
+        ids, r0, nr = stack.pop()
+        if nr == 1 or ids.size == 0:
+            owner[ids] = r0
+            continue
+        n1 = nr // 2
+        ext = xg[ids].max(axis=0) - xg[ids].min(axis=0)
+        axis = int(np.argmax(ext))
+        b, c = (axis + 1) % 3, (axis + 2) % 3   # ties on the cut coordinate (grid planes) are broken geometrically, then by id
+        order = ids[np.lexsort((ids, xg[ids, c], xg[ids, b], xg[ids, axis]))]
+        cut = int(round(ids.size * n1 / nr))
+        stack.append((order[:cut], r0, n1))
+        stack.append((order[cut:], r0 + n1, nr - n1))
+    return owner
+
+
+OWNERS = {"slab": slab_owner, "rcb": coordinate_owner}
+
+
 @dataclass
 class LocalMesh:
     rank: int
@@ -371,12 +399,12 @@ def gather_owned(lm, v_local, dist, torch):
     return t.cpu().numpy()
 
 
-def bench_parity(dist, torch, rank, world, local_rank, owner_fn=None, m=20):
+def bench_parity(dist, torch, rank, world, local_rank, owner_fn=None, m=20, mesh=None, label=None):
     """The embedded parity check of `bench.py --gpus N`: BASELINE configs[0] (m=20, 48,000 tets) split over ALL N ranks, the
     same collectives mode as the timed run (peer memory when available), one assembly + solve, gathered and compared on rank 0
     with the single-domain CPU oracle.  Bars: F <= 1e-12, dx and residual history <= 1e-10, identical iteration count."""
     from . import boxmesh
-    mesh = boxmesh.make_box(m)
+    mesh = mesh if mesh is not None else boxmesh.make_box(m)
     Ng = mesh.num_node
     npart = (owner_fn or slab_owner)(mesh, world)
     lm = partition(mesh, npart, rank, world)
@@ -393,7 +421,8 @@ def bench_parity(dist, torch, rank, world, local_rank, owner_fn=None, m=20):
     Fg = gather_owned(lm, F.cpu().numpy(), dist, torch)
     xg = gather_owned(lm, dx.cpu().numpy(), dist, torch)
     ghost = float(np.abs(lm.localize(xg)[:4 * N] - dx.cpu().numpy()[:4 * N]).max())   # ghosts of the solution after the final halo
-    out = {"mesh": f"Kuhn box m={m} ({mesh.num_tet} tets) over {world} ranks", "collectives": "peer-memory" if fs.p2p else "nccl",
+    out = {"mesh": f"{label or f'Kuhn box m={m}'} ({mesh.num_tet} tets) over {world} ranks, "
+                   f"{(owner_fn or slab_owner).__name__}", "collectives": "peer-memory" if fs.p2p else "nccl",
            "checker": "oracle/oracle.c (CPU, single domain)"}
     ok = True
     if rank == 0:
@@ -575,6 +604,14 @@ def bench_main(args, rank, world, local_rank, B=None):
     parity = None
     if not getattr(args, "no_parity", False):
         parity = bench_parity(dist, torch, rank, world, local_rank)
+        # the same on an UNSTRUCTURED mesh (ragged rows, arbitrary numbering) split by coordinate bisection
+        try:
+            dmesh = boxmesh.delaunay_cube(2400, 120)
+        except ImportError:
+            dmesh = None
+        if dmesh is not None:
+            p2 = bench_parity(dist, torch, rank, world, local_rank, owner_fn=coordinate_owner, mesh=dmesh, label="Delaunay cube")
+            parity = {"box": parity, "delaunay": p2, "ok": bool(parity["ok"] and p2["ok"])}
         if not parity["ok"]:
             if rank == 0:
                 print("bench.py: embedded parity check FAILED: " + json.dumps(parity), file=sys.stderr)
@@ -586,7 +623,8 @@ def bench_main(args, rank, world, local_rank, B=None):
     # on one GPU; strong scaling (--fixed-m and the strong blocks) runs the reference's stopping rule unchanged.
     fixed_its = None if args.fixed_m else 40
     mesh = boxmesh.make_box(m)
-    r = _bench_case(B, args, dist, torch, dlib, mesh, rank, world, local_rank, fixed_its, args.steps, args.warmup, True)
+    r = _bench_case(B, args, dist, torch, dlib, mesh, rank, world, local_rank, fixed_its, args.steps, args.warmup, True,
+                    owner_fn=OWNERS[getattr(args, "owner", "slab")])
     del mesh
     strong = {}
     if not args.fixed_m and not getattr(args, "no_strong", False) and args.m == 55:
@@ -606,7 +644,7 @@ def bench_main(args, rank, world, local_rank, B=None):
             "metric": B.METRIC, "value": Eg / (r["ms"] * 1e-3), "unit": B.UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "strong" if args.fixed_m else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"Kuhn box m={m}: {Eg} tets, {Ng} nodes over {world} GPUs (z-slab node ownership, ghost elements "
+            "config": {"workload": f"Kuhn box m={m}: {Eg} tets, {Ng} nodes over {world} GPUs ({getattr(args, 'owner', 'slab')} node ownership, ghost elements "
                                    f"recomputed; halo + all-reduces {'fused into the Krylov kernels over NVLink peer memory' if r['p2p'] else 'by NCCL'}); "
                                    f"step = AssembleSystem(F)+AssembleSystem(J)+KrylovSolve ({its} GMRES iterations"
                                    f"{', pinned: weak scaling keeps per-GPU work fixed' if fixed_its else ', reference stopping rule'}), state B",

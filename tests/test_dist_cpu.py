@@ -84,14 +84,21 @@ def _halo(lm, x):
         x[3 * n + rn] = rb[:, 3].numpy()
 
 
+def _make_mesh(m):
+    """m > 0: Kuhn box split into z-slabs; m == 0: the unstructured Delaunay cube split by coordinate bisection"""
+    if m > 0:
+        return boxmesh.make_box(m), ddist.slab_owner
+    return boxmesh.delaunay_cube(), ddist.coordinate_owner
+
+
 def _worker(rank, world, port, m, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import pyoracle
     O = pyoracle.get()
-    mesh = boxmesh.make_box(m)
+    mesh, owner_fn = _make_mesh(m)
     Ng = mesh.num_node
-    lm = ddist.partition(mesh, ddist.slab_owner(mesh, world), rank, world)
+    lm = ddist.partition(mesh, owner_fn(mesh, world), rank, world)
     wg_g, dwg_g = boxmesh.state_random(Ng)
     wg, dwg = lm.localize(wg_g), lm.localize(dwg_g)
     N, no = lm.num_node, lm.n_own
@@ -188,9 +195,45 @@ def _worker(rank, world, port, m, q):
     dist.destroy_process_group()
 
 
+def test_coordinate_owner_partitions_any_mesh():
+    """coordinate bisection: balanced, deterministic, usable on the unstructured mesh and on a RENUMBERED box (where the z-slab
+    rule, which reads the node id, would scatter every rank over the whole domain); partition invariants hold"""
+    mesh = boxmesh.delaunay_cube()
+    for world in (2, 3, 8):
+        npart = ddist.coordinate_owner(mesh, world)
+        cnt = np.bincount(npart, minlength=world)
+        assert cnt.max() - cnt.min() <= 1 and np.array_equal(npart, ddist.coordinate_owner(mesh, world))
+        lms = [ddist.partition(mesh, npart, r, world) for r in range(world)]
+        assert sum(lm.n_own for lm in lms) == mesh.num_node
+        for lm in lms:
+            assert np.array_equal(lm.nodes_g[lm.ien], mesh.ien[lm.elems_g])
+            touched = np.zeros(lm.num_node, bool)
+            touched[np.unique(lm.ien[(lm.ien >= lm.n_own).any(axis=1)])] = True
+            assert not touched[:lm.n_interior].any() and touched[lm.n_interior:lm.n_own].all()
+            for qi, q in enumerate(lm.neighbors):
+                snd = lm.nodes_g[lm.send_nodes[lm.send_offset[qi]:lm.send_offset[qi + 1]]]
+                other = lms[q]
+                ri = list(other.neighbors).index(lm.rank)
+                assert np.array_equal(snd, other.nodes_g[other.recv_nodes[other.recv_offset[ri]:other.recv_offset[ri + 1]]])
+    box = boxmesh.make_box(6)
+    perm = np.random.default_rng(1).permutation(box.num_node)          # renumber the nodes
+    inv = np.argsort(perm)
+    import copy
+    ren = copy.copy(box)
+    ren.xg = np.ascontiguousarray(box.xg[perm])
+    ren.ien = np.ascontiguousarray(inv[box.ien].astype(np.int32))
+    o_box, o_ren = ddist.coordinate_owner(box, 4), ddist.coordinate_owner(ren, 4)
+    # same geometric parts whatever the numbering: halo sizes stay those of compact blocks
+    halo = lambda mesh_, o: sum(ddist.partition(mesh_, o, r, 4, weak_group=99, bc_groups=()).recv_nodes.size for r in range(4))
+    assert np.bincount(o_ren).tolist() == np.bincount(o_box).tolist()
+    assert np.array_equal(o_ren, o_box[perm])                      # the same geometric parts
+    assert halo(ren, o_ren) == halo(box, o_box)
+
+
 @pytest.mark.timeout(300)
-def test_two_rank_gloo_solve_matches_single_domain_oracle(oracle):
-    m, world = 6, 2
+@pytest.mark.parametrize("m", [6, 0])
+def test_two_rank_gloo_solve_matches_single_domain_oracle(oracle, m):
+    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -203,7 +246,7 @@ def test_two_rank_gloo_solve_matches_single_domain_oracle(oracle):
         assert p.exitcode == 0
     # single-domain oracle
     from test_gpu_parity import oracle_system
-    mesh = boxmesh.make_box(m)
+    mesh, _ = _make_mesh(m)
     Ng = mesh.num_node
     wg, dwg = boxmesh.state_random(Ng)
     ref = oracle_system(oracle, mesh, wg, dwg)
