@@ -752,6 +752,7 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
   __shared__ f64 smj[8][JT];
   __shared__ f64 hsum[P2P_ACAP];
   __shared__ f64 h_s[128], gv_s[256], tc_s[128];   // staged inputs of the previous step's Givens update (peer-memory mode)
+  __shared__ f64 slot_s[P2P_MAXR * P2P_ACAP];      // the ranks' partial dots as they arrive in the mailbox
   const int ngrp = gridDim.y, gbase = ncol / ngrp, grem = ncol - gbase * ngrp;
   const int j0 = blockIdx.y * gbase + min((int)blockIdx.y, grem);
   const int nj = gbase + ((int)blockIdx.y < grem ? 1 : 0);
@@ -817,19 +818,25 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
     if (soff_prev) {
       const int itp = ncol - 2;   // the previous iteration
       gmres_step_stage(itp, hcol_prev, U.gv, U.tailc, h_s, gv_s, tc_s);
+      const unsigned long long sp = pv->seq_base[0] + soff_prev;
+      if ((int)threadIdx.x < R) smj[0][threadIdx.x] = ll_load(pv, pv->mbox_local + p2p_b_ll(R, (int)(sp & 1ull), threadIdx.x), (unsigned)sp);
       __syncthreads();
       if (threadIdx.x == 0) {
-        const unsigned long long sp = pv->seq_base[0] + soff_prev;
-        const int parp = (int)(sp & 1ull);
         f64 nrm2 = 0.0;
-        for (int r = 0; r < R; r++) nrm2 += ll_load(pv, pv->mbox_local + p2p_b_ll(R, parp, r), (unsigned)sp);
+        for (int r = 0; r < R; r++) nrm2 += smj[0][r];
         U.S->nrm2_live = nrm2;
         gmres_step_dev(itp, U.S, hcol_prev, U.gv, U.beta, U.tailc, U.res_hist, U.qs, h_s, gv_s, tc_s);
       }
     }
+    // all slots are polled in parallel (one thread per (rank, column)), then summed in rank order
+    for (int t = threadIdx.x; t < R * ncol; t += 256) {
+      const int r = t / ncol, j = t - r * ncol;
+      slot_s[r * P2P_ACAP + j] = ll_load(pv, pv->mbox_local + p2p_a_ll(R, par, r, j), (unsigned)seq);
+    }
+    __syncthreads();
     for (int j = threadIdx.x; j < ncol; j += 256) {
       f64 d = 0.0;
-      for (int r = 0; r < R; r++) d += ll_load(pv, pv->mbox_local + p2p_a_ll(R, par, r, j), (unsigned)seq);
+      for (int r = 0; r < R; r++) d += slot_s[r * P2P_ACAP + j];
       h[j] = d;
     }
   }
@@ -885,7 +892,6 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
   const int lane = threadIdx.x & 31;
   const size_t warp0 = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5, nwarp = ((size_t)gridDim.x * 256) >> 5;
   f64 ss = 0.0;
-  bool pushed = false;
   const int tgt_base = pv ? pv->tgt_base : 0, tgt_n = pv ? pv->tgt_n : 0;
   // The multi-dot has just swept the rows in ASCENDING order, so the highest rows of every column are what the 126 MB L2
   // still holds: sweep DESCENDING here (and leave the lowest rows behind for the next multi-dot's ascending sweep).
@@ -929,16 +935,21 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
       const double2 v = half == 0 ? pc_half(pcrec + (size_t)node * PCREC, 0, wn.x, wn.y, ox, oy)
                                   : pc_half(pcrec + (size_t)node * PCREC, 1, ox, oy, wn.x, wn.y);
       z2[i] = v;
-      if (pv) pushed |= push_half(pv, tgt_base, tgt_n, node, half, v);
+      if (pv) push_half(pv, tgt_base, tgt_n, node, half, v);
     }
   }
-  if (pv) {
-    if (pushed) __threadfence_system();   // this thread's halo stores are visible on the peers before the block joins the election
-    push_flag(pv, hoff);
-  }
+  // Halo stores need no fence of their own here (a system-scope fence per pushing thread measured +6 us on the kernel): they are
+  // ordered before this block's arrival in the election below (barrier + gpu-scope fence + atomic, last_block()), and the block
+  // that ends up last issues ONE system-scope fence before it raises the halo flags -- fences are cumulative, so every store
+  // that happens-before it is visible to the peer that acquires the flag.  (Same protocol as NCCL's: all workers store, a
+  // barrier, one thread fences and posts.)  ONE election serves the norm reduction and the halo.
   f64 r = block_sum_256(ss, sm);
   if (threadIdx.x == 0) part[blockIdx.x] = r;
   if (!last_block(ctr, gridDim.x)) return;
+  if (pv && (int)threadIdx.x < pv->n_nbr) {   // every block has pushed and fenced: this mat-vec's halo is complete on the neighbours
+    __threadfence_system();
+    p2p_signal(pv->mbox_peer[pv->nbr[threadIdx.x]] + p2p_h_flag(pv->nranks, pv->rank), pv->seq_base[1] + hoff);
+  }
   f64 s = 0.0;
   for (int c = threadIdx.x; c < (int)gridDim.x; c += 256) s += __ldcg(part + c);
   s = block_sum_256(s, sm);
