@@ -284,6 +284,7 @@ def run_ours(args, rank, world):
     torch.cuda.synchronize()
     setup_s = time.time() - t0
     if args.timesteps > 0:
+        fs.set_preconditioner(args.pc)
         return run_timesteps(args, fs, mesh, lambda t: t, 1, setup_s)
     Z = fs.nnz
     wg, dwg = boxmesh.state_random(N)
@@ -576,7 +577,8 @@ def run_timesteps(args, fs, mesh_or_local, localize, world, setup_s, dist=None, 
                 "data": "synthetic",
                 "config": {"workload": f"BASELINE configs[4]: {args.timesteps} time steps on the Kuhn box m={args.m} ({Eg} tets, {Ng} nodes, "
                                        f"4 live DOF/node) from the reference's initial condition, reassembly of F and J in every Newton "
-                                       f"iteration; a step = one Newton iteration", "l2": "working set exceeds the 126 MB L2"},
+                                       f"iteration; a step = one Newton iteration", "preconditioner": getattr(args, "pc", "jacobi"),
+                           "l2": "working set exceeds the 126 MB L2"},
                 "clocks": clocks,
                 "breakdown": {"time_steps": args.timesteps, "newton_iterations": newton, "gmres_iterations": gmres,
                               "s_per_time_step": ms * 1e-3 / args.timesteps, "setup_s": setup_s,
@@ -599,6 +601,8 @@ def main():
     ap.add_argument("--timesteps", type=int, default=0,
                     help="run BASELINE configs[4] instead: this many time steps with Newton reassembly (see run_timesteps)")
     ap.add_argument("--fixed-m", action="store_true", help="N > 1: keep --m (strong scaling) instead of growing the mesh with N")
+    ap.add_argument("--pc", default="jacobi", choices=["jacobi", "schur2"],
+                    help="--timesteps on one GPU: the reference's block-Jacobi (default) or the opt-in two-level Schur-complement preconditioner")
     ap.add_argument("--owner", default="slab", choices=["slab", "rcb"], help="N > 1: node ownership (z-slabs or coordinate bisection)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling blocks (16M-tet mesh; 64M at 8 GPUs)")
     ap.add_argument("--strong64", action="store_true", help="N = 1: also run the 64M-tet mesh on one GPU (about a minute)")

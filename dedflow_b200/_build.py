@@ -15,7 +15,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "_obj"
 LIB = PKG / "libdedflow_b200.so"
-SOURCES = ["setup.cu", "color.cu", "assemble.cu", "solve.cu", "newton.cu", "compat.cu", "dist.cu"]
+SOURCES = ["setup.cu", "color.cu", "assemble.cu", "solve.cu", "pc2.cu", "newton.cu", "compat.cu", "dist.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

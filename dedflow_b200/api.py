@@ -161,12 +161,32 @@ class FlowSystem:
     def pc_apply(self, x, y):
         _lib.check(self.L.dfb_pc_apply(self.N, _p(self.dinv00), _p(self.dinv11), _p(x), _p(y), self._stream()), "dfb_pc_apply")
 
-    def krylov_solve(self, dx, F):
-        """KrylovSolve(ksp, J, dx, F).  Returns (iterations, residual history |beta_k|, k = 0..iterations)."""
+    def _workspace(self):
         if self.gmres is None:
             ws = C.c_void_p()
             _lib.check(self.L.dfb_gmres_create(C.byref(ws), self.N, self.max_iter), "dfb_gmres_create")
             self.gmres = ws
+        return self.gmres
+
+    def set_preconditioner(self, kind="jacobi", agg_cells=4, cheb_degree=10):
+        """"jacobi": the reference's block-Jacobi (default, krylov.c:439-452).  "schur2": the opt-in two-level Schur-complement
+        preconditioner (the slot the reference reserves for AMGX on the pressure block, pc.c:160-235; csrc/pc2.cu)."""
+        ws = self._workspace()
+        if kind == "jacobi":
+            _lib.check(self.L.dfb_gmres_set_pc2(ws, None), "dfb_gmres_set_pc2")
+            return
+        if kind != "schur2":
+            raise ValueError(kind)
+        if getattr(self, "pc2", None) is None:
+            pc = C.c_void_p()
+            _lib.check(self.L.dfb_pc2_create(C.byref(pc), self.N, _p(self.row_ptr), _p(self.col_ind), _p(self.xg), agg_cells,
+                                             cheb_degree, self._stream()), "dfb_pc2_create")
+            self.pc2 = pc
+        _lib.check(self.L.dfb_gmres_set_pc2(ws, self.pc2), "dfb_gmres_set_pc2")
+
+    def krylov_solve(self, dx, F):
+        """KrylovSolve(ksp, J, dx, F).  Returns (iterations, residual history |beta_k|, k = 0..iterations)."""
+        self._workspace()
         iters = C.c_int(0)
         hist = np.zeros(self.max_iter + 1)
         _lib.check(self.L.dfb_gmres_solve(self.gmres, self.N, _p(self.row_ptr), _p(self.col_ind), *[_p(a) for a in self.blocks()],
@@ -225,6 +245,9 @@ class FlowSystem:
         if self.gmres is not None:
             self.L.dfb_gmres_destroy(self.gmres)
             self.gmres = None
+        if getattr(self, "pc2", None) is not None:
+            self.L.dfb_pc2_destroy(self.pc2)
+            self.pc2 = None
 
     def __del__(self):
         try:

@@ -20,6 +20,12 @@ extern std::atomic<long long> g_launches;
 
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+}  // namespace dfb
+struct dfb_pc2;
+// one application of the two-level Schur-complement preconditioner (pc2.cu) on interleaved vectors: z = P2^-1 w
+int pc2_apply_aos(const dfb_pc2* P, const double* A10, const double* w, double* z, cudaStream_t st);
+namespace dfb {
+
 #define DFB_CUDA(expr)                                                                        \
   do {                                                                                        \
     cudaError_t _e = (expr);                                                                  \
@@ -75,7 +81,7 @@ int num_sms();
 // dfb_set_option(): no entry point calls getenv on its launch path, and tests / A-B scripts switch variants inside one process
 // without touching the environment.  Keys are the environment names (DFB_J_VARIANT=pairs|pull|fused, DFB_J_PAIR_ROWS=8|16,
 // DFB_J_PAIR_ORDER=morton|natural, DFB_J_PULL_PLAIN=0|1, DFB_F_VARIANT=patch|scratch, DFB_F_PATCH_CTAS=2|3, DFB_SPMV_G=4|8|16|32, DFB_SPMV_TMA=0|1,
-// DFB_KRYLOV_TMA=0|1, DFB_GRAPH=0|1, DFB_PROFILE=0|1|2, DFB_ASSEMBLE_MODE=gather|atomic|colored, DFB_VERBOSE=0|1).
+// DFB_KRYLOV_TMA=0|1, DFB_GRAPH=0|1, DFB_PROFILE=0|1|2, DFB_ASSEMBLE_MODE=gather|atomic|colored, DFB_VERBOSE=0|1, DFB_PC=jacobi|schur2, DFB_PC_AGG=2..16, DFB_PC_DEGREE=1..64).
 struct Options {
   int j_variant = 2;        // 0 pull, 1 fused, 2 pairs
   int j_pair_rows = 8;
@@ -91,6 +97,8 @@ struct Options {
   int profile = 0;
   int assemble_mode = DFB_MODE_GATHER;
   int verbose = 0;
+  int pc = 0;               // drop-in KrylovSolve: 0 the reference's block-Jacobi, 1 two-level Schur complement (pc2.cu)
+  int pc_agg = 4, pc_degree = 10;
 };
 Options& options();
 

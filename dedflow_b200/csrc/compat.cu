@@ -236,6 +236,8 @@ struct KspBox {
   Krylov pub;
   dfb_gmres* ws = nullptr;
   int ws_nodes = 0, ws_maxit = 0;
+  dfb_pc2* pc2 = nullptr;          // DFB_PC=schur2: the opt-in two-level Schur-complement preconditioner (the reference's AMGX slot)
+  const int* pc2_row_ptr = nullptr;
   std::vector<f64> hist;
   int iters = -1;
 };
@@ -528,6 +530,24 @@ static void gmres_solve(Matrix* A, f64* x, f64* b, void* ctx) {
     k->ws_nodes = N; k->ws_maxit = ksp->max_iter;
     ksp->ksp_ctx = k->ws;
     ksp->ksp_ctx_size = dfb_gmres_bytes(k->ws);
+  }
+  if (options().pc == 1) {   // the slot krylov.c:449 leaves commented out (PCCreateAMGX on the pressure block)
+    if (!k->pc2 || k->pc2_row_ptr != spy->row_ptr) {
+      if (k->pc2) dfb_pc2_destroy(k->pc2);
+      k->pc2 = nullptr;
+      const f64* xg = nullptr;   // the coordinates come from the mesh this pattern was built for (CSRAttrCreate(mesh))
+      {
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (auto& kv : g_plans)
+          if (kv.second.row_ptr == spy->row_ptr) xg = static_cast<const Mesh3D*>(kv.first)->device->xg;
+      }
+      if (!xg) fprintf(stderr, "KrylovSolve: DFB_PC=schur2 needs the mesh of this matrix (assemble once first); using block-Jacobi\n");
+      else if (core_ok(dfb_pc2_create(&k->pc2, N, spy->row_ptr, spy->col_ind, xg, options().pc_agg, options().pc_degree, nullptr), "dfb_pc2_create"))
+        k->pc2_row_ptr = spy->row_ptr;
+    }
+    core_ok(dfb_gmres_set_pc2(k->ws, k->pc2), "dfb_gmres_set_pc2");
+  } else {
+    core_ok(dfb_gmres_set_pc2(k->ws, nullptr), "dfb_gmres_set_pc2");
   }
   PCDecomposition* d = static_cast<PCDecomposition*>(static_cast<PC*>(ksp->pc)->data);
   const f64* dinv00 = static_cast<const f64*>(static_cast<PCJacobi*>(d->pc[0]->data)->diag);
@@ -905,6 +925,7 @@ void KrylovDestroy(Krylov* ksp) {
   KspBox* k = reinterpret_cast<KspBox*>(ksp);
   PCDestroy(static_cast<PC*>(ksp->pc));
   if (k->ws) dfb_gmres_destroy(k->ws);
+  if (k->pc2) dfb_pc2_destroy(k->pc2);
   delete k;
 }
 

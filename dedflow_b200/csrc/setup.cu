@@ -45,6 +45,9 @@ static bool apply_option(Options& o, const char* key, const char* v) {
   if (is("DFB_GRAPH")) { o.graph = atoi(v) != 0; return true; }
   if (is("DFB_PROFILE")) { o.profile = atoi(v); return true; }
   if (is("DFB_VERBOSE")) { o.verbose = atoi(v) != 0; return true; }
+  if (is("DFB_PC")) { o.pc = !strcmp(v, "schur2") ? 1 : 0; return true; }
+  if (is("DFB_PC_AGG")) { const int a = atoi(v); o.pc_agg = (a >= 2 && a <= 16) ? a : 4; return true; }
+  if (is("DFB_PC_DEGREE")) { const int d = atoi(v); o.pc_degree = (d >= 1 && d <= 64) ? d : 10; return true; }
   if (is("DFB_ASSEMBLE_MODE")) {
     o.assemble_mode = !strcmp(v, "atomic") ? DFB_MODE_ATOMIC : (!strcmp(v, "colored") ? DFB_MODE_COLORED : DFB_MODE_GATHER);
     return true;
@@ -56,7 +59,7 @@ Options& options() {
   static Options o = [] {
     Options t;
     static const char* keys[] = {"DFB_J_VARIANT", "DFB_J_PAIR_ROWS", "DFB_J_PAIR_ORDER", "DFB_J_PULL_PLAIN", "DFB_F_VARIANT", "DFB_F_PATCH_CTAS", "DFB_SPMV_G",
-                                 "DFB_SPMV_TMA", "DFB_SPMV_PEER_SPLIT", "DFB_KRYLOV_TMA", "DFB_GRAPH", "DFB_PROFILE", "DFB_VERBOSE", "DFB_ASSEMBLE_MODE"};
+                                 "DFB_SPMV_TMA", "DFB_SPMV_PEER_SPLIT", "DFB_KRYLOV_TMA", "DFB_GRAPH", "DFB_PROFILE", "DFB_VERBOSE", "DFB_ASSEMBLE_MODE", "DFB_PC", "DFB_PC_AGG", "DFB_PC_DEGREE"};
     for (const char* k : keys) {
       const char* v = getenv(k);
       if (v && *v) apply_option(t, k, v);

@@ -928,7 +928,9 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
       w2[i] = wn;
       ss = fma(wn.y, wn.y, fma(wn.x, wn.x, ss));
     }
-    // z~ = P^-1 w~ for the node this lane shares with its neighbour lane (pair index i: node i >> 1, half i & 1)
+    // z~ = P^-1 w~ for the node this lane shares with its neighbour lane (pair index i: node i >> 1, half i & 1);
+    // pcrec == NULL: another preconditioner follows as its own launches (pc2.cu)
+    if (!pcrec) continue;   // kernel-uniform
     const f64 ox = __shfl_xor_sync(FULLM, wn.x, 1), oy = __shfl_xor_sync(FULLM, wn.y, 1);
     if (ok) {
       const int half = (int)(i & 1), node = (int)(i >> 1);
@@ -1017,6 +1019,15 @@ __global__ void k_pack_live(int n_own, const f64* __restrict__ v, size_t poff, f
   const size_t i = t >> 2;
   const int c = (int)(t & 3);
   out[t] = c < 3 ? v[i * 3 + c] : v[poff + i];
+}
+
+// x (ABI layout) += d (interleaved live part)
+__global__ void k_add_live_aos(int n_own, const f64* __restrict__ d, f64* __restrict__ x, size_t poff) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)4 * n_own) return;
+  const size_t i = t >> 2;
+  const int c = (int)(t & 3);
+  if (c < 3) x[i * 3 + c] += d[t]; else x[poff + i] += d[t];
 }
 
 // x_tail += coef * b_tail
@@ -1188,17 +1199,18 @@ struct dfb_gmres {
   int n_interior = 0;
   dfb_parallel_ops par = {0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool parallel = false;
+  dfb_pc2* pc2 = nullptr;   // opt-in two-level Schur-complement preconditioner (pc2.cu); nullptr = the reference's block-Jacobi
   std::string last_profile;   // per-kernel event times of the last solve (DFB_PROFILE != 0), see dfb_gmres_profile
   // CUDA graphs of the 20-iteration chunks between two convergence tests (one GPU), valid for one set of matrix pointers
   struct GraphKey {
-    const void *rp, *ci, *a00, *a01, *a10, *a11, *pv;
+    const void *rp, *ci, *a00, *a01, *a10, *a11, *pv, *pc2;
     int n_own, n_interior, split;
     bool operator==(const GraphKey& o) const {
-      return rp == o.rp && ci == o.ci && a00 == o.a00 && a01 == o.a01 && a10 == o.a10 && a11 == o.a11 && pv == o.pv && n_own == o.n_own &&
-             n_interior == o.n_interior && split == o.split;
+      return rp == o.rp && ci == o.ci && a00 == o.a00 && a01 == o.a01 && a10 == o.a10 && a11 == o.a11 && pv == o.pv && pc2 == o.pc2 &&
+             n_own == o.n_own && n_interior == o.n_interior && split == o.split;
     }
   };
-  GraphKey gkey = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0};
+  GraphKey gkey = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0};
   std::vector<cudaGraphExec_t> gexec;
   cudaStream_t cap_stream = nullptr;
   void drop_graphs() {
@@ -1275,6 +1287,13 @@ void dfb_gmres_destroy(dfb_gmres* w) {
 
 size_t dfb_gmres_bytes(const dfb_gmres* w) { return w ? w->bytes : 0; }
 
+int dfb_gmres_set_pc2(dfb_gmres* w, dfb_pc2* pc) {
+  if (!w) { set_error("dfb_gmres_set_pc2: bad argument"); return DFB_ERR_ARG; }
+  w->pc2 = pc;
+  w->drop_graphs();
+  return DFB_OK;
+}
+
 int dfb_gmres_profile(const dfb_gmres* w, char* buf, int capacity) {
   if (!w || !buf || capacity <= 0) { set_error("dfb_gmres_profile: bad argument"); return DFB_ERR_ARG; }
   snprintf(buf, (size_t)capacity, "%s", w->last_profile.c_str());
@@ -1331,6 +1350,11 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   }
   k_pc_pack<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, dinv00, dinv11, W->pcrec);
   DFB_LAUNCH_CHECK();
+  dfb_pc2* const pc2 = W->pc2;
+  if (pc2) {
+    if (W->parallel) { set_error("dfb_gmres_solve: the two-level preconditioner runs on one GPU only"); return DFB_ERR_ARG; }
+    DFB_CHECK(dfb_pc2_setup(pc2, A00, A01, A10, A11, st));
+  }
   DFB_CUDA(cudaMemsetAsync(W->H, 0, sizeof(f64) * (size_t)ldh * maxit, st));
   // r0 = b - A x  (krylov.c:114-118): x in the ABI layout (its ghosts refreshed by the callbacks), r0 interleaved
   k_pack_live<<<vgrid, 256, 0, st>>>(n_own, d_b, poffN, QCOL(0));
@@ -1365,8 +1389,12 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     k_set_seq_base<<<1, 1, 0, st>>>(ph->d_seq_base, *ph->seq, *ph->hseq);
     DFB_LAUNCH_CHECK();
   }
-  k_pc_apply_aos<<<ceil_div((i64)2 * n_own, 256), 256, 0, st>>>(n_own, W->pcrec, QCOL(0), zvec, pv, 1u);
-  DFB_LAUNCH_CHECK();
+  if (pc2) {
+    DFB_CHECK(pc2_apply_aos(pc2, A10, QCOL(0), zvec, st));
+  } else {
+    k_pc_apply_aos<<<ceil_div((i64)2 * n_own, 256), 256, 0, st>>>(n_own, W->pcrec, QCOL(0), zvec, pv, 1u);
+    DFB_LAUNCH_CHECK();
+  }
 
   int iter = 0;
   bool converged = false;
@@ -1414,10 +1442,15 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     // update + norm + P^-1 (+ Givens step on one GPU; + the fused collectives in peer-memory mode)  (krylov.c:176-183, 229-277)
     prof.begin("update", s);
     k_update<<<ugrid, 256, 0, s>>>(nl, Q, ldq, ncol, W->draw, HCOL(iter), iter ? HCOL(iter - 1) : HCOL(0), w, W->part, W->ctr + 1,
-                                   pv ? 2 : (W->parallel ? 1 : 0), US, W->pcrec, zvec, pv, soff,
+                                   pv ? 2 : (W->parallel ? 1 : 0), US, pc2 ? nullptr : W->pcrec, zvec, pv, soff,
                                    (unsigned)iter + 2u /* the halo of z~_{iter+1} leaves from this kernel */);
     DFB_LAUNCH_CHECK();
     prof.end(s);
+    if (pc2) {
+      prof.begin("pc2 apply", s);
+      DFB_CHECK(pc2_apply_aos(pc2, A10, w, zvec, s));
+      prof.end(s);
+    }
     if (pv) {
       // the norm reduction + Givens step of this iteration are folded into the NEXT update's prologue; they run on their own
       // only when the host needs the residual now (the every-20th test) or the loop ends
@@ -1450,7 +1483,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   // One GPU: the 20 iterations between two convergence tests (60 launches with fixed arguments for a given workspace and
   // matrix) are captured once into a CUDA graph per chunk and replayed -- the launch gaps shrink, the host does one call.
   const bool use_graph = (!W->parallel || pv) && !prof.on && options().graph != 0;
-  const dfb_gmres::GraphKey gkey = {rp, ci, A00, A01, A10, A11, pv, n_own, W->n_interior, options().spmv_peer_split};
+  const dfb_gmres::GraphKey gkey = {rp, ci, A00, A01, A10, A11, pv, pc2, n_own, W->n_interior, options().spmv_peer_split};
   while (!converged && iter < maxit && !peer_err) {
     if (use_graph && iter % 20 == 0 && iter + 20 <= maxit) {
       const size_t chunk = (size_t)iter / 20;
@@ -1469,7 +1502,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
         cudaGraphDestroy(graph);
         DFB_CUDA(ie);
       } else {
-        count_launch(pv ? (options().spmv_peer_split ? 81 : 61) : 60);
+        count_launch(pc2 ? 400 : (pv ? (options().spmv_peer_split ? 81 : 61) : 60));   // (pc2: 20 x (3 + 5 + its Chebyshev steps), approx.)
       }
       DFB_CUDA(cudaGraphLaunch(W->gexec[chunk], st));
       iter += 20;
@@ -1496,7 +1529,12 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     k_combine<<<cgrid, 256, 0, st>>>(nl, Q, ldq, iter, W->ycoef, W->t);
     DFB_LAUNCH_CHECK();
     // x += P^-1 (combination)  (krylov.c:313-319)
-    k_pc_add_live<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, W->pcrec, W->t, d_x, poffN);
+    if (pc2) {
+      DFB_CHECK(pc2_apply_aos(pc2, A10, W->t, zvec, st));
+      k_add_live_aos<<<vgrid, 256, 0, st>>>(n_own, zvec, d_x, poffN);
+    } else {
+      k_pc_add_live<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, W->pcrec, W->t, d_x, poffN);
+    }
     DFB_LAUNCH_CHECK();
     k_axpy_dev<<<ceil_div((i64)tail_n, 256), 256, 0, st>>>(tail_n, W->tail_coef, d_b + (size_t)4 * N, d_x + (size_t)4 * N);
     DFB_LAUNCH_CHECK();

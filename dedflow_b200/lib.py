@@ -28,6 +28,12 @@ _SIGS = {
     "dfb_launch_count": (C.c_longlong, []),
     "dfb_set_option": (ci, [C.c_char_p, C.c_char_p]),
     "dfb_gmres_profile": (ci, [vp, C.c_char_p, ci]),
+    "dfb_pc2_create": (ci, [C.POINTER(vp), ci, vp, vp, vp, ci, ci, vp]),
+    "dfb_pc2_info": (ci, [vp, C.POINTER(ci), C.POINTER(ci)]),
+    "dfb_pc2_setup": (ci, [vp, vp, vp, vp, vp, vp]),
+    "dfb_pc2_apply": (ci, [vp, vp, vp, vp, vp]),
+    "dfb_pc2_destroy": (None, [vp]),
+    "dfb_gmres_set_pc2": (ci, [vp, vp]),
     "dfb_pattern_rows": (ci, [ci, ci, vp, vp, C.POINTER(ci), vp]),
     "dfb_pattern_cols": (ci, [ci, ci, vp, vp, vp, vp]),
     "dfb_pattern_expand": (ci, [ci, vp, vp, ci, ci, vp, vp, vp]),

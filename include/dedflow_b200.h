@@ -50,7 +50,8 @@ int dfb_version(void);
 long long dfb_launch_count(void);
 /* Variant switches (A/B measurements, tests).  `key` is one of the environment names the library reads once at load
  * (DFB_J_VARIANT, DFB_J_PAIR_ROWS, DFB_J_PAIR_ORDER, DFB_J_PULL_PLAIN, DFB_F_VARIANT, DFB_SPMV_G, DFB_SPMV_TMA, DFB_KRYLOV_TMA,
- * DFB_GRAPH, DFB_PROFILE, DFB_VERBOSE, DFB_ASSEMBLE_MODE); no entry point reads the environment on its launch path. */
+ * DFB_GRAPH, DFB_PROFILE, DFB_VERBOSE, DFB_ASSEMBLE_MODE, DFB_PC, DFB_PC_AGG, DFB_PC_DEGREE); no entry point reads the
+ * environment on its launch path. */
 int dfb_set_option(const char* key, const char* value);
 
 /* ------------------------------------------------------------------------------------------
@@ -173,6 +174,24 @@ typedef struct dfb_parallel_ops {
   int (*halo_begin_aos)(double* d_x4, void* stream, void* user);
 } dfb_parallel_ops;
 int dfb_gmres_set_parallel(dfb_gmres* ws, const dfb_parallel_ops* ops);
+/* ------------------------------------------------------------------------------------------
+ * Stronger preconditioner (opt-in; the slot the reference reserves for AMGX on the pressure block, src/pc.c:160-235,
+ * src/krylov.c:392-453, compiled out there): block lower-triangular with an additive two-level approximation of the pressure
+ * Schur complement S = A11 - A10 D^-1 A01 (dedflow_b200/csrc/pc2.cu).  One GPU.
+ *   create: once per mesh (aggregates of agg_cells^3 average node spacings from the coordinates; cheb_degree Chebyshev steps
+ *           on the Galerkin coarse matrix).  d_row_ptr / d_col_ind are borrowed.
+ *   setup : once per solve (the Jacobian changes every Newton iteration); dfb_gmres_solve* calls it when a workspace carries
+ *           the preconditioner (dfb_gmres_set_pc2; NULL restores the reference's block-Jacobi).
+ *   apply : y = P^-1 x on 6N ABI-layout vectors (tests / drop-in PCApply). */
+typedef struct dfb_pc2 dfb_pc2;
+int dfb_pc2_create(dfb_pc2** out, int num_node, const int* d_row_ptr, const int* d_col_ind, const double* d_xg, int agg_cells,
+                   int cheb_degree, void* stream);
+int dfb_pc2_info(const dfb_pc2* pc, int* num_aggregates, int* coarse_nnz);
+int dfb_pc2_setup(dfb_pc2* pc, const double* d_A00, const double* d_A01, const double* d_A10, const double* d_A11, void* stream);
+int dfb_pc2_apply(dfb_pc2* pc, const double* d_A10, const double* d_x, double* d_y, void* stream);
+void dfb_pc2_destroy(dfb_pc2* pc);
+int dfb_gmres_set_pc2(dfb_gmres* ws, dfb_pc2* pc);
+
 /* Solve A x = b (x in/out, b in; both 6N device vectors).  Convergence is tested only when (iter+1)%20==0 against
  * |r| < atol || |r| < (|r0| + 1e-16)*rtol (src/krylov.c:281-290, defect D10).  res_hist (HOST, may be NULL) receives
  * max_iter+1 entries: |beta[k]| for k = 0..iters.  *iters (host, out). */

@@ -234,22 +234,31 @@ def test_oracle_driver_time_step(oracle):
     assert np.array_equal(state[1], state[2])                      # dwgold = dwg
 
 
+def _declared(header):
+    text = re.sub(r"/\*.*?\*/", "", header.read_text(), flags=re.S)
+    text = re.sub(r"typedef[^;{]*\(\s*\*[^;]*;", "", text)          # function-pointer typedefs
+    text = re.sub(r"(struct|enum)\s+\w+\s*\{[^{}]*\}", "", text)    # struct / enum bodies
+    return {d for d in re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", text) if not d.startswith("(")}
+
+
 def test_abi_library_exports_every_declared_symbol():
-    """libdedflow_b200.so loads on a GPU-less host and exports exactly what include/*.h declares."""
+    """the shared libraries load on a GPU-less host and export exactly what include/*.h declares: libdedflow_b200.so the hot path
+    (dedflow_b200.h, dedflow_compat.h), libdedflow_h5flat.so the file interface (dedflow_h5flat.h)"""
+    import ctypes
+    import __graft_entry__
     from dedflow_b200 import _build, lib
     _build.build()
     L = lib.load()
     assert L.dfb_version() >= 100
-    declared = set()
-    for h in (ROOT / "include").glob("*.h"):
-        text = re.sub(r"/\*.*?\*/", "", h.read_text(), flags=re.S)
-        text = re.sub(r"typedef[^;{]*\(\s*\*[^;]*;", "", text)          # function-pointer typedefs
-        text = re.sub(r"(struct|enum)\s+\w+\s*\{[^{}]*\}", "", text)    # struct / enum bodies
-        declared |= set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", text))
-    declared = {d for d in declared if not d.startswith("(")}
+    declared = _declared(ROOT / "include" / "dedflow_b200.h") | _declared(ROOT / "include" / "dedflow_compat.h")
     missing = [d for d in sorted(declared) if not hasattr(L, d)]
     assert not missing, f"declared but not exported: {missing}"
     assert set(lib.exported_symbols()) <= declared
+    __graft_entry__.build_h5flat()
+    H = ctypes.CDLL(str(ROOT / "dedflow_b200" / "libdedflow_h5flat.so"))
+    h5 = _declared(ROOT / "include" / "dedflow_h5flat.h")
+    assert len(h5) == 20 and not [d for d in sorted(h5) if not hasattr(H, d)]
+    assert {p.name for p in (ROOT / "include").glob("*.h")} == {"dedflow_b200.h", "dedflow_compat.h", "dedflow_h5flat.h"}
 
 
 def test_no_cpu_fallback_without_gpu():
