@@ -933,6 +933,7 @@ extern "C" {
 int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, const double* d_dwg, double* d_F,
                      double* d_A00, double* d_A01, double* d_A10, double* d_A11, int mode, int overwrite, void* stream) {
   cudaStream_t st = as_stream(stream);
+  NvtxRange nvtx(d_A00 ? (d_F ? "dfb_assemble_tet F+J" : "dfb_assemble_tet J") : "dfb_assemble_tet F");
   if (!P || !d_xg || !d_wg || !d_dwg) { set_error("dfb_assemble_tet: bad argument"); return DFB_ERR_ARG; }
   const bool doJ = d_A00 != nullptr;
   if (doJ && (!d_A01 || !d_A10 || !d_A11)) { set_error("dfb_assemble_tet: all four sub-block arrays are required"); return DFB_ERR_ARG; }
@@ -949,12 +950,8 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
       if (P->fp_state == 1) {
         const int mn = (P->fp_max_nodes + 1) & ~1;   // even: keeps the 16-byte alignment of what follows the node records
         const size_t smem = sizeof(f64) * ((size_t)mn * FP_SN + (size_t)FP_PE * FP_SE) + sizeof(unsigned short) * ((size_t)4 * FP_PE + mn + 8);
-        static size_t smem_set = 0;   // (monotone high-water mark of an attribute that only ever needs to grow)
-        if (smem > smem_set) {
-          DFB_CUDA(cudaFuncSetAttribute(k_patchF<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          DFB_CUDA(cudaFuncSetAttribute(k_patchF<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          smem_set = smem;
-        }
+        DFB_CHECK(ensure_dynamic_smem((const void*)k_patchF<2>, smem));
+        DFB_CHECK(ensure_dynamic_smem((const void*)k_patchF<3>, smem));
         if (options().f_patch_ctas == 2)
           k_patchF<2><<<P->fp_n_patch, 128, smem, st>>>(N, P->fp_hdr, P->fp_nodes, P->fp_lnode, P->fp_corner, P->fp_cstart, d_xg, d_wg,
                                                         d_dwg, P->fp_part, mn);
@@ -1007,12 +1004,8 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
           const int R = P->pr_rows, ncta = P->pr_n_cta;
 #define DFB_PAIR_LAUNCH(NT, MINB)                                                                                                  \
   do {                                                                                                                             \
-    static size_t set_smem = 0;                                                                                                    \
-    if (smem > set_smem) {                                                                                                         \
-      DFB_CUDA(cudaFuncSetAttribute(k_pairJ<0, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
-      DFB_CUDA(cudaFuncSetAttribute(k_pairJ<1, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
-      set_smem = smem;                                                                                                             \
-    }                                                                                                                              \
+    DFB_CHECK(ensure_dynamic_smem((const void*)k_pairJ<0, NT, MINB>, smem));                                                       \
+    DFB_CHECK(ensure_dynamic_smem((const void*)k_pairJ<1, NT, MINB>, smem));                                                       \
     if (overwrite)                                                                                                                 \
       k_pairJ<1, NT, MINB><<<ncta, NT, smem, st>>>(N, P->n_rows, R, P->pr_grp, P->pr_meta, P->pr_item_ptr, P->pr_contrib,          \
                                                    P->pr_enodes, d_xg, d_wg, P->row_ptr, P->col_ind, d_A00, d_A01, d_A10, d_A11);  \
@@ -1042,11 +1035,7 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
           }
           P->items_rows = P->n_rows;
         }
-        static bool jprep2_attr = false;
-        if (!jprep2_attr) {
-          DFB_CUDA(cudaFuncSetAttribute(k_jprep2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(f64) * 128 * PREC_S)));
-          jprep2_attr = true;
-        }
+        DFB_CHECK(ensure_dynamic_smem((const void*)k_jprep2, sizeof(f64) * 128 * PREC_S));
         k_jprep2<<<ceil_div(E, 128), 128, sizeof(f64) * 128 * PREC_S, st>>>(E, P->ien, d_xg, d_wg, P->prec);
         DFB_LAUNCH_CHECK();
         if (options().j_pull_plain) {   // the unstaged kernel, kept for measurement
@@ -1058,12 +1047,8 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
         } else {
           const int nst = std::min(P->max_cta_elems, PULL_MAX_STAGED);
           const size_t smem = (size_t)std::max(1, nst) * PULL_SREC * sizeof(double2);
-          static size_t smem_set = 0;
-          if (smem > smem_set) {
-            DFB_CUDA(cudaFuncSetAttribute(k_pullJ_staged<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            DFB_CUDA(cudaFuncSetAttribute(k_pullJ_staged<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            smem_set = smem;
-          }
+          DFB_CHECK(ensure_dynamic_smem((const void*)k_pullJ_staged<0>, smem));
+          DFB_CHECK(ensure_dynamic_smem((const void*)k_pullJ_staged<1>, smem));
           const int ncta = ceil_div(P->n_rows, PULL_ROWS);
           if (overwrite)
             k_pullJ_staged<1><<<ncta, 128, smem, st>>>(N, P->n_rows, P->row_item, P->item_meta, P->item_ptr, P->contrib, P->contrib16,
@@ -1101,6 +1086,7 @@ int dfb_assemble_face(const dfb_plan* P, int nf, const int* d_f2e, const int* d_
                       const double* d_wg, const double* d_dwg, double* d_F, double* d_A00, double* d_A01, double* d_A10,
                       double* d_A11, void* stream) {
   cudaStream_t st = as_stream(stream);
+  NvtxRange nvtx("dfb_assemble_face");
   if (!P || nf < 0 || !d_xg || !d_wg || !d_dwg) { set_error("dfb_assemble_face: bad argument"); return DFB_ERR_ARG; }
   if (nf == 0 || (!d_F && !d_A00)) return DFB_OK;
   if (d_A00 && (!d_A01 || !d_A10 || !d_A11)) { set_error("dfb_assemble_face: all four sub-block arrays are required"); return DFB_ERR_ARG; }

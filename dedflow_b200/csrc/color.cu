@@ -96,25 +96,29 @@ int dfb_color_jpl(int N, int E, const int* d_ien, const int* d_weight, int max_c
                   void* stream) {
   cudaStream_t st = as_stream(stream);
   if (N <= 0 || E <= 0 || !d_ien || !d_weight || !d_color || !num_color) { set_error("dfb_color_jpl: bad argument"); return DFB_ERR_ARG; }
-  int *ptr = nullptr, *v2c = nullptr, *lists = nullptr, *counts = nullptr;
-  DFB_CHECK(build_v2c(N, E, d_ien, &ptr, &v2c, st));
-  DFB_CUDA(cudaMalloc(&lists, sizeof(int) * (size_t)E * 2));
-  DFB_CUDA(cudaMalloc(&counts, sizeof(int) * ((size_t)max_color + 1)));
+  // scoped device scratch: released on every return path (the DFB_CUDA / DFB_CHECK macros return early on errors)
+  DevBuf<int> ptr, v2c, lists, counts;
+  {
+    int *p0 = nullptr, *p1 = nullptr;
+    DFB_CHECK(build_v2c(N, E, d_ien, &p0, &p1, st));
+    ptr.p = p0; v2c.p = p1;
+  }
+  DFB_CHECK(lists.alloc((size_t)E * 2));
+  DFB_CHECK(counts.alloc((size_t)max_color + 1));
   DFB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * ((size_t)max_color + 1), st));
   k_init_list<<<ceil_div(E, 256), 256, 0, st>>>(E, lists, d_color);
   DFB_LAUNCH_CHECK();
   int n_active = E, c = 0;
   int* cur = lists;
-  int* nxt = lists + E;
+  int* nxt = lists.p + E;
   for (; c < max_color && n_active > 0; c++) {
-    k_jpl_round<<<ceil_div(n_active, 256), 256, 0, st>>>(n_active, cur, nxt, counts + c, d_ien, ptr, v2c, d_weight,
+    k_jpl_round<<<ceil_div(n_active, 256), 256, 0, st>>>(n_active, cur, nxt, counts.p + c, d_ien, ptr, v2c, d_weight,
                                                         d_color, c);
     DFB_LAUNCH_CHECK();
-    DFB_CUDA(cudaMemcpyAsync(&n_active, counts + c, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DFB_CUDA(cudaMemcpyAsync(&n_active, counts.p + c, sizeof(int), cudaMemcpyDeviceToHost, st));
     DFB_CUDA(cudaStreamSynchronize(st));
     int* t = cur; cur = nxt; nxt = t;
   }
-  cudaFree(ptr); cudaFree(v2c); cudaFree(lists); cudaFree(counts);
   if (n_active > 0) { set_error("dfb_color_jpl: %d elements uncoloured after %d rounds", n_active, max_color); return DFB_ERR_COLOR; }
   *num_color = c;
   return DFB_OK;
@@ -123,29 +127,28 @@ int dfb_color_jpl(int N, int E, const int* d_ien, const int* d_weight, int max_c
 int dfb_color_batches(int E, const int* d_color, int num_color, int* h_batch_offset, int* d_batch_ind, void* stream) {
   cudaStream_t st = as_stream(stream);
   if (E <= 0 || num_color <= 0 || !d_color || !h_batch_offset || !d_batch_ind) { set_error("dfb_color_batches: bad argument"); return DFB_ERR_ARG; }
-  int *keys_out = nullptr, *ids = nullptr, *hist = nullptr;
-  DFB_CUDA(cudaMalloc(&keys_out, sizeof(int) * (size_t)E));
-  DFB_CUDA(cudaMalloc(&ids, sizeof(int) * (size_t)E));
-  DFB_CUDA(cudaMalloc(&hist, sizeof(int) * ((size_t)num_color + 1)));
+  DevBuf<int> keys_out, ids, hist;
+  DevBuf<char> tmp;
+  DFB_CHECK(keys_out.alloc((size_t)E));
+  DFB_CHECK(ids.alloc((size_t)E));
+  DFB_CHECK(hist.alloc((size_t)num_color + 1));
   k_iota<<<ceil_div(E, 256), 256, 0, st>>>(E, ids);
   DFB_LAUNCH_CHECK();
   int bits = 1;
   while ((1 << bits) < num_color) bits++;
   size_t tmp_bytes = 0, tmp2 = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_color, keys_out, ids, d_batch_ind, E, 0, bits, st);
-  cub::DeviceHistogram::HistogramEven(nullptr, tmp2, d_color, hist, num_color + 1, 0, num_color, E, st);
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_color, keys_out.p, ids.p, d_batch_ind, E, 0, bits, st);
+  cub::DeviceHistogram::HistogramEven(nullptr, tmp2, d_color, hist.p, num_color + 1, 0, num_color, E, st);
   if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
-  void* tmp = nullptr;
-  DFB_CUDA(cudaMalloc(&tmp, tmp_bytes));
-  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d_color, keys_out, ids, d_batch_ind, E, 0, bits, st);  // stable
+  DFB_CHECK(tmp.alloc(tmp_bytes));
+  cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, d_color, keys_out.p, ids.p, d_batch_ind, E, 0, bits, st);  // stable
   DFB_LAUNCH_CHECK();
-  cub::DeviceHistogram::HistogramEven(tmp, tmp_bytes, d_color, hist, num_color + 1, 0, num_color, E, st);
+  cub::DeviceHistogram::HistogramEven(tmp.p, tmp_bytes, d_color, hist.p, num_color + 1, 0, num_color, E, st);
   DFB_LAUNCH_CHECK();
-  DFB_CUDA(cudaMemcpyAsync(h_batch_offset + 1, hist, sizeof(int) * (size_t)num_color, cudaMemcpyDeviceToHost, st));
+  DFB_CUDA(cudaMemcpyAsync(h_batch_offset + 1, hist.p, sizeof(int) * (size_t)num_color, cudaMemcpyDeviceToHost, st));
   DFB_CUDA(cudaStreamSynchronize(st));
   h_batch_offset[0] = 0;
   for (int c = 0; c < num_color; c++) h_batch_offset[c + 1] += h_batch_offset[c];
-  cudaFree(tmp); cudaFree(keys_out); cudaFree(ids); cudaFree(hist);
   return DFB_OK;
 }
 

@@ -74,6 +74,17 @@ struct DevBuf {
 };
 inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is process-wide state of a kernel: raise it under a lock and only ever upwards
+// (entry points may be called from several host threads; no function-local static caches).
+int ensure_dynamic_smem(const void* func, size_t bytes);
+
+// NVTX range of one phase of the hot path (the reference has no tracing at all); a no-op unless a tool
+// (nsys, ncu --nvtx) is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name);
+  ~NvtxRange();
+};
+
 // number of SMs of the current device (B200: 148); cached
 int num_sms();
 

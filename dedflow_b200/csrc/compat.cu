@@ -40,6 +40,16 @@ static bool core_ok(int status, const char* what) {
   return false;
 }
 
+// A failed KrylovSolve must not look like a solve that returned dx = 0 (the reference's driver would apply a zero Newton
+// update and carry on): like the reference's CUGUARD / ASSERT (common.h:69-98) the drop-in layer traps, unless the host
+// program opted out with DFB_COMPAT_NO_TRAP=1 and checks dfb_compat_last_history() (< 0: the solve failed) itself.
+static void solve_failed(const char* why) {
+  fprintf(stderr, "dedflow_b200: KrylovSolve failed: %s\n", why);
+  fflush(stderr);
+  const char* e = getenv("DFB_COMPAT_NO_TRAP");
+  if (!(e && *e && *e != '0')) __builtin_trap();
+}
+
 template <typename T>
 static T* host_zeroed(size_t count = 1) {
   return static_cast<T*>(calloc(count ? count : 1, sizeof(T)));
@@ -518,7 +528,7 @@ static void gmres_solve(Matrix* A, f64* x, f64* b, void* ctx) {
   FsBox* f = fs_of(A);
   k->iters = -1;
   if (!f || !f->flow) {
-    fprintf(stderr, "KrylovSolve: GMRES is implemented for the field-split flow matrix (offsets {0,3,4,5,6}) only\n");
+    solve_failed("GMRES is implemented for the field-split flow matrix (offsets {0,3,4,5,6}) only");
     return;
   }
   const CSRAttr* spy = f->pub.spy1x1;
@@ -526,7 +536,10 @@ static void gmres_solve(Matrix* A, f64* x, f64* b, void* ctx) {
   if (!k->ws || k->ws_nodes != N || k->ws_maxit != ksp->max_iter) {
     if (k->ws) dfb_gmres_destroy(k->ws);
     k->ws = nullptr;
-    if (!core_ok(dfb_gmres_create(&k->ws, N, ksp->max_iter), "dfb_gmres_create")) return;
+    if (!core_ok(dfb_gmres_create(&k->ws, N, ksp->max_iter), "dfb_gmres_create")) {
+      solve_failed("workspace (max_iter must be in [1,127]: INTEGRATION.md section 4)");
+      return;
+    }
     k->ws_nodes = N; k->ws_maxit = ksp->max_iter;
     ksp->ksp_ctx = k->ws;
     ksp->ksp_ctx_size = dfb_gmres_bytes(k->ws);
@@ -555,8 +568,10 @@ static void gmres_solve(Matrix* A, f64* x, f64* b, void* ctx) {
   k->hist.assign((size_t)ksp->max_iter + 1, 0.0);
   int iters = 0;
   if (!core_ok(dfb_gmres_solve_pc(k->ws, N, spy->row_ptr, spy->col_ind, f->A00, f->A01, f->A10, f->A11, dinv00, dinv11, x, b,
-                                  ksp->atol, ksp->rtol, &iters, k->hist.data(), nullptr), "dfb_gmres_solve"))
+                                  ksp->atol, ksp->rtol, &iters, k->hist.data(), nullptr), "dfb_gmres_solve")) {
+    solve_failed(dfb_last_error());
     return;
+  }
   k->iters = iters;
   // the reference's residual log (krylov.c:137-138,284-286)
   const f64 r0 = k->hist[0];

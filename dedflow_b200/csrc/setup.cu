@@ -13,6 +13,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
+#include <unordered_map>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "common.cuh"
 #include "plan.cuh"
@@ -68,6 +72,21 @@ Options& options() {
   }();
   return o;
 }
+
+int ensure_dynamic_smem(const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, size_t> high;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& h = high[func];
+  if (bytes > h) {
+    DFB_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    h = bytes;
+  }
+  return DFB_OK;
+}
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 int num_sms() {
   static int n = 0;

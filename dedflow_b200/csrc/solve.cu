@@ -463,14 +463,10 @@ int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, cons
   if (!pv && spmv_tma_on() && layout != LAY_YAOS &&
       (((uintptr_t)row_ptr | (uintptr_t)col_ind | (uintptr_t)A00 | (uintptr_t)A01 | (uintptr_t)A10 | (uintptr_t)A11) & 15u) == 0) {
     constexpr size_t smem = sizeof(SpmvStage) * TS_STAGES + 2 * TS_STAGES * sizeof(uint64_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-      DFB_CUDA(cudaFuncSetAttribute(k_spmv_tma<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      DFB_CUDA(cudaFuncSetAttribute(k_spmv_tma<3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      DFB_CUDA(cudaFuncSetAttribute(k_spmv_tma<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      DFB_CUDA(cudaFuncSetAttribute(k_spmv_tma<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
+    DFB_CHECK(ensure_dynamic_smem((const void*)k_spmv_tma<2, false, false>, smem));
+    DFB_CHECK(ensure_dynamic_smem((const void*)k_spmv_tma<3, false, false>, smem));
+    DFB_CHECK(ensure_dynamic_smem((const void*)k_spmv_tma<2, true, true>, smem));
+    DFB_CHECK(ensure_dynamic_smem((const void*)k_spmv_tma<3, true, true>, smem));
     const int ntile = ceil_div(rows, TS_TR), grid = std::min(ntile, num_sms());
     const bool two = options().spmv_tma == 2;
 #define DFB_TMA(GR, AX, AY)                                                                                                        \
@@ -519,7 +515,7 @@ int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, cons
 // dinv00[9*i + r + 3*c] is that column-major inverse; y_r = sum_c dinv[r + 3c] x_c.
 __global__ void k_pc_setup(int N, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
                            const f64* __restrict__ A00, const f64* __restrict__ A11, f64* __restrict__ dinv00,
-                           f64* __restrict__ dinv11) {
+                           f64* __restrict__ dinv11, int* __restrict__ bad) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const int start = row_ptr[i], end = row_ptr[i + 1], len = end - start;
@@ -529,6 +525,12 @@ __global__ void k_pc_setup(int N, const int* __restrict__ row_ptr, const int* __
     if (col_ind[mid] < i) lo = mid + 1; else hi = mid;
   }
   const int k = lo - start;
+  if (lo >= end || col_ind[lo] != i) {   // no diagonal entry (orphan node in a converted mesh): identity block, flagged
+    if (bad) atomicExch(bad, 1);
+    for (int t = 0; t < 9; t++) dinv00[(size_t)i * 9 + t] = (t % 4 == 0) ? 1.0 : 0.0;
+    dinv11[i] = 1.0;
+    return;
+  }
   // M = column-major view of the row-major block: M(r,c) = B(c,r)
   f64 B[3][3];
 #pragma unroll
@@ -539,6 +541,13 @@ __global__ void k_pc_setup(int N, const int* __restrict__ row_ptr, const int* __
   const f64 c00 = B[1][1] * B[2][2] - B[1][2] * B[2][1], c01 = B[1][2] * B[2][0] - B[1][0] * B[2][2],
             c02 = B[1][0] * B[2][1] - B[1][1] * B[2][0];
   const f64 det = B[0][0] * c00 + B[0][1] * c01 + B[0][2] * c02;
+  const f64 a11 = A11[start + k];
+  if (det == 0.0 || a11 == 0.0 || !isfinite(det) || !isfinite(a11)) {   // singular diagonal block: identity, flagged (an inf here
+    if (bad) atomicExch(bad, 2);                                         // would poison the whole Krylov basis)
+    for (int t = 0; t < 9; t++) dinv00[(size_t)i * 9 + t] = (t % 4 == 0) ? 1.0 : 0.0;
+    dinv11[i] = 1.0;
+    return;
+  }
   const f64 id = 1.0 / det;
   f64 C[3][3];  // C = B^-1
   C[0][0] = c00 * id; C[1][0] = c01 * id; C[2][0] = c02 * id;
@@ -553,7 +562,7 @@ __global__ void k_pc_setup(int N, const int* __restrict__ row_ptr, const int* __
   for (int r = 0; r < 3; r++)
 #pragma unroll
     for (int c = 0; c < 3; c++) dinv00[(size_t)i * 9 + r + 3 * c] = C[c][r];
-  dinv11[i] = 1.0 / A11[start + k];
+  dinv11[i] = 1.0 / a11;
 }
 
 // y = P^-1 x on the live rows (+ optional copy of the phi/T tail when tail_n > 0).
@@ -1232,7 +1241,7 @@ int dfb_spmv_fs(int N, const int* d_row_ptr, const int* d_col_ind, const double*
 int dfb_pc_setup(int N, const int* d_row_ptr, const int* d_col_ind, const double* d_A00, const double* d_A11,
                  double* d_dinv00, double* d_dinv11, void* stream) {
   if (N <= 0 || !d_row_ptr || !d_col_ind || !d_A00 || !d_A11 || !d_dinv00 || !d_dinv11) { set_error("dfb_pc_setup: bad argument"); return DFB_ERR_ARG; }
-  k_pc_setup<<<ceil_div(N, 128), 128, 0, as_stream(stream)>>>(N, d_row_ptr, d_col_ind, d_A00, d_A11, d_dinv00, d_dinv11);
+  k_pc_setup<<<ceil_div(N, 128), 128, 0, as_stream(stream)>>>(N, d_row_ptr, d_col_ind, d_A00, d_A11, d_dinv00, d_dinv11, nullptr);
   DFB_LAUNCH_CHECK();
   return DFB_OK;
 }
@@ -1266,8 +1275,8 @@ int dfb_gmres_create(dfb_gmres** out, int N, int maxit) {
     w->bytes += a.n * sizeof(f64);
   }
   DFB_CUDA(cudaMalloc(&w->S, sizeof(GmresScalars)));
-  DFB_CUDA(cudaMalloc(&w->ctr, 2 * sizeof(unsigned)));
-  DFB_CUDA(cudaMemset(w->ctr, 0, 2 * sizeof(unsigned)));
+  DFB_CUDA(cudaMalloc(&w->ctr, 4 * sizeof(unsigned)));   // [0..1] last-block elections, [2] preconditioner-setup flag
+  DFB_CUDA(cudaMemset(w->ctr, 0, 4 * sizeof(unsigned)));
   DFB_CUDA(cudaMemset(w->z, 0, sizeof(f64) * 6 * (size_t)N));
   DFB_CUDA(cudaMemset(w->t, 0, sizeof(f64) * 6 * (size_t)N));
   *out = w;
@@ -1322,6 +1331,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
                        double* d_x, const double* d_b, double atol, double rtol, int* iters, double* res_hist,
                        void* stream) {
   cudaStream_t st = as_stream(stream);
+  NvtxRange nvtx("dfb_gmres_solve");
   if (!W || N != W->N || !rp || !ci || !A00 || !A01 || !A10 || !A11 || !d_x || !d_b || !iters) { set_error("dfb_gmres_solve: bad argument"); return DFB_ERR_ARG; }
   const int n_own = W->n_own, maxit = W->maxit, ldh = W->ldh;
   const size_t nl = (size_t)4 * n_own;          // compact live length
@@ -1345,7 +1355,8 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   if (ext_dinv00) {  // the caller has run PCSetup already (drop-in layer: the PC tree owns the arrays)
     dinv00 = ext_dinv00; dinv11 = ext_dinv11;
   } else {           // preconditioner setup on every solve, like KrylovSolve -> PCSetup (krylov.c:453)
-    k_pc_setup<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, rp, ci, A00, A11, W->dinv00, W->dinv11);
+    DFB_CUDA(cudaMemsetAsync(W->ctr + 2, 0, sizeof(unsigned), st));
+    k_pc_setup<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, rp, ci, A00, A11, W->dinv00, W->dinv11, reinterpret_cast<int*>(W->ctr + 2));
     DFB_LAUNCH_CHECK();
   }
   k_pc_pack<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, dinv00, dinv11, W->pcrec);
@@ -1399,6 +1410,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   int iter = 0;
   bool converged = false;
   unsigned peer_err = 0;   // peer-memory mode: raised by a kernel whose bounded wait for another rank ran out
+  unsigned pc_bad = 0;     // raised by k_pc_setup: a node row without (1) or with a singular (2) diagonal block
   f64 rnrm_init = 0.0;
   std::vector<f64> hist((size_t)maxit + 1, 0.0);
   SolveProfiler prof;
@@ -1473,7 +1485,13 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   auto convergence_test = [&](int done) -> int {
     DFB_CUDA(cudaMemcpyAsync(hist.data(), W->res_hist, sizeof(f64) * ((size_t)done + 1), cudaMemcpyDeviceToHost, st));
     if (ph) DFB_CUDA(cudaMemcpyAsync(&peer_err, ph->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    if (!ext_dinv00) DFB_CUDA(cudaMemcpyAsync(&pc_bad, W->ctr + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     DFB_CUDA(cudaStreamSynchronize(st));
+    if (pc_bad) {
+      set_error("dfb_gmres_solve: the block-Jacobi setup met a %s (node row without / with a singular diagonal block)",
+                pc_bad == 1 ? "missing diagonal entry" : "singular diagonal block");
+      return DFB_ERR_ARG;
+    }
     if (peer_err) return DFB_OK;
     rnrm_init = hist[0];
     const f64 rnrm = hist[done];
@@ -1519,11 +1537,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   }
   if (iter && !peer_err) {
     prof.begin("trsv..axpy", st);
-    static bool trsv_attr = false;
-    if (!trsv_attr) {
-      DFB_CUDA(cudaFuncSetAttribute(k_gmres_trsv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(f64) * 127 * 127)));
-      trsv_attr = true;
-    }
+    DFB_CHECK(ensure_dynamic_smem((const void*)k_gmres_trsv, sizeof(f64) * 127 * 127));
     k_gmres_trsv<<<1, 128, sizeof(f64) * (size_t)iter * iter, st>>>(iter, W->H, ldh, W->beta, W->tailc, W->tail_coef, W->qs, W->ycoef);
     DFB_LAUNCH_CHECK();
     k_combine<<<cgrid, 256, 0, st>>>(nl, Q, ldq, iter, W->ycoef, W->t);
@@ -1546,7 +1560,13 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   }
   DFB_CUDA(cudaMemcpyAsync(hist.data(), W->res_hist, sizeof(f64) * ((size_t)iter + 1), cudaMemcpyDeviceToHost, st));
   if (ph && !peer_err) DFB_CUDA(cudaMemcpyAsync(&peer_err, ph->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  if (!ext_dinv00) DFB_CUDA(cudaMemcpyAsync(&pc_bad, W->ctr + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   DFB_CUDA(cudaStreamSynchronize(st));
+  if (pc_bad) {
+    set_error("dfb_gmres_solve: the block-Jacobi setup met a %s (node row without / with a singular diagonal block)",
+              pc_bad == 1 ? "missing diagonal entry" : "singular diagonal block");
+    return DFB_ERR_ARG;
+  }
   if (peer_err) {
     set_error("dfb_gmres_solve: a peer-memory wait timed out (a rank died or left the solve early); destroy the communicator");
     return DFB_ERR_PEER;

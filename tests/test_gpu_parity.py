@@ -261,6 +261,18 @@ def test_error_behaviour(api):
     F[4 * mesh.num_node:] = 0
     assert torch.equal(F, F2)                                                            # same kernels, same order: bit-identical
     L.dfb_plan_destroy(plan)
+    # a singular diagonal block in the block-Jacobi setup is reported, not inverted into inf / NaN
+    wgj, dwgj = (torch.from_numpy(a).cuda() for a in boxmesh.state_random(mesh.num_node))
+    fs.assemble_system(wgj, dwgj, J=True)
+    rp_h, ci_h = fs.row_ptr.cpu().numpy(), fs.col_ind.cpu().numpy()
+    node = 5
+    s0, ln = int(rp_h[node]), int(rp_h[node + 1] - rp_h[node])
+    kd = int(np.searchsorted(ci_h[s0:s0 + ln], node))
+    for r in range(3):
+        fs.A00[s0 * 9 + kd * 3 + r * ln * 3:s0 * 9 + kd * 3 + r * ln * 3 + 3] = 0.0
+    Fz = torch.ones(6 * mesh.num_node, dtype=torch.float64, device="cuda")
+    with pytest.raises(dlib.DfbError, match="singular"):
+        fs.krylov_solve(torch.zeros_like(Fz), Fz)
     # bad arguments
     assert L.dfb_spmv_fs(0, None, None, None, None, None, None, 1.0, None, 0.0, None, None) == -2
     ws = C.c_void_p()
