@@ -440,7 +440,9 @@ def run_ours(args, rank, world):
             tp = ROOT / "profiles" / name
             if tp.exists():
                 try:
-                    traffic = json.loads(tp.read_text())["k_spmv_fs"]["dram_bytes_per_launch"]
+                    tj = json.loads(tp.read_text())
+                    key = next(k for k in ("k_spmv_fs<8, 0, 0, 0>", "k_spmv_fs") if k in tj)   # the ABI-layout launch timed below
+                    traffic = tj[key]["dram_bytes_per_launch"]
                     break
                 except Exception:
                     traffic = None
