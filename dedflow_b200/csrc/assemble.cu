@@ -255,6 +255,147 @@ __global__ void __launch_bounds__(128, MINB) k_patchF(int N, const int2* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// F, PATCH variant, persistent and double-buffered (DFB_F_VARIANT=pipe).  Same three phases as k_patchF, but a CTA walks
+// patches p, p + grid, ... and the node records of the NEXT patch are copied into a second shared-memory buffer by cp.async
+// (LDGSTS: global -> shared without passing through registers) while the FP64 phase of the current patch runs; the node ids of
+// the patch after that travel in two registers.  k_patchF's stall samples were 26 % node staging / 52 % FP64 / 22 % sums: the
+// staging latency is what this removes.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// issue the copies of one node record (14 doubles from five places) into shared memory
+__device__ __forceinline__ void stage_node_async(f64* rec, size_t nd, int N, const f64* __restrict__ xg, const f64* __restrict__ wg,
+                                                 const f64* __restrict__ dwg) {
+  const f64* px = xg + nd * 3;
+  const f64* pu = wg + nd * 3;
+  const f64* pd = dwg + nd * 3;
+#pragma unroll
+  for (int c = 0; c < 3; c++) { cp_async8(rec + c, px + c); cp_async8(rec + 3 + c, pu + c); cp_async8(rec + 6 + c, pd + c); }
+  cp_async8(rec + 9, dwg + (size_t)3 * N + nd);
+  cp_async8(rec + 10, wg + (size_t)4 * N + nd);
+  cp_async8(rec + 11, dwg + (size_t)4 * N + nd);
+  cp_async8(rec + 12, wg + (size_t)5 * N + nd);
+  cp_async8(rec + 13, dwg + (size_t)5 * N + nd);
+}
+
+__global__ void __launch_bounds__(128, 2) k_patchF_pipe(int N, int n_patch, const int2* __restrict__ hdr, const int* __restrict__ pnodes,
+                                                        const ushort4* __restrict__ lnode, const unsigned short* __restrict__ corner,
+                                                        const unsigned short* __restrict__ cstart, const f64* __restrict__ xg,
+                                                        const f64* __restrict__ wg, const f64* __restrict__ dwg,
+                                                        f64* __restrict__ part, int max_nodes) {
+  extern __shared__ __align__(16) f64 fp_smem[];
+  // [2][max_nodes][FP_SN] node records | [FP_PE][FP_SE] staging | [2][4 FP_PE] corner lists | [2][max_nodes + 2] corner ranges
+  f64* sn0 = fp_smem;
+  f64* se = fp_smem + (size_t)2 * max_nodes * FP_SN;
+  unsigned short* scl0 = reinterpret_cast<unsigned short*>(se + (size_t)FP_PE * FP_SE);
+  unsigned short* scs0 = scl0 + 2 * 4 * FP_PE;
+  const int tid = threadIdx.x, stride = gridDim.x;
+  int p = blockIdx.x;
+  if (p >= n_patch) return;
+  // ---- prologue: patch p into buffer 0 (waited for), node ids of patch p + stride into registers ----
+  int2 h = __ldg(hdr + p);
+  {
+    for (int k = tid; k < h.y; k += 128) stage_node_async(sn0 + (size_t)k * FP_SN, (size_t)__ldg(pnodes + h.x + k), N, xg, wg, dwg);
+    cp_async16(scl0 + 8 * tid, corner + (size_t)p * 4 * FP_PE + 8 * tid);
+    const unsigned short* cs = cstart + (size_t)h.x + p;
+    for (int k = tid; k <= h.y; k += 128) scs0[k] = cs[k];
+  }
+  ushort4 ln0 = lnode[(size_t)p * FP_PE + tid], ln1 = lnode[(size_t)p * FP_PE + 128 + tid];
+  int pn = p + stride;
+  int2 hn = make_int2(0, 0);
+  int nid[2] = {0, 0};
+  if (pn < n_patch) {
+    hn = __ldg(hdr + pn);
+    if (tid < hn.y) nid[0] = __ldg(pnodes + hn.x + tid);
+    if (tid + 128 < hn.y) nid[1] = __ldg(pnodes + hn.x + tid + 128);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  for (int it = 0; p < n_patch; it++) {
+    const int b = it & 1;
+    f64* sn = sn0 + (size_t)b * max_nodes * FP_SN;
+    f64* snn = sn0 + (size_t)(b ^ 1) * max_nodes * FP_SN;
+    unsigned short* scl = scl0 + b * 4 * FP_PE;
+    unsigned short* scs = scs0 + b * (max_nodes + 2);
+    // ---- the next patch: its node records start travelling now (ids already in registers); lists and connectivity too ----
+    ushort4 ln0n = make_ushort4(0xffffu, 0, 0, 0), ln1n = ln0n;
+    unsigned short csn[2] = {0, 0};
+    if (pn < n_patch) {
+      if (tid < hn.y) stage_node_async(snn + (size_t)tid * FP_SN, (size_t)nid[0], N, xg, wg, dwg);
+      if (tid + 128 < hn.y) stage_node_async(snn + (size_t)(tid + 128) * FP_SN, (size_t)nid[1], N, xg, wg, dwg);
+      for (int k = tid + 256; k < hn.y; k += 128)   // (patches with more than 256 nodes: the rest is fetched here)
+        stage_node_async(snn + (size_t)k * FP_SN, (size_t)__ldg(pnodes + hn.x + k), N, xg, wg, dwg);
+      cp_async16(scl0 + (b ^ 1) * 4 * FP_PE + 8 * tid, corner + (size_t)pn * 4 * FP_PE + 8 * tid);
+      ln0n = lnode[(size_t)pn * FP_PE + tid];
+      ln1n = lnode[(size_t)pn * FP_PE + 128 + tid];
+      const unsigned short* cs = cstart + (size_t)hn.x + pn;
+      if (tid <= hn.y) csn[0] = cs[tid];
+      if (tid + 128 <= hn.y) csn[1] = cs[tid + 128];
+    }
+    // node ids of the patch after the next one: two registers, needed one iteration from now
+    const int pnn = pn + stride;
+    int2 hnn = make_int2(0, 0);
+    int nidn[2] = {0, 0};
+    if (pnn < n_patch) {
+      hnn = __ldg(hdr + pnn);
+      if (tid < hnn.y) nidn[0] = __ldg(pnodes + hnn.x + tid);
+      if (tid + 128 < hnn.y) nidn[1] = __ldg(pnodes + hnn.x + tid + 128);
+    }
+    // ---- B: two elements per thread out of the staged records ----
+#pragma unroll 1
+    for (int j = 0; j < 2; j++) {
+      const ushort4 ln = j ? ln1 : ln0;
+      if (ln.x == 0xffffu) continue;
+      const f64* n0 = sn + (size_t)ln.x * FP_SN;
+      const f64* n1 = sn + (size_t)ln.y * FP_SN;
+      const f64* n2 = sn + (size_t)ln.z * FP_SN;
+      const f64* n3 = sn + (size_t)ln.w * FP_SN;
+      f64 x[4][3];
+#pragma unroll
+      for (int d = 0; d < 3; d++) { x[0][d] = n0[d]; x[1][d] = n1[d]; x[2][d] = n2[d]; x[3][d] = n3[d]; }
+      Geom g;
+      geometry(x, g);
+      residual_rec(g, n0, n1, n2, n3, se + (size_t)(j * 128 + tid) * FP_SE);
+    }
+    __syncthreads();
+    // ---- C: per patch-node partial sums, fixed corner order ----
+    for (int k = tid; k < h.y; k += 128) {
+      const int c0 = scs[k], c1 = scs[k + 1];
+      f64 sacc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      for (int i = c0; i < c1; i++) {
+        const int cr = scl[i];
+        const f64* src = se + (cr >> 2) * FP_SE + (cr & 3) * 6;
+#pragma unroll
+        for (int c = 0; c < 6; c++) sacc[c] += src[c];
+      }
+      f64* dst = part + (size_t)(h.x + k) * 6;
+#pragma unroll
+      for (int c = 0; c < 6; c += 2) *reinterpret_cast<double2*>(dst + c) = make_double2(sacc[c], sacc[c + 1]);
+    }
+    // ---- rotate: the next patch's ranges into shared memory, its records have landed ----
+    if (pn < n_patch) {
+      unsigned short* scsn = scs0 + (b ^ 1) * (max_nodes + 2);
+      if (tid <= hn.y) scsn[tid] = csn[0];
+      if (tid + 128 <= hn.y) scsn[tid + 128] = csn[1];
+      const unsigned short* cs = cstart + (size_t)hn.x + pn;
+      for (int k = tid + 256; k <= hn.y; k += 128) scsn[k] = cs[k];
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    p = pn; h = hn; ln0 = ln0n; ln1 = ln1n;
+    pn = pnn; hn = hnn; nid[0] = nidn[0]; nid[1] = nidn[1];
+  }
+}
+
 // F[node] (+)= sum of the node's patch partials, ascending patch order
 __global__ void k_gatherF2(int N, int n_rows, const int* __restrict__ np_ptr, const int* __restrict__ np, const f64* __restrict__ part,
                            f64* __restrict__ F, int overwrite) {
@@ -945,14 +1086,26 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
   const u32* slot32 = reinterpret_cast<const u32*>(P->slot);
   if (d_F) {
     bool patch_done = false;
-    if (mode == DFB_MODE_GATHER && options().f_variant == 1) {
+    if (mode == DFB_MODE_GATHER && options().f_variant >= 1) {
       DFB_CHECK(build_fpatch(P, d_xg, st));
       if (P->fp_state == 1) {
         const int mn = (P->fp_max_nodes + 1) & ~1;   // even: keeps the 16-byte alignment of what follows the node records
         const size_t smem = sizeof(f64) * ((size_t)mn * FP_SN + (size_t)FP_PE * FP_SE) + sizeof(unsigned short) * ((size_t)4 * FP_PE + mn + 8);
         DFB_CHECK(ensure_dynamic_smem((const void*)k_patchF<2>, smem));
         DFB_CHECK(ensure_dynamic_smem((const void*)k_patchF<3>, smem));
-        if (options().f_patch_ctas == 2)
+        if (options().f_variant == 2) {
+          const size_t smem2 = sizeof(f64) * ((size_t)2 * mn * FP_SN + (size_t)FP_PE * FP_SE) +
+                               sizeof(unsigned short) * ((size_t)2 * 4 * FP_PE + 2 * (mn + 2) + 8);
+          if (smem2 <= 113 * 1024) {   // two CTAs per SM
+            DFB_CHECK(ensure_dynamic_smem((const void*)k_patchF_pipe, smem2));
+            k_patchF_pipe<<<std::min(P->fp_n_patch, 2 * num_sms()), 128, smem2, st>>>(N, P->fp_n_patch, P->fp_hdr, P->fp_nodes, P->fp_lnode,
+                                                                                     P->fp_corner, P->fp_cstart, d_xg, d_wg, d_dwg,
+                                                                                     P->fp_part, mn);
+          } else {
+            k_patchF<2><<<P->fp_n_patch, 128, smem, st>>>(N, P->fp_hdr, P->fp_nodes, P->fp_lnode, P->fp_corner, P->fp_cstart, d_xg, d_wg,
+                                                          d_dwg, P->fp_part, mn);
+          }
+        } else if (options().f_patch_ctas == 2)
           k_patchF<2><<<P->fp_n_patch, 128, smem, st>>>(N, P->fp_hdr, P->fp_nodes, P->fp_lnode, P->fp_corner, P->fp_cstart, d_xg, d_wg,
                                                         d_dwg, P->fp_part, mn);
         else
@@ -1016,7 +1169,9 @@ int dfb_assemble_tet(const dfb_plan* P, const double* d_xg, const double* d_wg, 
           // 96 threads (3 warps: one of diagonal items, two of pair items) and 4 CTAs per SM measured best on B200 at 1M tets:
           // 96x5 (128 registers, spills) 377 us, 128x3 432 us, 128x4 403 us, 160x2 547 us, 16 rows x 192 threads 404 us vs 372 us;
           // after the arithmetic trim: 64x5 and 64x6 370 us vs 362 us
-          if (R == 16) DFB_PAIR_LAUNCH(192, 2);
+          const int nt = options().j_pair_nt;
+          if (R == 16) { if (nt == 224) DFB_PAIR_LAUNCH(224, 2); else DFB_PAIR_LAUNCH(192, 2); }
+          else if (nt == 128) DFB_PAIR_LAUNCH(128, 3);
           else DFB_PAIR_LAUNCH(96, 4);
 #undef DFB_PAIR_LAUNCH
           DFB_LAUNCH_CHECK();

@@ -91,14 +91,15 @@ int num_sms();
 // Variant switches of the library.  Read ONCE from the environment (first use) and afterwards only changed through
 // dfb_set_option(): no entry point calls getenv on its launch path, and tests / A-B scripts switch variants inside one process
 // without touching the environment.  Keys are the environment names (DFB_J_VARIANT=pairs|pull|fused, DFB_J_PAIR_ROWS=8|16,
-// DFB_J_PAIR_ORDER=morton|natural, DFB_J_PULL_PLAIN=0|1, DFB_F_VARIANT=patch|scratch, DFB_F_PATCH_CTAS=2|3, DFB_SPMV_G=4|8|16|32, DFB_SPMV_TMA=0|1,
+// DFB_J_PAIR_ORDER=morton|natural, DFB_J_PULL_PLAIN=0|1, DFB_F_VARIANT=patch|pipe|scratch, DFB_F_PATCH_CTAS=2|3, DFB_SPMV_G=4|8|16|32, DFB_SPMV_TMA=0|1,
 // DFB_KRYLOV_TMA=0|1, DFB_GRAPH=0|1, DFB_PROFILE=0|1|2, DFB_ASSEMBLE_MODE=gather|atomic|colored, DFB_VERBOSE=0|1, DFB_PC=jacobi|schur2, DFB_PC_AGG=2..16, DFB_PC_DEGREE=1..64).
 struct Options {
   int j_variant = 2;        // 0 pull, 1 fused, 2 pairs
   int j_pair_rows = 8;
   int j_pair_natural = 0;
+  int j_pair_nt = 96;       // threads per CTA of k_pairJ (96 | 128 for 8-row groups, 192 | 224 for 16-row groups)
   int j_pull_plain = 0;
-  int f_variant = 1;        // 0 scratch (k_elemF + k_gatherF), 1 patch (k_patchF)
+  int f_variant = 1;        // 0 scratch (k_elemF + k_gatherF), 1 patch (k_patchF), 2 pipe (k_patchF_pipe: persistent, double-buffered)
   int f_patch_ctas = 2;     // register budget of k_patchF: resident CTAs per SM (2: 232 registers, measured faster; 3: 168 + spills)
   int spmv_g = 8;
   int spmv_tma = 0;        // 0 register-staged k_spmv_fs (default: measured faster in-solve), 1/2 TMA ring with 3/2 consumer groups

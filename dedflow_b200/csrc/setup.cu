@@ -38,9 +38,10 @@ static bool apply_option(Options& o, const char* key, const char* v) {
   auto is = [&](const char* k) { return !strcmp(key, k); };
   if (is("DFB_J_VARIANT")) { o.j_variant = !strcmp(v, "pull") ? 0 : (!strcmp(v, "fused") ? 1 : 2); return true; }
   if (is("DFB_J_PAIR_ROWS")) { const int r = atoi(v); o.j_pair_rows = (r >= 8 && r <= 16 && (r & 7) == 0) ? r : 8; return true; }
+  if (is("DFB_J_PAIR_NT")) { o.j_pair_nt = atoi(v); return true; }
   if (is("DFB_J_PAIR_ORDER")) { o.j_pair_natural = !strcmp(v, "natural"); return true; }
   if (is("DFB_J_PULL_PLAIN")) { o.j_pull_plain = atoi(v) != 0; return true; }
-  if (is("DFB_F_VARIANT")) { o.f_variant = !strcmp(v, "scratch") ? 0 : 1; return true; }
+  if (is("DFB_F_VARIANT")) { o.f_variant = !strcmp(v, "scratch") ? 0 : (!strcmp(v, "pipe") ? 2 : 1); return true; }
   if (is("DFB_F_PATCH_CTAS")) { o.f_patch_ctas = atoi(v) == 3 ? 3 : 2; return true; }
   if (is("DFB_SPMV_G")) { const int g = atoi(v); o.spmv_g = (g == 4 || g == 8 || g == 16 || g == 32) ? g : 8; return true; }
   if (is("DFB_SPMV_TMA")) { o.spmv_tma = atoi(v); return true; }
@@ -62,7 +63,7 @@ static bool apply_option(Options& o, const char* key, const char* v) {
 Options& options() {
   static Options o = [] {
     Options t;
-    static const char* keys[] = {"DFB_J_VARIANT", "DFB_J_PAIR_ROWS", "DFB_J_PAIR_ORDER", "DFB_J_PULL_PLAIN", "DFB_F_VARIANT", "DFB_F_PATCH_CTAS", "DFB_SPMV_G",
+    static const char* keys[] = {"DFB_J_VARIANT", "DFB_J_PAIR_ROWS", "DFB_J_PAIR_NT", "DFB_J_PAIR_ORDER", "DFB_J_PULL_PLAIN", "DFB_F_VARIANT", "DFB_F_PATCH_CTAS", "DFB_SPMV_G",
                                  "DFB_SPMV_TMA", "DFB_SPMV_PEER_SPLIT", "DFB_KRYLOV_TMA", "DFB_GRAPH", "DFB_PROFILE", "DFB_VERBOSE", "DFB_ASSEMBLE_MODE", "DFB_PC", "DFB_PC_AGG", "DFB_PC_DEGREE"};
     for (const char* k : keys) {
       const char* v = getenv(k);

@@ -15,7 +15,7 @@ from dedflow_b200 import api, boxmesh, lib as dlib  # noqa: E402
 
 P = lambda t: C.c_void_p(t.data_ptr())
 CFGS = [("scratch", {"DFB_F_VARIANT": "scratch"}), ("patch 3 CTAs/SM", {"DFB_F_VARIANT": "patch", "DFB_F_PATCH_CTAS": "3"}),
-        ("patch 2 CTAs/SM", {"DFB_F_VARIANT": "patch", "DFB_F_PATCH_CTAS": "2"})]
+        ("patch 2 CTAs/SM", {"DFB_F_VARIANT": "patch", "DFB_F_PATCH_CTAS": "2"}), ("pipe", {"DFB_F_VARIANT": "pipe"})]
 
 
 def run(mesh, name, reps=0):

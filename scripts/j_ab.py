@@ -27,7 +27,11 @@ d_wg, d_dwg = torch.from_numpy(wg).cuda(), torch.from_numpy(dwg).cuda()
 P = lambda t: C.c_void_p(t.data_ptr())
 ref = None
 shuffle = len(sys.argv) > 2 and sys.argv[2] == "shuffle"
-CFGS = [("pull", {"DFB_J_VARIANT": "pull"}),
+CFGS = [("pairs 96x4", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "morton", "DFB_J_PAIR_ROWS": "8", "DFB_J_PAIR_NT": "96"}),
+        ("pairs 128x3", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "morton", "DFB_J_PAIR_ROWS": "8", "DFB_J_PAIR_NT": "128"}),
+        ("pairs R16 224x2", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "morton", "DFB_J_PAIR_ROWS": "16", "DFB_J_PAIR_NT": "224"}),
+        ("pairs R16 192x2", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "morton", "DFB_J_PAIR_ROWS": "16", "DFB_J_PAIR_NT": "192"})]
+OLD_CFGS = [("pull", {"DFB_J_VARIANT": "pull"}),
         ("pairs morton", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "morton"}),
         ("pairs natural", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "natural"}),
         ("pairs R=16", {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "morton", "DFB_J_PAIR_ROWS": "16"}),
