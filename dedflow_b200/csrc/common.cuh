@@ -104,6 +104,7 @@ struct Options {
   int spmv_g = 8;
   int spmv_tma = 0;        // 0 register-staged k_spmv_fs (default: measured faster in-solve), 1/2 TMA ring with 3/2 consumer groups
   int spmv_peer_split = 0;  // peer-memory mat-vec as two launches (interior rows by the plain kernel)
+  int halo_defer = 1;       // peer-memory mode: the mat-vec's first block raises the halo flag of the update before it (DFB_HALO_DEFER=0: the update's last block does)
   int krylov_tma = 1;
   int graph = 1;
   int profile = 0;

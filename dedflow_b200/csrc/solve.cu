@@ -257,9 +257,18 @@ __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int
                                                  const f64* __restrict__ A00, const f64* __restrict__ A01,
                                                  const f64* __restrict__ A10, const f64* __restrict__ A11, f64 alpha,
                                                  const f64* __restrict__ x, size_t x_poff, f64 beta, f64* __restrict__ y,
-                                                 size_t y_poff, const P2PView* __restrict__ pv, unsigned hoff, int n_interior) {
+                                                 size_t y_poff, const P2PView* __restrict__ pv, unsigned hoff, int n_interior,
+                                                 int post_flag) {
   bool halo_block = false;   // block-uniform: this block owns boundary rows (they reference ghost columns)
   if (PEER) {
+    // Deferred halo flag: the update kernel before this launch stored z~'s boundary entries into the neighbours but left the
+    // flag to us, so that its own completion (and with it the start of this mat-vec's interior rows, on both sides) does not
+    // wait for a system-scope fence.  The first block raises it before anything else; the blocks that need the NEIGHBOURS'
+    // flags are the last ones of the grid.
+    if (post_flag && blockIdx.x == 0 && (int)threadIdx.x < pv->n_nbr) {
+      __threadfence_system();
+      p2p_signal(pv->mbox_peer[pv->nbr[threadIdx.x]] + p2p_h_flag(pv->nranks, pv->rank), pv->seq_base[1] + hoff);
+    }
     const int last_row = row0 + (int)((((size_t)blockIdx.x + 1) * blockDim.x - 1) / G);
     halo_block = last_row >= n_interior;
     if (halo_block) {
@@ -456,7 +465,7 @@ static bool spmv_tma_on() { return options().spmv_tma != 0; }   // 0 selects the
 enum { LAY_ABI = 0, LAY_XAOS = 1, LAY_YAOS = 2 };
 int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, const f64* A00, const f64* A01, const f64* A10,
                 const f64* A11, f64 alpha, const f64* x, size_t x_poff, f64 beta, f64* y, size_t y_poff, cudaStream_t st,
-                int layout = LAY_ABI, const P2PView* pv = nullptr, unsigned hoff = 0, int n_interior = 0) {
+                int layout = LAY_ABI, const P2PView* pv = nullptr, unsigned hoff = 0, int n_interior = 0, int post_flag = 0) {
   if (row1 <= row0) return DFB_OK;
   const i64 rows = row1 - row0;
   if (pv && layout != (LAY_XAOS | LAY_YAOS)) { set_error("launch_spmv: the peer-memory mat-vec runs on interleaved vectors only"); return DFB_ERR_ARG; }
@@ -481,17 +490,17 @@ int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, cons
   const int grid8 = ceil_div(rows * 8, 256);
   if (pv) {
     k_spmv_fs<8, true, true, true><<<grid8, 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x, x_poff, beta, y,
-                                                         y_poff, pv, hoff, n_interior);
+                                                         y_poff, pv, hoff, n_interior, post_flag);
   } else if (layout == LAY_YAOS) {
     k_spmv_fs<8, false, false, true><<<grid8, 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x, x_poff, beta, y,
-                                                           y_poff, nullptr, 0u, 0);
+                                                           y_poff, nullptr, 0u, 0, 0);
   } else if (layout == (LAY_XAOS | LAY_YAOS)) {
     k_spmv_fs<8, false, true, true><<<grid8, 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x, x_poff, beta, y,
-                                                          y_poff, nullptr, 0u, 0);
+                                                          y_poff, nullptr, 0u, 0, 0);
   } else if (layout == LAY_ABI) {
 #define DFB_SPMV(G)                                                                                                              \
   k_spmv_fs<G, false, false, false><<<ceil_div(rows * G, 256), 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11,   \
-                                                                             alpha, x, x_poff, beta, y, y_poff, nullptr, 0u, 0)
+                                                                             alpha, x, x_poff, beta, y, y_poff, nullptr, 0u, 0, 0)
     switch (spmv_group()) {
       case 4: DFB_SPMV(4); break;
       case 32: DFB_SPMV(32); break;
@@ -868,7 +877,7 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
 __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict__ Q, size_t ldq, int ncol, const f64* __restrict__ draw,
                                                 f64* hcol, f64* hcol_prev, f64* __restrict__ w, f64* part, unsigned* ctr, int mode,
                                                 UpdateScalars U, const f64* __restrict__ pcrec, f64* __restrict__ z,
-                                                const P2PView* __restrict__ pv, unsigned soff, unsigned hoff) {
+                                                const P2PView* __restrict__ pv, unsigned soff, unsigned hoff, int defer_flag) {
   __shared__ f64 sh[128];    // c_i = h_i s_i: coefficient of the stored (unnormalised) column i
   __shared__ f64 shh[128];   // h_i: the Hessenberg column
   __shared__ f64 sm[8];
@@ -949,15 +958,17 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
       if (pv) push_half(pv, tgt_base, tgt_n, node, half, v);
     }
   }
-  // Halo stores need no fence of their own here (a system-scope fence per pushing thread measured +6 us on the kernel): they are
-  // ordered before this block's arrival in the election below (barrier + gpu-scope fence + atomic, last_block()), and the block
-  // that ends up last issues ONE system-scope fence before it raises the halo flags -- fences are cumulative, so every store
-  // that happens-before it is visible to the peer that acquires the flag.  (Same protocol as NCCL's: all workers store, a
-  // barrier, one thread fences and posts.)  ONE election serves the norm reduction and the halo.
+  // Halo stores need no fence of their own here (a system-scope fence per pushing thread measured +6 us on the kernel).
+  // defer_flag (default): the flag is raised by the first block of the NEXT mat-vec -- the kernel boundary orders every store
+  // of this grid before that block's system-scope fence -- because even ONE such fence in this kernel's last block held the
+  // kernel's completion, i.e. the start of the mat-vec's interior rows on both sides, for ~9 us (2 GPUs: update 37.9 -> 29.3 us,
+  // the single-GPU figure; solve 5.48 -> 5.35 ms).  Otherwise the stores are ordered before this block's arrival in the
+  // election below (barrier + gpu-scope fence + atomic, last_block()), and the block that ends up last issues one cumulative
+  // system-scope fence before it raises the flags.  ONE election serves the norm reduction and the halo.
   f64 r = block_sum_256(ss, sm);
   if (threadIdx.x == 0) part[blockIdx.x] = r;
   if (!last_block(ctr, gridDim.x)) return;
-  if (pv && (int)threadIdx.x < pv->n_nbr) {   // every block has pushed and fenced: this mat-vec's halo is complete on the neighbours
+  if (pv && !defer_flag && (int)threadIdx.x < pv->n_nbr) {   // every block has pushed: this mat-vec's halo is complete on the neighbours
     __threadfence_system();
     p2p_signal(pv->mbox_peer[pv->nbr[threadIdx.x]] + p2p_h_flag(pv->nranks, pv->rank), pv->seq_base[1] + hoff);
   }
@@ -1416,6 +1427,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   SolveProfiler prof;
   const UpdateScalars US = {W->S, W->qs, W->gv, W->beta, W->tailc, W->res_hist};
   // one Arnoldi step = three launches on stream `s` (+ the standalone collectives of the NCCL path)
+  const int halo_defer = (pv && options().halo_defer && !options().spmv_peer_split) ? 1 : 0;
   auto arnoldi_step = [&](int iter, cudaStream_t s) -> int {
     // w_raw = A z~_iter into column iter + 1 (no scaling: the update applies s_iter)
     f64* w = QCOL(iter + 1);
@@ -1424,7 +1436,8 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
       DFB_CHECK(launch_spmv(0, W->n_interior, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, s, LAY_XAOS | LAY_YAOS));
       DFB_CHECK(launch_spmv(W->n_interior, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, s, LAY_XAOS | LAY_YAOS, pv, (unsigned)iter + 1u, W->n_interior));
     } else if (pv) {   // ONE launch whose boundary-row blocks (scheduled last) wait for the neighbours' halo flags
-      DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, s, LAY_XAOS | LAY_YAOS, pv, (unsigned)iter + 1u, W->n_interior));
+      DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, s, LAY_XAOS | LAY_YAOS, pv, (unsigned)iter + 1u, W->n_interior,
+                            halo_defer && iter > 0));   // (z~_0's flag left k_pc_apply_aos)
     } else if (W->parallel) {
       DFB_CHECK(W->par.halo_begin_aos(zvec, s, W->par.user));
       DFB_CHECK(launch_spmv(0, W->n_interior, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, s, LAY_XAOS | LAY_YAOS));
@@ -1455,7 +1468,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     prof.begin("update", s);
     k_update<<<ugrid, 256, 0, s>>>(nl, Q, ldq, ncol, W->draw, HCOL(iter), iter ? HCOL(iter - 1) : HCOL(0), w, W->part, W->ctr + 1,
                                    pv ? 2 : (W->parallel ? 1 : 0), US, pc2 ? nullptr : W->pcrec, zvec, pv, soff,
-                                   (unsigned)iter + 2u /* the halo of z~_{iter+1} leaves from this kernel */);
+                                   (unsigned)iter + 2u /* the halo of z~_{iter+1} leaves from this kernel */, halo_defer);
     DFB_LAUNCH_CHECK();
     prof.end(s);
     if (pc2) {
@@ -1501,7 +1514,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   // One GPU: the 20 iterations between two convergence tests (60 launches with fixed arguments for a given workspace and
   // matrix) are captured once into a CUDA graph per chunk and replayed -- the launch gaps shrink, the host does one call.
   const bool use_graph = (!W->parallel || pv) && !prof.on && options().graph != 0;
-  const dfb_gmres::GraphKey gkey = {rp, ci, A00, A01, A10, A11, pv, pc2, n_own, W->n_interior, options().spmv_peer_split};
+  const dfb_gmres::GraphKey gkey = {rp, ci, A00, A01, A10, A11, pv, pc2, n_own, W->n_interior, options().spmv_peer_split | (options().halo_defer << 1)};
   while (!converged && iter < maxit && !peer_err) {
     if (use_graph && iter % 20 == 0 && iter + 20 <= maxit) {
       const size_t chunk = (size_t)iter / 20;

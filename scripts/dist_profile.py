@@ -25,9 +25,32 @@ F = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
 dx = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
 fs.assemble_system(d_wg, d_dwg, F=F)
 fs.assemble_system(d_wg, d_dwg, J=True)
-for _ in range(3):
-    dx.zero_()
-    fs.krylov_solve(dx, F)
+
+
+def timed(label, opts):
+    """median event time of 7 graph-replayed solves under `opts` (rank 0 prints)"""
+    for k, v in opts.items():
+        dlib.set_option(k, v)
+    ts = []
+    for i in range(10):
+        dx.zero_()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _, hist = fs.krylov_solve(dx, F)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(a.elapsed_time(b))
+    if rank == 0:
+        print(f"[variant] {label:28s} solve {sorted(ts)[len(ts) // 2]:7.3f} ms (min {min(ts):7.3f})  final residual {hist[-1]:.6e}", flush=True)
+
+
+for label, opts in (("flag from the update", {"DFB_HALO_DEFER": "0"}), ("flag from the next mat-vec", {"DFB_HALO_DEFER": "1"}),
+                    ("flag from the update", {"DFB_HALO_DEFER": "0"}), ("flag from the next mat-vec", {"DFB_HALO_DEFER": "1"})):
+    timed(label, opts)
+if len(sys.argv) > 1:
+    dlib.set_option("DFB_HALO_DEFER", sys.argv[1])
 torch.cuda.synchronize()
 dist.barrier()
 dlib.set_option("DFB_PROFILE", 2 if rank == 0 else -1)
