@@ -90,8 +90,8 @@ int num_sms();
 
 // Variant switches of the library.  Read ONCE from the environment (first use) and afterwards only changed through
 // dfb_set_option(): no entry point calls getenv on its launch path, and tests / A-B scripts switch variants inside one process
-// without touching the environment.  Keys are the environment names (DFB_J_VARIANT=pairs|pull|fused, DFB_J_PAIR_ROWS=8|16,
-// DFB_J_PAIR_ORDER=morton|natural, DFB_J_PULL_PLAIN=0|1, DFB_F_VARIANT=patch|pipe|scratch, DFB_F_PATCH_CTAS=2|3, DFB_SPMV_G=4|8|16|32, DFB_SPMV_TMA=0|1,
+// without touching the environment.  Keys are the environment names (DFB_J_VARIANT=pairs|pull|fused, DFB_J_PAIR_ROWS=8|16, DFB_J_PAIR_NT=96|128|192|224,
+// DFB_J_PAIR_ORDER=morton|natural, DFB_J_PULL_PLAIN=0|1, DFB_F_VARIANT=patch|pipe|scratch, DFB_F_PATCH_CTAS=2|3, DFB_SPMV_G=4|8|16|32, DFB_SPMV_TMA=0|1, DFB_SPMV_PEER_SPLIT=0|1, DFB_HALO_DEFER=0|1,
 // DFB_KRYLOV_TMA=0|1, DFB_GRAPH=0|1, DFB_PROFILE=0|1|2, DFB_ASSEMBLE_MODE=gather|atomic|colored, DFB_VERBOSE=0|1, DFB_PC=jacobi|schur2, DFB_PC_AGG=2..16, DFB_PC_DEGREE=1..64).
 struct Options {
   int j_variant = 2;        // 0 pull, 1 fused, 2 pairs
