@@ -1221,7 +1221,7 @@ struct dfb_gmres {
   bool parallel = false;
   dfb_pc2* pc2 = nullptr;   // opt-in two-level Schur-complement preconditioner (pc2.cu); nullptr = the reference's block-Jacobi
   std::string last_profile;   // per-kernel event times of the last solve (DFB_PROFILE != 0), see dfb_gmres_profile
-  // CUDA graphs of the 20-iteration chunks between two convergence tests (one GPU), valid for one set of matrix pointers
+  // CUDA graphs of the chunks of iterations between two convergence tests, valid for one set of matrix pointers and options
   struct GraphKey {
     const void *rp, *ci, *a00, *a01, *a10, *a11, *pv, *pc2;
     int n_own, n_interior, split;
@@ -1428,6 +1428,10 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   const UpdateScalars US = {W->S, W->qs, W->gv, W->beta, W->tailc, W->res_hist};
   // one Arnoldi step = three launches on stream `s` (+ the standalone collectives of the NCCL path)
   const int halo_defer = (pv && options().halo_defer && !options().spmv_peer_split) ? 1 : 0;
+  // iterations between two convergence tests: 20 is the reference's rule (krylov.c:281-290) and the default; a shorter interval
+  // (DFB_GMRES_CHECK, 1..20) stops closer to the first iteration that meets the tolerance at the price of one host round trip
+  // per test -- same arithmetic, the residual history is a prefix of the default's
+  const int chk = std::min(20, std::max(1, options().gmres_check));
   auto arnoldi_step = [&](int iter, cudaStream_t s) -> int {
     // w_raw = A z~_iter into column iter + 1 (no scaling: the update applies s_iter)
     f64* w = QCOL(iter + 1);
@@ -1450,8 +1454,8 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     // raw dots d = Q^T w_raw  (krylov.c:166-174)
     const int ncol = iter + 1;
     const unsigned soff = pv ? (unsigned)iter + 1u : 0u;
-    // peer-memory mode: the norm + Givens step of the previous iteration is still pending unless it closed a 20-iteration chunk
-    const unsigned soff_prev = (pv && iter > 0 && iter % 20 != 0) ? (unsigned)iter : 0u;
+    // peer-memory mode: the norm + Givens step of the previous iteration is still pending unless it closed a chunk (a convergence test follows a chunk)
+    const unsigned soff_prev = (pv && iter > 0 && iter % chk != 0) ? (unsigned)iter : 0u;
     prof.begin("multidot", s);
     const int ny = ceil_div(ncol, JT);
     const int mg = std::max(1, std::min(mgrid, (4 * num_sms()) / ny));   // one resident wave of (row chunk, column group) blocks
@@ -1479,7 +1483,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     if (pv) {
       // the norm reduction + Givens step of this iteration are folded into the NEXT update's prologue; they run on their own
       // only when the host needs the residual now (the every-20th test) or the loop ends
-      if ((iter + 1) % 20 == 0 || iter + 1 == maxit) {
+      if ((iter + 1) % chk == 0 || iter + 1 == maxit) {
         prof.begin("step (peer sum)", s);
         k_gmres_step_peer<<<1, 128, 0, s>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist, W->qs, pv, soff);
         DFB_LAUNCH_CHECK();
@@ -1511,13 +1515,13 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     if (rnrm < atol || rnrm < (rnrm_init + 1e-16) * rtol) converged = true;
     return DFB_OK;
   };
-  // One GPU: the 20 iterations between two convergence tests (60 launches with fixed arguments for a given workspace and
+  // The iterations between two convergence tests (20: 60 launches with fixed arguments for a given workspace and
   // matrix) are captured once into a CUDA graph per chunk and replayed -- the launch gaps shrink, the host does one call.
   const bool use_graph = (!W->parallel || pv) && !prof.on && options().graph != 0;
-  const dfb_gmres::GraphKey gkey = {rp, ci, A00, A01, A10, A11, pv, pc2, n_own, W->n_interior, options().spmv_peer_split | (options().halo_defer << 1)};
+  const dfb_gmres::GraphKey gkey = {rp, ci, A00, A01, A10, A11, pv, pc2, n_own, W->n_interior, options().spmv_peer_split | (options().halo_defer << 1) | (chk << 2)};
   while (!converged && iter < maxit && !peer_err) {
-    if (use_graph && iter % 20 == 0 && iter + 20 <= maxit) {
-      const size_t chunk = (size_t)iter / 20;
+    if (use_graph && iter % chk == 0 && iter + chk <= maxit) {
+      const size_t chunk = (size_t)iter / chk;
       if (!(W->gkey == gkey)) { W->drop_graphs(); W->gkey = gkey; }
       if (W->gexec.size() <= chunk) W->gexec.resize(chunk + 1, nullptr);
       if (!W->gexec[chunk]) {
@@ -1525,7 +1529,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
         cudaGraph_t graph = nullptr;
         DFB_CUDA(cudaStreamBeginCapture(W->cap_stream, cudaStreamCaptureModeThreadLocal));
         int rc = DFB_OK;
-        for (int k = 0; k < 20 && rc == DFB_OK; k++) rc = arnoldi_step(iter + k, W->cap_stream);
+        for (int k = 0; k < chk && rc == DFB_OK; k++) rc = arnoldi_step(iter + k, W->cap_stream);
         const cudaError_t ce = cudaStreamEndCapture(W->cap_stream, &graph);
         if (rc != DFB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
         DFB_CUDA(ce);
@@ -1533,16 +1537,16 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
         cudaGraphDestroy(graph);
         DFB_CUDA(ie);
       } else {
-        count_launch(pc2 ? 400 : (pv ? (options().spmv_peer_split ? 81 : 61) : 60));   // (pc2: 20 x (3 + 5 + its Chebyshev steps), approx.)
+        count_launch(chk * (pc2 ? 20 : (options().spmv_peer_split && pv ? 4 : 3)) + (pv ? 1 : 0));   // (pc2: 3 + 5 + its Chebyshev steps, approx.)
       }
       DFB_CUDA(cudaGraphLaunch(W->gexec[chunk], st));
-      iter += 20;
+      iter += chk;
       DFB_CHECK(convergence_test(iter));
       continue;
     }
     DFB_CHECK(arnoldi_step(iter, st));
     iter++;
-    if (iter % 20 == 0) DFB_CHECK(convergence_test(iter));
+    if (iter % chk == 0) DFB_CHECK(convergence_test(iter));
   }
   if (ph) {   // identical control flow on every rank: the communicator's counters advance by what this solve used
     *ph->seq += (unsigned long long)iter;

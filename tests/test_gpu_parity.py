@@ -396,6 +396,44 @@ def test_gmres_matches_oracle(api, oracle, m, state):
     fs.close()
 
 
+@pytest.mark.parametrize("every", [1, 5, 8])
+def test_finer_convergence_test_stops_on_a_prefix_of_the_default_history(api, oracle, every):
+    """DFB_GMRES_CHECK (opt-in; the reference tests every 20th iteration, krylov.c:281-290): same arithmetic, so the residual
+    history is a prefix of the default run's, the run stops at the FIRST tested iteration that meets the tolerance, and the
+    returned solution has exactly the residual the history claims."""
+    from dedflow_b200 import lib as dlib
+    mesh = boxmesh.make_box(12)
+    fs, wg, dwg = make_pair(api, oracle, mesh, "B")
+    N = mesh.num_node
+    wg, dwg = torch.from_numpy(wg).cuda(), torch.from_numpy(dwg).cuda()
+    F = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    fs.assemble_system(wg, dwg, F=F)
+    fs.assemble_system(wg, dwg, J=True)
+    dx20 = torch.zeros(6 * N, dtype=torch.float64, device="cuda")
+    it20, hist20 = fs.krylov_solve(dx20, F)
+    assert it20 % 20 == 0
+    try:
+        dlib.set_option("DFB_GMRES_CHECK", every)
+        dx = torch.zeros_like(dx20)
+        for _ in range(2):                               # second pass replays the re-captured graphs
+            dx.zero_()
+            it, hist = fs.krylov_solve(dx, F)
+            assert it <= it20 and (it % every == 0 or it == fs.max_iter)
+            assert np.abs(hist - hist20[:it + 1]).max() <= 1e-12 * hist20[0]
+            ok = lambda r: r < fs.atol or r < (hist[0] + 1e-16) * fs.rtol
+            assert ok(hist[it]) or it == fs.max_iter
+            assert not any(ok(hist[k]) for k in range(every, it, every))
+            y = torch.zeros_like(dx)
+            fs.matrix_matvec(dx, y)
+            assert abs((F - y)[:4 * N].norm().item() - hist[-1]) <= 1e-8 * hist[0]
+    finally:
+        dlib.set_option("DFB_GMRES_CHECK", 20)
+    dx.zero_()
+    it, hist = fs.krylov_solve(dx, F)                    # and the default is back
+    assert it == it20 and np.array_equal(hist, hist20)
+    fs.close()
+
+
 def test_gmres_dead_tail_rank_one(api, oracle):
     """b[4N:6N) != 0: the reference carries the dead rows through CGS (defect D4); ours does so with one scalar per
     basis vector.  x0 != 0 as well.  40 iterations: beyond that this (never-converging) system stagnates and single-pass
