@@ -258,7 +258,8 @@ __global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int
                                                  const f64* __restrict__ A10, const f64* __restrict__ A11, f64 alpha,
                                                  const f64* __restrict__ x, size_t x_poff, f64 beta, f64* __restrict__ y,
                                                  size_t y_poff, const P2PView* __restrict__ pv, unsigned hoff, int n_interior,
-                                                 int post_flag) {
+                                                 int post_flag, const unsigned* __restrict__ run_if) {
+  if (run_if && *run_if == 0u) return;   // x is known to be all zero (y = y - A 0): the caller's flag, grid-uniform
   bool halo_block = false;   // block-uniform: this block owns boundary rows (they reference ghost columns)
   if (PEER) {
     // Deferred halo flag: the update kernel before this launch stored z~'s boundary entries into the neighbours but left the
@@ -465,7 +466,8 @@ static bool spmv_tma_on() { return options().spmv_tma != 0; }   // 0 selects the
 enum { LAY_ABI = 0, LAY_XAOS = 1, LAY_YAOS = 2 };
 int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, const f64* A00, const f64* A01, const f64* A10,
                 const f64* A11, f64 alpha, const f64* x, size_t x_poff, f64 beta, f64* y, size_t y_poff, cudaStream_t st,
-                int layout = LAY_ABI, const P2PView* pv = nullptr, unsigned hoff = 0, int n_interior = 0, int post_flag = 0) {
+                int layout = LAY_ABI, const P2PView* pv = nullptr, unsigned hoff = 0, int n_interior = 0, int post_flag = 0,
+                const unsigned* run_if = nullptr) {
   if (row1 <= row0) return DFB_OK;
   const i64 rows = row1 - row0;
   if (pv && layout != (LAY_XAOS | LAY_YAOS)) { set_error("launch_spmv: the peer-memory mat-vec runs on interleaved vectors only"); return DFB_ERR_ARG; }
@@ -490,17 +492,17 @@ int launch_spmv(int row0, int row1, const int* row_ptr, const int* col_ind, cons
   const int grid8 = ceil_div(rows * 8, 256);
   if (pv) {
     k_spmv_fs<8, true, true, true><<<grid8, 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x, x_poff, beta, y,
-                                                         y_poff, pv, hoff, n_interior, post_flag);
+                                                         y_poff, pv, hoff, n_interior, post_flag, nullptr);
   } else if (layout == LAY_YAOS) {
     k_spmv_fs<8, false, false, true><<<grid8, 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x, x_poff, beta, y,
-                                                           y_poff, nullptr, 0u, 0, 0);
+                                                           y_poff, nullptr, 0u, 0, 0, run_if);
   } else if (layout == (LAY_XAOS | LAY_YAOS)) {
     k_spmv_fs<8, false, true, true><<<grid8, 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11, alpha, x, x_poff, beta, y,
-                                                          y_poff, nullptr, 0u, 0, 0);
+                                                          y_poff, nullptr, 0u, 0, 0, nullptr);
   } else if (layout == LAY_ABI) {
 #define DFB_SPMV(G)                                                                                                              \
   k_spmv_fs<G, false, false, false><<<ceil_div(rows * G, 256), 256, 0, st>>>(row0, row1, row_ptr, col_ind, A00, A01, A10, A11,   \
-                                                                             alpha, x, x_poff, beta, y, y_poff, nullptr, 0u, 0, 0)
+                                                                             alpha, x, x_poff, beta, y, y_poff, nullptr, 0u, 0, 0, nullptr)
     switch (spmv_group()) {
       case 4: DFB_SPMV(4); break;
       case 32: DFB_SPMV(32); break;
@@ -1033,6 +1035,14 @@ __global__ void __launch_bounds__(256) k_sumsq(size_t n, const f64* __restrict__
 }
 
 // gather the live part of an ABI-layout vector (u at v[3i + c], p at v[poff + i]) into the interleaved layout out[4i + c]
+// *flag = 1 if any of v[0, n) is not (plus or minus) zero -- NaN counts as nonzero.  The flag starts at 0.
+__global__ void __launch_bounds__(256) k_nonzero_flag(size_t n, const f64* __restrict__ v, unsigned* flag) {
+  bool any = false;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+    any |= (__double_as_longlong(v[i]) << 1) != 0ll;
+  if (__syncthreads_or(any) && threadIdx.x == 0) *flag = 1u;
+}
+
 __global__ void k_pack_live(int n_own, const f64* __restrict__ v, size_t poff, f64* __restrict__ out) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)4 * n_own) return;
@@ -1387,7 +1397,12 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     DFB_CHECK(W->par.halo_end(d_x, st, W->par.user));
     DFB_CHECK(launch_spmv(W->n_interior, n_own, rp, ci, A00, A01, A10, A11, -1.0, d_x, poffN, 1.0, QCOL(0), 0, st, LAY_YAOS));
   } else {
-    DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, -1.0, d_x, poffN, 1.0, QCOL(0), 0, st, LAY_YAOS));
+    // a Newton driver starts every solve from x = 0 (main.c:211): one sweep over x decides whether the mat-vec has anything to do
+    DFB_CUDA(cudaMemsetAsync(W->ctr + 3, 0, sizeof(unsigned), st));
+    k_nonzero_flag<<<NCHUNK, 256, 0, st>>>((size_t)4 * N, d_x, W->ctr + 3);
+    DFB_LAUNCH_CHECK();
+    DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, -1.0, d_x, poffN, 1.0, QCOL(0), 0, st, LAY_YAOS, nullptr, 0u, 0, 0,
+                          W->ctr + 3));
   }
   k_sumsq<<<NCHUNK, 256, 0, st>>>(nl, QCOL(0), W->part);
   DFB_LAUNCH_CHECK();
