@@ -47,6 +47,7 @@ static bool apply_option(Options& o, const char* key, const char* v) {
   if (is("DFB_SPMV_TMA")) { o.spmv_tma = atoi(v); return true; }
   if (is("DFB_SPMV_PEER_SPLIT")) { o.spmv_peer_split = atoi(v) != 0; return true; }
   if (is("DFB_HALO_DEFER")) { o.halo_defer = atoi(v) != 0; return true; }
+  if (is("DFB_GIVENS_DEFER")) { o.givens_defer = atoi(v) != 0; return true; }
   if (is("DFB_GMRES_CHECK")) { o.gmres_check = std::min(20, std::max(1, atoi(v))); return true; }
   if (is("DFB_KRYLOV_TMA")) { o.krylov_tma = atoi(v) != 0; return true; }
   if (is("DFB_GRAPH")) { o.graph = atoi(v) != 0; return true; }

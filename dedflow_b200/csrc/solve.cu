@@ -537,7 +537,7 @@ __global__ void k_pc_setup(int N, const int* __restrict__ row_ptr, const int* __
   }
   const int k = lo - start;
   if (lo >= end || col_ind[lo] != i) {   // no diagonal entry (orphan node in a converted mesh): identity block, flagged
-    if (bad) atomicExch(bad, 1);
+    if (bad) *(volatile int*)bad = 1;
     for (int t = 0; t < 9; t++) dinv00[(size_t)i * 9 + t] = (t % 4 == 0) ? 1.0 : 0.0;
     dinv11[i] = 1.0;
     return;
@@ -554,7 +554,7 @@ __global__ void k_pc_setup(int N, const int* __restrict__ row_ptr, const int* __
   const f64 det = B[0][0] * c00 + B[0][1] * c01 + B[0][2] * c02;
   const f64 a11 = A11[start + k];
   if (det == 0.0 || a11 == 0.0 || !isfinite(det) || !isfinite(a11)) {   // singular diagonal block: identity, flagged (an inf here
-    if (bad) atomicExch(bad, 2);                                         // would poison the whole Krylov basis)
+    if (bad) *(volatile int*)bad = 2;                                    // would poison the whole Krylov basis)
     for (int t = 0; t < 9; t++) dinv00[(size_t)i * 9 + t] = (t % 4 == 0) ? 1.0 : 0.0;
     dinv11[i] = 1.0;
     return;
@@ -812,13 +812,49 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
   if (!last_block(ctr, gridDim.x * gridDim.y)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = gridDim.x;
-  for (int j = warp; j < ncol; j += 8) {
-    f64 s = 0.0;
-    for (int c = lane; c < nchunk; c += 32) s += __ldcg(part + (size_t)j * NCHUNK + c);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULLM, s, o);
+  // The scalar Givens step of the PREVIOUS iteration (nothing has needed it until now: its outputs are the scale and the
+  // dead-tail coefficient the coming update reads) runs on one thread of the last warp WHILE the other warps sum the partial
+  // dots -- two serial tails of ~1.5 us each side by side instead of one after the other at the end of two kernels.
+  const bool prev = soff_prev != 0u;
+  const int itp = ncol - 2;   // the previous iteration
+  if (prev) {
+    gmres_step_stage(itp, hcol_prev, U.gv, U.tailc, h_s, gv_s, tc_s);
+    if (pv) {   // the ranks' partial norms of the newest column: published at the end of the previous update, long since arrived
+      const unsigned long long sp = pv->seq_base[0] + soff_prev;
+      if ((int)threadIdx.x < pv->nranks)
+        smj[0][threadIdx.x] = ll_load(pv, pv->mbox_local + p2p_b_ll(pv->nranks, (int)(sp & 1ull), threadIdx.x), (unsigned)sp);
+    }
+    __syncthreads();
+  }
+  if (prev && warp == 7) {
     if (lane == 0) {
-      if (pv) hsum[j] = s; else h[j] = s;
+      if (pv) {
+        f64 nrm2 = 0.0;
+        for (int r = 0; r < pv->nranks; r++) nrm2 += smj[0][r];
+        U.S->nrm2_live = nrm2;
+      }
+      gmres_step_dev(itp, U.S, hcol_prev, U.gv, U.beta, U.tailc, U.res_hist, U.qs, h_s, gv_s, tc_s);
+    }
+  } else {
+    // column j by warp j mod nw; four columns per trip so that their loads are in flight together (per column the chunks are
+    // still added in ascending order by the same lanes: bit-identical to the one-column loop)
+    const int nw = prev ? 7 : 8;
+    for (int j = warp; j < ncol; j += 4 * nw) {
+      f64 sv[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int c = lane; c < nchunk; c += 32) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (j + u * nw < ncol) sv[u] += __ldcg(part + (size_t)(j + u * nw) * NCHUNK + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        f64 v = sv[u];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLM, v, o);
+        if (lane == 0 && j + u * nw < ncol) {
+          if (pv) hsum[j + u * nw] = v; else h[j + u * nw] = v;
+        }
+      }
     }
   }
   if (pv) {
@@ -832,21 +868,6 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
     for (int t = threadIdx.x; t < R * ncol; t += 256) {
       const int r = t / ncol, j = t - r * ncol;
       ll_store(pv->mbox_peer[r] + p2p_a_ll(R, par, pv->rank, j), hsum[j], (unsigned)seq);
-    }
-    // meanwhile: the norm of the newest column (published at the end of the previous update, long since arrived) and the
-    // scalar Givens step of the previous iteration, which nothing has needed until now
-    if (soff_prev) {
-      const int itp = ncol - 2;   // the previous iteration
-      gmres_step_stage(itp, hcol_prev, U.gv, U.tailc, h_s, gv_s, tc_s);
-      const unsigned long long sp = pv->seq_base[0] + soff_prev;
-      if ((int)threadIdx.x < R) smj[0][threadIdx.x] = ll_load(pv, pv->mbox_local + p2p_b_ll(R, (int)(sp & 1ull), threadIdx.x), (unsigned)sp);
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        f64 nrm2 = 0.0;
-        for (int r = 0; r < R; r++) nrm2 += smj[0][r];
-        U.S->nrm2_live = nrm2;
-        gmres_step_dev(itp, U.S, hcol_prev, U.gv, U.beta, U.tailc, U.res_hist, U.qs, h_s, gv_s, tc_s);
-      }
     }
     // all slots are polled in parallel (one thread per (rank, column)), then summed in rank order
     for (int t = threadIdx.x; t < R * ncol; t += 256) {
@@ -1220,7 +1241,13 @@ using namespace dfb;
 struct dfb_gmres {
   int N = 0, maxit = 0, ldh = 0;
   int n_own = 0;  // rows reduced in the inner products (== N on a single GPU)
-  f64 *Q = nullptr, *H = nullptr, *gv = nullptr, *beta = nullptr, *tailc = nullptr, *res_hist = nullptr;
+  f64 *Q = nullptr, *H = nullptr, *gv = nullptr, *beta = nullptr, *tailc = nullptr;
+  // Host-visible status block (pinned, mapped): the residual history [0, maxit] and, behind it, the preconditioner-setup flag.
+  // The one thread that runs the scalar Arnoldi step stores each residual straight into it (a posted PCIe write), so the
+  // convergence tests cost the host one stream synchronisation and no device-to-host copy.
+  f64* h_status = nullptr;    // host address
+  f64* res_hist = nullptr;    // the same memory as the device sees it
+  int* pc_bad_dev = nullptr;  // device view of the flag word (h_status + maxit + 1)
   f64 *z = nullptr, *t = nullptr, *part = nullptr, *dinv00 = nullptr, *dinv11 = nullptr, *tail_coef = nullptr;
   f64 *qs = nullptr, *draw = nullptr, *ycoef = nullptr, *pcrec = nullptr;   // column scales, raw dots, combination coefficients, packed P^-1
   GmresScalars* S = nullptr;
@@ -1282,7 +1309,7 @@ int dfb_gmres_create(dfb_gmres** out, int N, int maxit) {
   const size_t nl = (size_t)4 * N;
   struct { f64** p; size_t n; } allocs[] = {
       {&w->Q, nl * ((size_t)maxit + 1)}, {&w->H, (size_t)w->ldh * maxit}, {&w->gv, (size_t)2 * maxit},
-      {&w->beta, (size_t)maxit + 1},    {&w->tailc, (size_t)maxit + 1},  {&w->res_hist, (size_t)maxit + 1},
+      {&w->beta, (size_t)maxit + 1},    {&w->tailc, (size_t)maxit + 1},
       {&w->z, (size_t)6 * N},           {&w->t, (size_t)6 * N},          {&w->part, (size_t)NCHUNK * (maxit + 2) + UCHUNK},
       {&w->dinv00, (size_t)9 * N},      {&w->dinv11, (size_t)N},         {&w->tail_coef, 8},
       {&w->qs, (size_t)maxit + 2},      {&w->draw, (size_t)maxit + 2},   {&w->ycoef, (size_t)maxit + 2},
@@ -1295,8 +1322,12 @@ int dfb_gmres_create(dfb_gmres** out, int N, int maxit) {
     }
     w->bytes += a.n * sizeof(f64);
   }
+  DFB_CUDA(cudaHostAlloc(&w->h_status, sizeof(f64) * ((size_t)maxit + 2), cudaHostAllocMapped));
+  memset(w->h_status, 0, sizeof(f64) * ((size_t)maxit + 2));
+  DFB_CUDA(cudaHostGetDevicePointer(&w->res_hist, w->h_status, 0));
+  w->pc_bad_dev = reinterpret_cast<int*>(w->res_hist + maxit + 1);
   DFB_CUDA(cudaMalloc(&w->S, sizeof(GmresScalars)));
-  DFB_CUDA(cudaMalloc(&w->ctr, 4 * sizeof(unsigned)));   // [0..1] last-block elections, [2] preconditioner-setup flag
+  DFB_CUDA(cudaMalloc(&w->ctr, 4 * sizeof(unsigned)));   // [0..1] last-block elections, [3] "x0 is nonzero" flag
   DFB_CUDA(cudaMemset(w->ctr, 0, 4 * sizeof(unsigned)));
   DFB_CUDA(cudaMemset(w->z, 0, sizeof(f64) * 6 * (size_t)N));
   DFB_CUDA(cudaMemset(w->t, 0, sizeof(f64) * 6 * (size_t)N));
@@ -1306,7 +1337,8 @@ int dfb_gmres_create(dfb_gmres** out, int N, int maxit) {
 
 void dfb_gmres_destroy(dfb_gmres* w) {
   if (!w) return;
-  cudaFree(w->Q); cudaFree(w->H); cudaFree(w->gv); cudaFree(w->beta); cudaFree(w->tailc); cudaFree(w->res_hist);
+  cudaFree(w->Q); cudaFree(w->H); cudaFree(w->gv); cudaFree(w->beta); cudaFree(w->tailc);
+  if (w->h_status) cudaFreeHost(w->h_status);
   cudaFree(w->z); cudaFree(w->t); cudaFree(w->part); cudaFree(w->dinv00); cudaFree(w->dinv11); cudaFree(w->tail_coef);
   cudaFree(w->qs); cudaFree(w->draw); cudaFree(w->ycoef); cudaFree(w->pcrec);
   cudaFree(w->S); cudaFree(w->ctr);
@@ -1376,8 +1408,8 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   if (ext_dinv00) {  // the caller has run PCSetup already (drop-in layer: the PC tree owns the arrays)
     dinv00 = ext_dinv00; dinv11 = ext_dinv11;
   } else {           // preconditioner setup on every solve, like KrylovSolve -> PCSetup (krylov.c:453)
-    DFB_CUDA(cudaMemsetAsync(W->ctr + 2, 0, sizeof(unsigned), st));
-    k_pc_setup<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, rp, ci, A00, A11, W->dinv00, W->dinv11, reinterpret_cast<int*>(W->ctr + 2));
+    *reinterpret_cast<volatile int*>(W->h_status + maxit + 1) = 0;   // (host store: every earlier solve of this workspace ended synchronised)
+    k_pc_setup<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, rp, ci, A00, A11, W->dinv00, W->dinv11, W->pc_bad_dev);
     DFB_LAUNCH_CHECK();
   }
   k_pc_pack<<<ceil_div(n_own, 128), 128, 0, st>>>(n_own, dinv00, dinv11, W->pcrec);
@@ -1447,6 +1479,9 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   // (DFB_GMRES_CHECK, 1..20) stops closer to the first iteration that meets the tolerance at the price of one host round trip
   // per test -- same arithmetic, the residual history is a prefix of the default's
   const int chk = std::min(20, std::max(1, options().gmres_check));
+  // the scalar Givens step of iteration j runs in the tail of iteration j + 1's multi-dot, next to the partial-dot sums
+  // (peer-memory mode always; one GPU unless DFB_GIVENS_DEFER=0; the NCCL path keeps its own step kernel)
+  const bool givens_defer = pv || (!W->parallel && options().givens_defer);
   auto arnoldi_step = [&](int iter, cudaStream_t s) -> int {
     // w_raw = A z~_iter into column iter + 1 (no scaling: the update applies s_iter)
     f64* w = QCOL(iter + 1);
@@ -1470,7 +1505,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     const int ncol = iter + 1;
     const unsigned soff = pv ? (unsigned)iter + 1u : 0u;
     // peer-memory mode: the norm + Givens step of the previous iteration is still pending unless it closed a chunk (a convergence test follows a chunk)
-    const unsigned soff_prev = (pv && iter > 0 && iter % chk != 0) ? (unsigned)iter : 0u;
+    const unsigned soff_prev = (givens_defer && iter > 0 && iter % chk != 0) ? (unsigned)iter : 0u;
     prof.begin("multidot", s);
     const int ny = ceil_div(ncol, JT);
     const int mg = std::max(1, std::min(mgrid, (4 * num_sms()) / ny));   // one resident wave of (row chunk, column group) blocks
@@ -1486,7 +1521,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
     // update + norm + P^-1 (+ Givens step on one GPU; + the fused collectives in peer-memory mode)  (krylov.c:176-183, 229-277)
     prof.begin("update", s);
     k_update<<<ugrid, 256, 0, s>>>(nl, Q, ldq, ncol, W->draw, HCOL(iter), iter ? HCOL(iter - 1) : HCOL(0), w, W->part, W->ctr + 1,
-                                   pv ? 2 : (W->parallel ? 1 : 0), US, pc2 ? nullptr : W->pcrec, zvec, pv, soff,
+                                   pv ? 2 : ((W->parallel || givens_defer) ? 1 : 0), US, pc2 ? nullptr : W->pcrec, zvec, pv, soff,
                                    (unsigned)iter + 2u /* the halo of z~_{iter+1} leaves from this kernel */, halo_defer);
     DFB_LAUNCH_CHECK();
     prof.end(s);
@@ -1504,6 +1539,13 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
         DFB_LAUNCH_CHECK();
         prof.end(s);
       }
+    } else if (givens_defer) {   // one GPU: same folding, the step runs on its own where a convergence test (or the end) follows
+      if ((iter + 1) % chk == 0 || iter + 1 == maxit) {
+        prof.begin("step", s);
+        k_gmres_step<<<1, 128, 0, s>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist, W->qs);
+        DFB_LAUNCH_CHECK();
+        prof.end(s);
+      }
     } else if (W->parallel) {
       prof.begin("allreduce nrm+step", s);
       DFB_CHECK(W->par.allreduce(&W->S->nrm2_live, 1, s, W->par.user));
@@ -1515,10 +1557,12 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   };
   // the reference's only convergence test, after every 20th iteration (krylov.c:281-290)
   auto convergence_test = [&](int done) -> int {
-    DFB_CUDA(cudaMemcpyAsync(hist.data(), W->res_hist, sizeof(f64) * ((size_t)done + 1), cudaMemcpyDeviceToHost, st));
     if (ph) DFB_CUDA(cudaMemcpyAsync(&peer_err, ph->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    if (!ext_dinv00) DFB_CUDA(cudaMemcpyAsync(&pc_bad, W->ctr + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     DFB_CUDA(cudaStreamSynchronize(st));
+    const volatile f64* hs = W->h_status;   // written by the device, complete once the stream is idle
+    pc_bad = ext_dinv00 ? 0u : (unsigned)*reinterpret_cast<const volatile int*>(W->h_status + maxit + 1);
+    hist[0] = hs[0];
+    hist[(size_t)done] = hs[done];
     if (pc_bad) {
       set_error("dfb_gmres_solve: the block-Jacobi setup met a %s (node row without / with a singular diagonal block)",
                 pc_bad == 1 ? "missing diagonal entry" : "singular diagonal block");
@@ -1533,7 +1577,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
   // The iterations between two convergence tests (20: 60 launches with fixed arguments for a given workspace and
   // matrix) are captured once into a CUDA graph per chunk and replayed -- the launch gaps shrink, the host does one call.
   const bool use_graph = (!W->parallel || pv) && !prof.on && options().graph != 0;
-  const dfb_gmres::GraphKey gkey = {rp, ci, A00, A01, A10, A11, pv, pc2, n_own, W->n_interior, options().spmv_peer_split | (options().halo_defer << 1) | (chk << 2)};
+  const dfb_gmres::GraphKey gkey = {rp, ci, A00, A01, A10, A11, pv, pc2, n_own, W->n_interior, options().spmv_peer_split | (options().halo_defer << 1) | (options().givens_defer << 2) | (chk << 3)};
   while (!converged && iter < maxit && !peer_err) {
     if (use_graph && iter % chk == 0 && iter + chk <= maxit) {
       const size_t chunk = (size_t)iter / chk;
@@ -1552,7 +1596,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
         cudaGraphDestroy(graph);
         DFB_CUDA(ie);
       } else {
-        count_launch(chk * (pc2 ? 20 : (options().spmv_peer_split && pv ? 4 : 3)) + (pv ? 1 : 0));   // (pc2: 3 + 5 + its Chebyshev steps, approx.)
+        count_launch(chk * (pc2 ? 20 : (options().spmv_peer_split && pv ? 4 : 3)) + (givens_defer ? 1 : 0));   // (pc2: 3 + 5 + its Chebyshev steps, approx.)
       }
       DFB_CUDA(cudaGraphLaunch(W->gexec[chunk], st));
       iter += chk;
@@ -1590,10 +1634,10 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
       DFB_CHECK(W->par.halo_end(d_x, st, W->par.user));
     }
   }
-  DFB_CUDA(cudaMemcpyAsync(hist.data(), W->res_hist, sizeof(f64) * ((size_t)iter + 1), cudaMemcpyDeviceToHost, st));
   if (ph && !peer_err) DFB_CUDA(cudaMemcpyAsync(&peer_err, ph->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-  if (!ext_dinv00) DFB_CUDA(cudaMemcpyAsync(&pc_bad, W->ctr + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   DFB_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k <= iter; k++) hist[(size_t)k] = const_cast<const volatile f64*>(W->h_status)[k];
+  if (!ext_dinv00) pc_bad = (unsigned)*reinterpret_cast<const volatile int*>(W->h_status + maxit + 1);
   if (pc_bad) {
     set_error("dfb_gmres_solve: the block-Jacobi setup met a %s (node row without / with a singular diagonal block)",
               pc_bad == 1 ? "missing diagonal entry" : "singular diagonal block");
