@@ -904,28 +904,21 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
   __shared__ f64 sh[128];    // c_i = h_i s_i: coefficient of the stored (unnormalised) column i
   __shared__ f64 shh[128];   // h_i: the Hessenberg column
   __shared__ f64 sm[8];
-  __shared__ f64 s_sj, s_tcj;
   __shared__ f64 sgv[256], stc[128];   // staged inputs of the scalar Givens step (gmres_step_dev)
   const int jc = ncol - 1;   // index of the newest column w~_j (the one A z~ was formed from)
   const unsigned long long seq = pv ? pv->seq_base[0] + soff : 0ull;
-  if (threadIdx.x == 0) {   // scale and dead-tail coefficient of the newest column: written by the previous step's Givens update
-    s_sj = U.qs[jc];
-    s_tcj = U.tailc[jc];
+  // scale of the newest column (written by the previous step's Givens update): every thread reads it itself -- one broadcast
+  // transaction per warp, in flight together with the coefficient loads below instead of a round trip + barrier before them
+  const f64 sj = U.qs[jc];
+  for (int i = threadIdx.x; i < ncol; i += 256) {
+    const f64 d = draw[i];   // raw dots, all-reduced (peer mode: by the multi-dot's last block)
+    const f64 si = U.qs[i];
+    const f64 h = si * sj * d;
+    shh[i] = h;
+    sh[i] = h * si;
+    if (mode != 0 && blockIdx.x == 0) hcol[i] = h;   // a later kernel's Givens step reads the column from global memory
   }
   __syncthreads();
-  {
-    const f64 sj = s_sj;
-    for (int i = threadIdx.x; i < ncol; i += 256) {
-      const f64 d = draw[i];   // raw dots, all-reduced (peer mode: by the multi-dot's last block)
-      const f64 si = U.qs[i];
-      const f64 h = si * sj * d;
-      shh[i] = h;
-      sh[i] = h * si;
-      if (pv && blockIdx.x == 0) hcol[i] = h;   // the next multi-dot's Givens step reads the column from global memory
-    }
-  }
-  __syncthreads();
-  const f64 sj = s_sj;
   const double2* q2 = reinterpret_cast<const double2*>(Q);
   double2* w2 = reinterpret_cast<double2*>(w);
   double2* z2 = reinterpret_cast<double2*>(z);
@@ -998,9 +991,11 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
   f64 s = 0.0;
   for (int c = threadIdx.x; c < (int)gridDim.x; c += 256) s += __ldcg(part + c);
   s = block_sum_256(s, sm);
-  // inputs of the scalar tail below from shared memory (h itself is in shh already)
-  gmres_step_stage(jc, nullptr, U.gv, U.tailc, nullptr, sgv, stc);
-  __syncthreads();
+  // inputs of the scalar tail below from shared memory (h itself is in shh already); mode 1 has no scalar tail here
+  if (mode != 1) {   // kernel-uniform
+    gmres_step_stage(jc, nullptr, U.gv, U.tailc, nullptr, sgv, stc);
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     *ctr = 0u;
     if (pv) {   // publish the partial sum of squares; the next update (or the step kernel) sums the ranks
@@ -1013,7 +1008,7 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
     } else {
       U.S->nrm2_live = s;
       if (mode == 0) gmres_step_dev(jc, U.S, hcol, U.gv, U.beta, U.tailc, U.res_hist, U.qs, shh, sgv, stc);
-      else for (int i = 0; i < ncol; i++) hcol[i] = shh[i];   // NCCL path: k_gmres_step reads the column from global memory
+      // (mode 1: the column is in global memory already, block 0's prologue stored it)
     }
   }
 }
