@@ -252,8 +252,13 @@ __device__ __forceinline__ void spmv_row_smem(const f64* __restrict__ p00, const
   }
 }
 
+#ifndef SPMV_MINB
+#define SPMV_MINB 1   // A/B builds (_build.build_variant): resident CTAs per SM the register allocation is held to.  Unconstrained:
+                      // 80 registers, 3 CTAs = 24 warps per SM; -DSPMV_MINB=4: 64 registers + 44 bytes of spills, 32 warps,
+                      // and a SLOWER solve (5.17 vs 5.02 ms on the same GPU): the kernel wants registers, not warps
+#endif
 template <int G, bool PEER, bool AOSX, bool AOSY>
-__global__ void __launch_bounds__(256) k_spmv_fs(int row0, int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
+__global__ void __launch_bounds__(256, SPMV_MINB) k_spmv_fs(int row0, int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
                                                  const f64* __restrict__ A00, const f64* __restrict__ A01,
                                                  const f64* __restrict__ A10, const f64* __restrict__ A11, f64 alpha,
                                                  const f64* __restrict__ x, size_t x_poff, f64 beta, f64* __restrict__ y,
