@@ -1322,9 +1322,13 @@ int dfb_gmres_create(dfb_gmres** out, int N, int maxit) {
     }
     w->bytes += a.n * sizeof(f64);
   }
-  DFB_CUDA(cudaHostAlloc(&w->h_status, sizeof(f64) * ((size_t)maxit + 2), cudaHostAllocMapped));
+  if (cudaHostAlloc(&w->h_status, sizeof(f64) * ((size_t)maxit + 2), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer(&w->res_hist, w->h_status, 0) != cudaSuccess) {
+    set_error("dfb_gmres_create: no mapped host memory for the status block");
+    dfb_gmres_destroy(w);
+    return DFB_ERR_CUDA;
+  }
   memset(w->h_status, 0, sizeof(f64) * ((size_t)maxit + 2));
-  DFB_CUDA(cudaHostGetDevicePointer(&w->res_hist, w->h_status, 0));
   w->pc_bad_dev = reinterpret_cast<int*>(w->res_hist + maxit + 1);
   DFB_CUDA(cudaMalloc(&w->S, sizeof(GmresScalars)));
   DFB_CUDA(cudaMalloc(&w->ctr, 4 * sizeof(unsigned)));   // [0..1] last-block elections, [3] "x0 is nonzero" flag

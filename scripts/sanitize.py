@@ -25,11 +25,22 @@ for mesh in (delaunay_mesh(120, 12), boxmesh.make_box(5)):
         dlib.set_option("DFB_J_VARIANT", variant)
         fs.assemble_system(wg, dwg, J=True, mode="gather")
     dlib.set_option("DFB_J_VARIANT", "pairs")
+    for variant in ("scratch", "pipe", "patch"):     # the residual kernels
+        dlib.set_option("DFB_F_VARIANT", variant)
+        fs.assemble_system(wg, dwg, F=F, mode="gather")
     x = torch.randn(6 * N, dtype=torch.float64, device="cuda")
     y = torch.zeros_like(x)
     fs.matrix_matvec(x, y)
     dx = torch.zeros_like(x)
     it, hist = fs.krylov_solve(dx, F)
+    for key, val in (("DFB_GMRES_CHECK", 5), ("DFB_GIVENS_DEFER", 0), ("DFB_GRAPH", 0)):   # the other solver paths
+        dlib.set_option(key, val)
+        fs.krylov_solve(dx, F)                        # (x0 != 0 from here on: r0 runs its mat-vec)
+    dlib.set_option("DFB_GMRES_CHECK", 20); dlib.set_option("DFB_GIVENS_DEFER", 1); dlib.set_option("DFB_GRAPH", 1)
+    fs.set_preconditioner("schur2")
+    dx.zero_()
+    fs.krylov_solve(dx, F)
+    fs.set_preconditioner("jacobi")
     state = [torch.from_numpy(a.copy()).cuda() for a in boxmesh.state_initial(mesh)]
     h = fs.time_step(*state)
     torch.cuda.synchronize()
