@@ -253,9 +253,10 @@ __device__ __forceinline__ void spmv_row_smem(const f64* __restrict__ p00, const
 }
 
 #ifndef SPMV_MINB
-#define SPMV_MINB 1   // A/B builds (_build.build_variant): resident CTAs per SM the register allocation is held to.  Unconstrained:
-                      // 80 registers, 3 CTAs = 24 warps per SM; -DSPMV_MINB=4: 64 registers + 44 bytes of spills, 32 warps,
-                      // and a SLOWER solve (5.17 vs 5.02 ms on the same GPU): the kernel wants registers, not warps
+// Resident CTAs per SM the register allocation is held to: 3 x 256 threads = 24 warps at <= 80 registers.  Two registers more
+// (82 -> allocated as 88) silently drop the kernel to 2 CTAs per SM and cost 13 % (78.8 vs 69.5 us in-solve at 1M tets); 4 CTAs
+// (64 registers, 44 bytes of spills) are slower as well.  (-DSPMV_MINB=n: A/B builds, _build.build_variant.)
+#define SPMV_MINB 3
 #endif
 template <int G, bool PEER, bool AOSX, bool AOSY>
 __global__ void __launch_bounds__(256, SPMV_MINB) k_spmv_fs(int row0, int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
