@@ -166,6 +166,8 @@ struct P2PView {
   const int* tgt_ptr;
   const int* tgt_q;
   const int* tgt_rid;
+  f64* nrm_part;                           // this rank's partial norm of the newest column, parked by the update for a later kernel to publish
+  f64* const* tgt_addr;                    // the same targets resolved once: address of the node's four entries in that neighbour's z
   // Bounded waits: every poll loop below gives up after `timeout_ns` (a peer died or returned early from the solve) and raises
   // *err; once *err is set every later wait of every later kernel returns at once, so the stream drains and the host sees
   // the word at its next synchronisation point (dfb_gmres_solve_pc returns DFB_ERR_PEER).  A hung peer can therefore cost

@@ -123,6 +123,8 @@ struct dfb_comm {
   void* peer_base[P2P_MAXR] = {nullptr};
   int* d_remote_nodes = nullptr;
   int *d_tgt_ptr = nullptr, *d_tgt_q = nullptr, *d_tgt_rid = nullptr;
+  f64** d_tgt_addr = nullptr;
+  f64* d_nrm_part = nullptr;
   unsigned* d_push_ctr = nullptr;
   unsigned* d_err = nullptr;            // raised by a kernel whose bounded wait ran out (common.cuh p2p_give_up)
   unsigned long long seq = 0, hseq = 0; // sequence counters of the fused collectives: ONE owner per communicator
@@ -163,7 +165,7 @@ void dfb_comm_destroy(dfb_comm* c) {
   cudaFree(c->d_send_nodes); cudaFree(c->d_recv_nodes); cudaFree(c->d_send_buf); cudaFree(c->d_recv_buf);
   for (int r = 0; r < c->nranks && r < P2P_MAXR; r++)
     if (c->peer_base[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_base[r]);
-  cudaFree(c->d_tgt_ptr); cudaFree(c->d_tgt_q); cudaFree(c->d_tgt_rid);
+  cudaFree(c->d_tgt_ptr); cudaFree(c->d_tgt_q); cudaFree(c->d_tgt_rid); cudaFree(c->d_tgt_addr); cudaFree(c->d_nrm_part);
   cudaFree(c->shared); cudaFree(c->d_remote_nodes); cudaFree(c->d_push_ctr); cudaFree(c->d_err); cudaFree(c->d_seq_base); cudaFree(c->d_view);
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
   if (c->ev_done) cudaEventDestroy(c->ev_done);
@@ -314,7 +316,11 @@ int dfb_comm_p2p_connect(dfb_comm* c, const void* handles, const int* h_remote_n
         tq[pos] = q;
         trid[pos] = h_remote_nodes[t];
       }
-    cudaFree(c->d_tgt_ptr); cudaFree(c->d_tgt_q); cudaFree(c->d_tgt_rid);
+    std::vector<f64*> taddr((size_t)c->n_send);
+    for (int t = 0; t < c->n_send; t++) taddr[(size_t)t] = v.z_peer[v.nbr[tq[(size_t)t]]] + (size_t)trid[(size_t)t] * 4;
+    cudaFree(c->d_tgt_ptr); cudaFree(c->d_tgt_q); cudaFree(c->d_tgt_rid); cudaFree(c->d_tgt_addr);
+    DFB_CUDA(cudaMalloc(&c->d_tgt_addr, sizeof(f64*) * (size_t)c->n_send));
+    DFB_CUDA(cudaMemcpy(c->d_tgt_addr, taddr.data(), sizeof(f64*) * (size_t)c->n_send, cudaMemcpyHostToDevice));
     DFB_CUDA(cudaMalloc(&c->d_tgt_ptr, sizeof(int) * ((size_t)n + 1)));
     DFB_CUDA(cudaMalloc(&c->d_tgt_q, sizeof(int) * (size_t)c->n_send));
     DFB_CUDA(cudaMalloc(&c->d_tgt_rid, sizeof(int) * (size_t)c->n_send));
@@ -322,8 +328,13 @@ int dfb_comm_p2p_connect(dfb_comm* c, const void* handles, const int* h_remote_n
     DFB_CUDA(cudaMemcpy(c->d_tgt_q, tq.data(), sizeof(int) * (size_t)c->n_send, cudaMemcpyHostToDevice));
     DFB_CUDA(cudaMemcpy(c->d_tgt_rid, trid.data(), sizeof(int) * (size_t)c->n_send, cudaMemcpyHostToDevice));
     v.tgt_base = lo; v.tgt_n = n;
-    v.tgt_ptr = c->d_tgt_ptr; v.tgt_q = c->d_tgt_q; v.tgt_rid = c->d_tgt_rid;
+    v.tgt_ptr = c->d_tgt_ptr; v.tgt_q = c->d_tgt_q; v.tgt_rid = c->d_tgt_rid; v.tgt_addr = c->d_tgt_addr;
   }
+  if (!c->d_nrm_part) {
+    DFB_CUDA(cudaMalloc(&c->d_nrm_part, sizeof(f64)));
+    DFB_CUDA(cudaMemset(c->d_nrm_part, 0, sizeof(f64)));
+  }
+  v.nrm_part = c->d_nrm_part;
   if (!c->d_push_ctr) {
     DFB_CUDA(cudaMalloc(&c->d_push_ctr, sizeof(unsigned)));
     DFB_CUDA(cudaMemset(c->d_push_ctr, 0, sizeof(unsigned)));

@@ -87,7 +87,6 @@ struct GmresScalars {
   f64 tail2;       // |b[4N:6N)|^2 (after the cross-rank reduction)
   f64 inv_norm;    // 1/||w||
   f64 rnrm_init;
-  f64 cw;          // peer-memory mode: dead-tail coefficient of the current w, -sum_j h_j tailc_j (set by k_update)
 };
 
 struct UpdateScalars {   // device arrays of the recurrence (all persistent in the workspace)
@@ -272,9 +271,16 @@ __global__ void __launch_bounds__(256, SPMV_MINB) k_spmv_fs(int row0, int n_rows
     // flag to us, so that its own completion (and with it the start of this mat-vec's interior rows, on both sides) does not
     // wait for a system-scope fence.  The first block raises it before anything else; the blocks that need the NEIGHBOURS'
     // flags are the last ones of the grid.
-    if (post_flag && blockIdx.x == 0 && (int)threadIdx.x < pv->n_nbr) {
+    if ((post_flag & 1) && blockIdx.x == 0 && (int)threadIdx.x < pv->n_nbr) {
       __threadfence_system();
       p2p_signal(pv->mbox_peer[pv->nbr[threadIdx.x]] + p2p_h_flag(pv->nranks, pv->rank), pv->seq_base[1] + hoff);
+    }
+    // Same for the partial norm the update parked (bit 1): a store to a peer at the very end of a kernel holds the kernel's
+    // completion for the NVLink round trip; here it costs one block a few hundred cycles.  Its readers (the next multi-dot's
+    // last block) are a whole mat-vec away.
+    if ((post_flag & 2) && blockIdx.x == 0 && (int)threadIdx.x >= 32 && (int)threadIdx.x < 32 + pv->nranks) {
+      const unsigned long long sq = pv->seq_base[0] + (hoff - 1u);   // the all-reduce sequence number of that update
+      ll_store(pv->mbox_peer[threadIdx.x - 32] + p2p_b_ll(pv->nranks, (int)(sq & 1ull), pv->rank), *pv->nrm_part, (unsigned)sq);
     }
     const int last_row = row0 + (int)((((size_t)blockIdx.x + 1) * blockDim.x - 1) / G);
     halo_block = last_row >= n_interior;
@@ -631,10 +637,9 @@ __device__ __forceinline__ double2 pc_half(const f64* __restrict__ rec, int half
 __device__ __forceinline__ bool push_half(const P2PView* __restrict__ pv, int tgt_base, int tgt_n, int i, int half, double2 v) {
   const int b = i - tgt_base;
   if (b < 0 || b >= tgt_n) return false;
-  for (int t = pv->tgt_ptr[b]; t < pv->tgt_ptr[b + 1]; t++) {
-    f64* zr = pv->z_peer[pv->nbr[pv->tgt_q[t]]];
-    *reinterpret_cast<double2*>(zr + (size_t)pv->tgt_rid[t] * 4 + 2 * half) = v;
-  }
+  const int* tp = pv->tgt_ptr;
+  f64* const* ta = pv->tgt_addr;   // resolved at connect time: two dependent loads before the store instead of five
+  for (int t = tp[b], te = tp[b + 1]; t < te; t++) *reinterpret_cast<double2*>(ta[t] + 2 * half) = v;
   return true;
 }
 
@@ -997,20 +1002,20 @@ __global__ void __launch_bounds__(256) k_update(size_t nl, const f64* __restrict
   f64 s = 0.0;
   for (int c = threadIdx.x; c < (int)gridDim.x; c += 256) s += __ldcg(part + c);
   s = block_sum_256(s, sm);
-  // inputs of the scalar tail below from shared memory (h itself is in shh already); mode 1 has no scalar tail here
-  if (mode != 1) {   // kernel-uniform
+  // mode 0 runs the scalar step here: its inputs from shared memory (h itself is in shh already)
+  if (mode == 0) {   // kernel-uniform
     gmres_step_stage(jc, nullptr, U.gv, U.tailc, nullptr, sgv, stc);
     __syncthreads();
   }
   if (threadIdx.x == 0) {
     *ctr = 0u;
-    if (pv) {   // publish the partial sum of squares; the next update (or the step kernel) sums the ranks
-      const int R = pv->nranks, par = (int)(seq & 1ull);
-      f64 cw = 0.0;
-      for (int i = 0; i < ncol; i++) cw -= shh[i] * stc[i];   // same expression and order as gmres_step_dev
-      U.S->cw = cw;
-      __threadfence();   // S->cw before the norm becomes visible anywhere
-      for (int rr = 0; rr < R; rr++) ll_store(pv->mbox_peer[rr] + p2p_b_ll(R, par, pv->rank), s, (unsigned)seq);
+    if (pv) {   // the partial sum of squares goes to every rank; a later kernel's Givens step sums the ranks
+      if (defer_flag) {
+        *pv->nrm_part = s;   // published by the next kernel (the mat-vec's first block, or the step kernel at the end of a chunk)
+      } else {
+        const int R = pv->nranks, par = (int)(seq & 1ull);
+        for (int rr = 0; rr < R; rr++) ll_store(pv->mbox_peer[rr] + p2p_b_ll(R, par, pv->rank), s, (unsigned)seq);
+      }
     } else {
       U.S->nrm2_live = s;
       if (mode == 0) gmres_step_dev(jc, U.S, hcol, U.gv, U.beta, U.tailc, U.res_hist, U.qs, shh, sgv, stc);
@@ -1186,11 +1191,13 @@ __global__ void __launch_bounds__(128) k_gmres_step(int it, GmresScalars* S, f64
 
 // peer-memory mode: fused all-reduce of ||w||^2 (rank order) + the scalar Arnoldi/Givens step; one warp
 __global__ void k_gmres_step_peer(int it, GmresScalars* S, f64* hcol, f64* gv, f64* beta, f64* tailc, f64* res_hist, f64* qs,
-                                  const P2PView* __restrict__ pv, unsigned soff) {
+                                  const P2PView* __restrict__ pv, unsigned soff, int publish) {
   const unsigned long long seq = pv->seq_base[0] + soff;
   const int R = pv->nranks, par = (int)(seq & 1ull);
   __shared__ f64 s_part[P2P_MAXR];
   __shared__ f64 h_s[128], gv_s[256], tc_s[128];
+  if (publish && (int)threadIdx.x >= 32 && (int)threadIdx.x < 32 + R)   // the update parked this rank's partial for us
+    ll_store(pv->mbox_peer[threadIdx.x - 32] + p2p_b_ll(R, par, pv->rank), *pv->nrm_part, (unsigned)seq);
   gmres_step_stage(it, hcol, gv, tailc, h_s, gv_s, tc_s);
   if ((int)threadIdx.x < R) s_part[threadIdx.x] = ll_load(pv, pv->mbox_local + p2p_b_ll(R, par, threadIdx.x), (unsigned)seq);
   __syncthreads();
@@ -1496,7 +1503,9 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
       DFB_CHECK(launch_spmv(W->n_interior, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, s, LAY_XAOS | LAY_YAOS, pv, (unsigned)iter + 1u, W->n_interior));
     } else if (pv) {   // ONE launch whose boundary-row blocks (scheduled last) wait for the neighbours' halo flags
       DFB_CHECK(launch_spmv(0, n_own, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, s, LAY_XAOS | LAY_YAOS, pv, (unsigned)iter + 1u, W->n_interior,
-                            halo_defer && iter > 0));   // (z~_0's flag left k_pc_apply_aos)
+                            // bit 0: raise the flag of z~_iter's halo (z~_0's left k_pc_apply_aos); bit 1: publish the norm the
+                            // previous update parked, unless that iteration closed a chunk (its step kernel did)
+                            (halo_defer && iter > 0 ? 1 : 0) | (halo_defer && iter > 0 && iter % chk != 0 ? 2 : 0)));
     } else if (W->parallel) {
       DFB_CHECK(W->par.halo_begin_aos(zvec, s, W->par.user));
       DFB_CHECK(launch_spmv(0, W->n_interior, rp, ci, A00, A01, A10, A11, 1.0, zvec, 0, 0.0, w, 0, s, LAY_XAOS | LAY_YAOS));
@@ -1540,7 +1549,7 @@ int dfb_gmres_solve_pc(dfb_gmres* W, int N, const int* rp, const int* ci, const 
       // only when the host needs the residual now (the every-20th test) or the loop ends
       if ((iter + 1) % chk == 0 || iter + 1 == maxit) {
         prof.begin("step (peer sum)", s);
-        k_gmres_step_peer<<<1, 128, 0, s>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist, W->qs, pv, soff);
+        k_gmres_step_peer<<<1, 128, 0, s>>>(iter, W->S, HCOL(iter), W->gv, W->beta, W->tailc, W->res_hist, W->qs, pv, soff, halo_defer);
         DFB_LAUNCH_CHECK();
         prof.end(s);
       }
