@@ -617,7 +617,8 @@ def main():
     ap.add_argument("--fixed-m", action="store_true", help="N > 1: keep --m (strong scaling) instead of growing the mesh with N")
     ap.add_argument("--pc", default="jacobi", choices=["jacobi", "schur2"],
                     help="--timesteps on one GPU: the reference's block-Jacobi (default) or the opt-in two-level Schur-complement preconditioner")
-    ap.add_argument("--owner", default="slab", choices=["slab", "rcb"], help="N > 1: node ownership (z-slabs or coordinate bisection)")
+    ap.add_argument("--owner", default="auto", choices=["auto", "slab", "rcb"],
+                    help="N > 1: node ownership (z-slabs, coordinate bisection; auto = slabs when the planes divide evenly, else bisection)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling blocks (16M-tet mesh; 64M at 8 GPUs)")
     ap.add_argument("--strong64", action="store_true", help="N = 1: also run the 64M-tet mesh on one GPU (about a minute)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the embedded parity check against the oracle")
