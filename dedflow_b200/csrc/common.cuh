@@ -92,7 +92,7 @@ int num_sms();
 // dfb_set_option(): no entry point calls getenv on its launch path, and tests / A-B scripts switch variants inside one process
 // without touching the environment.  Keys are the environment names (DFB_J_VARIANT=pairs|pull|fused, DFB_J_PAIR_ROWS=8|16, DFB_J_PAIR_NT=96|128|192|224,
 // DFB_J_PAIR_ORDER=morton|natural, DFB_J_PULL_PLAIN=0|1, DFB_F_VARIANT=patch|pipe|scratch, DFB_F_PATCH_CTAS=2|3, DFB_SPMV_G=4|8|16|32, DFB_SPMV_TMA=0|1, DFB_SPMV_PEER_SPLIT=0|1, DFB_HALO_DEFER=0|1,
-// DFB_KRYLOV_TMA=0|1, DFB_GRAPH=0|1, DFB_GMRES_CHECK=1..20, DFB_GIVENS_DEFER=0|1, DFB_PROFILE=0|1|2, DFB_ASSEMBLE_MODE=gather|atomic|colored, DFB_VERBOSE=0|1, DFB_PC=jacobi|schur2, DFB_PC_AGG=2..16, DFB_PC_DEGREE=1..64).
+// DFB_GRAPH=0|1, DFB_GMRES_CHECK=1..20, DFB_GIVENS_DEFER=0|1, DFB_PROFILE=0|1|2, DFB_ASSEMBLE_MODE=gather|atomic|colored, DFB_VERBOSE=0|1, DFB_PC=jacobi|schur2, DFB_PC_AGG=2..16, DFB_PC_DEGREE=1..64).
 struct Options {
   int j_variant = 2;        // 0 pull, 1 fused, 2 pairs
   int j_pair_rows = 8;
@@ -107,7 +107,6 @@ struct Options {
   int gmres_check = 20;     // iterations between two convergence tests (the reference: 20; DFB_GMRES_CHECK=1..20)
   int givens_defer = 1;     // one GPU: the scalar Givens step runs in the next multi-dot's tail (DFB_GIVENS_DEFER=0: in the update's)
   int halo_defer = 1;       // peer-memory mode: the mat-vec's first block raises the halo flag of the update before it (DFB_HALO_DEFER=0: the update's last block does)
-  int krylov_tma = 1;
   int graph = 1;
   int profile = 0;
   int assemble_mode = DFB_MODE_GATHER;

@@ -49,7 +49,6 @@ static bool apply_option(Options& o, const char* key, const char* v) {
   if (is("DFB_HALO_DEFER")) { o.halo_defer = atoi(v) != 0; return true; }
   if (is("DFB_GIVENS_DEFER")) { o.givens_defer = atoi(v) != 0; return true; }
   if (is("DFB_GMRES_CHECK")) { o.gmres_check = std::min(20, std::max(1, atoi(v))); return true; }
-  if (is("DFB_KRYLOV_TMA")) { o.krylov_tma = atoi(v) != 0; return true; }
   if (is("DFB_GRAPH")) { o.graph = atoi(v) != 0; return true; }
   if (is("DFB_PROFILE")) { o.profile = atoi(v); return true; }
   if (is("DFB_VERBOSE")) { o.verbose = atoi(v) != 0; return true; }
@@ -67,7 +66,7 @@ Options& options() {
   static Options o = [] {
     Options t;
     static const char* keys[] = {"DFB_J_VARIANT", "DFB_J_PAIR_ROWS", "DFB_J_PAIR_NT", "DFB_J_PAIR_ORDER", "DFB_J_PULL_PLAIN", "DFB_F_VARIANT", "DFB_F_PATCH_CTAS", "DFB_SPMV_G",
-                                 "DFB_SPMV_TMA", "DFB_SPMV_PEER_SPLIT", "DFB_KRYLOV_TMA", "DFB_GRAPH", "DFB_PROFILE", "DFB_VERBOSE", "DFB_ASSEMBLE_MODE", "DFB_PC", "DFB_PC_AGG", "DFB_PC_DEGREE"};
+                                 "DFB_SPMV_TMA", "DFB_SPMV_PEER_SPLIT", "DFB_HALO_DEFER", "DFB_GIVENS_DEFER", "DFB_GMRES_CHECK", "DFB_GRAPH", "DFB_PROFILE", "DFB_VERBOSE", "DFB_ASSEMBLE_MODE", "DFB_PC", "DFB_PC_AGG", "DFB_PC_DEGREE"};
     for (const char* k : keys) {
       const char* v = getenv(k);
       if (v && *v) apply_option(t, k, v);

@@ -50,7 +50,7 @@ int dfb_version(void);
 long long dfb_launch_count(void);
 /* Variant switches (A/B measurements, tests).  `key` is one of the environment names the library reads once at load
  * (DFB_J_VARIANT, DFB_J_PAIR_ROWS, DFB_J_PAIR_NT, DFB_J_PAIR_ORDER, DFB_J_PULL_PLAIN, DFB_F_VARIANT, DFB_F_PATCH_CTAS, DFB_SPMV_G,
- * DFB_SPMV_TMA, DFB_SPMV_PEER_SPLIT, DFB_HALO_DEFER, DFB_KRYLOV_TMA, DFB_GRAPH, DFB_GMRES_CHECK, DFB_GIVENS_DEFER, DFB_PROFILE, DFB_VERBOSE, DFB_ASSEMBLE_MODE, DFB_PC, DFB_PC_AGG, DFB_PC_DEGREE); no entry point reads the
+ * DFB_SPMV_TMA, DFB_SPMV_PEER_SPLIT, DFB_HALO_DEFER, DFB_GRAPH, DFB_GMRES_CHECK, DFB_GIVENS_DEFER, DFB_PROFILE, DFB_VERBOSE, DFB_ASSEMBLE_MODE, DFB_PC, DFB_PC_AGG, DFB_PC_DEGREE); no entry point reads the
  * environment on its launch path. */
 int dfb_set_option(const char* key, const char* value);
 

@@ -268,3 +268,48 @@ def test_no_cpu_fallback_without_gpu():
     from dedflow_b200 import api, lib
     with pytest.raises(lib.DfbError):
         api.FlowSystem(boxmesh.make_box(2))
+
+
+def test_option_table_accepts_the_documented_switches_and_rejects_others():
+    """dfb_set_option is host-only: every key the header documents is accepted, an unknown one is an argument error"""
+    from dedflow_b200 import _build, lib
+    _build.build()
+    lib.load()
+    header = (ROOT / "include" / "dedflow_b200.h").read_text()
+    block = header[header.index("Variant switches"):header.index("int dfb_set_option")]
+    keys = sorted(set(re.findall(r"DFB_[A-Z0-9_]+", block)))
+    assert {"DFB_GMRES_CHECK", "DFB_HALO_DEFER", "DFB_GIVENS_DEFER", "DFB_F_VARIANT", "DFB_J_PAIR_NT"} <= set(keys)
+    defaults = {"DFB_J_VARIANT": "pairs", "DFB_J_PAIR_ORDER": "morton", "DFB_F_VARIANT": "patch", "DFB_ASSEMBLE_MODE": "gather",
+                "DFB_PC": "jacobi", "DFB_J_PAIR_ROWS": "8", "DFB_J_PAIR_NT": "96", "DFB_F_PATCH_CTAS": "2", "DFB_SPMV_G": "8",
+                "DFB_GMRES_CHECK": "20", "DFB_PC_AGG": "4", "DFB_PC_DEGREE": "10", "DFB_HALO_DEFER": "1", "DFB_GIVENS_DEFER": "1",
+                "DFB_GRAPH": "1"}
+    for k in keys:
+        lib.set_option(k, defaults.get(k, "0"))            # (sets every switch to its default)
+    with pytest.raises(lib.DfbError):
+        lib.set_option("DFB_NO_SUCH_SWITCH", "1")
+
+
+def test_bench_ownership_policy():
+    """bench.py --owner auto: slabs when the box's planes divide evenly among the ranks, coordinate bisection otherwise"""
+    from dedflow_b200 import dist as ddist
+    for world, m, want in ((2, 69, "slab"), (4, 87, "slab"), (8, 110, "rcb"), (3, 8, "slab"), (3, 9, "rcb")):
+        mesh = boxmesh.make_box(m) if m < 20 else type("M", (), {"m": m})()
+        name, fn = ddist.pick_owner("auto", mesh, world)
+        assert name == want and fn is ddist.OWNERS[want]
+    mesh = boxmesh.make_box(9)
+    for name in ("slab", "rcb"):
+        npart = ddist.pick_owner(name, mesh, 3)[1](mesh, 3)
+        counts = np.bincount(npart, minlength=3)
+        assert counts.sum() == mesh.num_node and counts.min() > 0
+        if name == "rcb":
+            assert counts.max() - counts.min() <= 1         # balanced to a node
+
+
+def test_every_parsed_switch_is_also_read_from_the_environment():
+    """setup.cu: the keys apply_option() parses and the keys options() reads from the environment at load are the same set
+    (a switch missing from the second list works through dfb_set_option but silently ignores the environment)"""
+    src = (ROOT / "dedflow_b200" / "csrc" / "setup.cu").read_text()
+    parsed = set(re.findall(r'is\("(DFB_[A-Z0-9_]+)"\)', src))
+    env_list = src[src.index("static const char* keys[]"):]
+    env_list = set(re.findall(r'"(DFB_[A-Z0-9_]+)"', env_list[:env_list.index("};")]))
+    assert parsed == env_list, (sorted(parsed - env_list), sorted(env_list - parsed))
