@@ -8,18 +8,24 @@
 //                             + k one-element Drot launches + Drotg + memset + <<<1,1>>> kernel; 5 cudaMalloc/Free
 //                             and a 1 GB memset per solve
 //
-// B200 design:
-//   * SpMV: ONE kernel over the four sub-blocks.  A warp owns a nodal row: the 9+3+3+1 value streams of the row
-//     are contiguous (blocked scalar-CSR layout), so every load is a coalesced 256-byte warp transaction; the
-//     nodal column index is read once (4 B per 16 values instead of the reference's 4 B per value); x is
-//     gathered through L2.  Algorithmic traffic 132 B per nodal nonzero instead of 192 B.
-//   * Krylov vectors hold only the live 4N rows (defect D4); the dead tail b[4N:6N) is carried exactly as one
-//     scalar per basis vector (it stays a multiple of b's tail), see tail_* below.
-//   * CGS: one multi-dot kernel (h = Q^T w, 8 columns per block, fixed-order two-stage reduction) and one
-//     update kernel (w -= Q h, fused with the sum of squares of the new w).  Givens rotations, the Hessenberg
-//     column, beta and the normalisation factor live on the device (one 1-block kernel): no host round trip
-//     inside an iteration; the host reads the residual only at the reference's every-20th-iteration test.
-//   * Workspace is persistent (dfb_gmres), nothing is allocated or memset per solve.
+// B200 design (DESIGN.md sections 3, 5, 6):
+//   * SpMV: ONE kernel over the four sub-blocks.  Eight lanes own a nodal row: the 9+3+3+1 value streams of the row are
+//     contiguous (blocked scalar-CSR layout), the nodal column index is read once (4 B per 16 values instead of the
+//     reference's 4 B per value), x is gathered through L2 as one 32-byte sector per column (interleaved vectors).
+//     Algorithmic traffic 132 B per nodal nonzero instead of 192 B.
+//   * Krylov vectors hold only the live 4N rows (defect D4), interleaved per node; the dead tail b[4N:6N) is carried exactly as
+//     one scalar per basis vector (it stays a multiple of b's tail), see tail_* below.  The basis is stored UNNORMALISED with
+//     its scales on the device, so no kernel waits for a norm that has only just been reduced.
+//   * CGS, three launches per iteration: mat-vec; multi-dot (raw dots, fixed-order two-stage reduction; its last block also
+//     runs the previous iteration's Givens step beside the partial sums); update (w~ -= Q c, fused with the sum of squares of the
+//     new column and with z~ = P^-1 w~).  Givens rotations, the Hessenberg column, beta and the scales live on the device; the
+//     residual history is written straight into mapped host memory: the host synchronises only at the convergence tests
+//     (every 20th iteration like the reference, DFB_GMRES_CHECK for a shorter interval) and copies nothing.
+//   * The iterations between two tests replay from a CUDA graph per chunk.
+//   * Peer-memory mode (one process per GPU): the halo of z~ leaves the update as plain stores into the neighbours, the dots and
+//     the norm travel as self-validating LL words; flags and publications that would hold a kernel's completion for an NVLink
+//     round trip are raised by the first block of the NEXT kernel.
+//   * Workspace is persistent (dfb_gmres), nothing is allocated per solve.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -897,10 +903,12 @@ __global__ void __launch_bounds__(256) k_multidot(size_t nl, const f64* __restri
 
 // The update of one Arnoldi step (see the header above): w~_{j+1} = s_j w_raw - sum_i (h_i s_i) w~_i with h_i = s_i s_j d_i,
 // fused with (a) the sum of squares of the new vector (stage 2 by the last block), (b) z~_{j+1} = P^-1 w~_{j+1}: a node's four
-// entries sit in two adjacent lanes, which swap their halves with one shuffle each and write z with coalesced 16-byte stores,
-// (c) mode 0 (one GPU): the scalar Arnoldi/Givens step in the last block, (d) mode 2 (peer memory): the all-reduce of the raw
-// dots and of the PREVIOUS step's norm in the prologue (block 0 also runs that step's Givens update), the halo push of z~ in
-// the epilogue and the publication of this step's partial norm by the last block.
+// entries sit in two adjacent lanes, which swap their halves with one shuffle each and write z with coalesced 16-byte stores.
+// mode 0: the scalar Arnoldi/Givens step runs here, in the last block (one GPU, DFB_GIVENS_DEFER=0).
+// mode 1: the step runs later (the next multi-dot's tail, or a step kernel): block 0 leaves the Hessenberg column in global
+//         memory, the last block the sum of squares (one GPU default; the NCCL path, which all-reduces it first).
+// mode 2: peer memory: like mode 1, plus the halo stores of z~ into the neighbours in the sweep and this rank's partial norm
+//         parked for the next kernel to publish (defer_flag) or published here together with the halo flags.
 // One resident wave of blocks (4 per SM) strides over 16-byte row pairs; a thread keeps 8 independent 16-byte loads in flight.
 #ifndef UPDATE_REVERSE
 #define UPDATE_REVERSE 1
