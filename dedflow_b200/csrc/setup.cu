@@ -539,29 +539,48 @@ __global__ void k_morton_keys(int n, int nblk, const f64* __restrict__ xg, const
     bb[threadIdx.x] = r;
   }
   __syncthreads();
+  // Cell size s: one node per cell, cells CENTRED on the nodes.  A lattice of n_d nodes per direction spans ext_d = (n_d - 1) s,
+  // so s solves prod_d (ext_d / s + 1) = n over the non-flat directions (bisection; flat directions count as one cell).  With
+  // s = (volume / n)^(1/nd) instead, the cells of a box that is only a few planes thick (the local mesh of a rank) come out
+  // smaller than the node spacing and drift against the lattice: 8-row groups then stage 128 elements instead of 112.
+  __shared__ f64 s_cell;
+  if (threadIdx.x == 0) {
+    const f64 cnt = (f64)(ien ? n_cells_ref : n);
+    f64 emax = 0.0;
+    for (int d = 0; d < 3; d++) emax = fmax(emax, bb[3 + d] - bb[d]);
+    f64 lo = 0.0, hi = emax;
+    if (emax > 0.0) {
+      for (int it = 0; it < 100; it++) {
+        const f64 mid = 0.5 * (lo + hi);
+        f64 cells = 1.0;
+        for (int d = 0; d < 3; d++) {
+          const f64 e = bb[3 + d] - bb[d];
+          if (e > 0.0) cells *= e / mid + 1.0;
+        }
+        if (cells > cnt) lo = mid; else hi = mid;   // cells(s) falls as s grows
+      }
+    }
+    s_cell = hi > 0.0 ? hi : 1.0;
+  }
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  // cell size: one node per cell on average over the occupied box (flat directions count as one cell)
-  f64 ext[3], vol = 1.0;
-  int nd = 0;
-  for (int d = 0; d < 3; d++) {
-    ext[d] = bb[3 + d] - bb[d];
-    if (ext[d] > 0.0) { vol *= ext[d]; nd++; }
-  }
-  const f64 h = nd ? pow(vol / (f64)(ien ? n_cells_ref : n), 1.0 / nd) : 1.0;
+  const f64 h = s_cell;
   unsigned long long key = 0;
   for (int d = 0; d < 3; d++) {
     unsigned long long c = 0;
-    if (ext[d] > 0.0) {
-      const f64 nb = fmin(2097151.0, fmax(1.0, ceil(ext[d] / h)));
-      f64 xv;
+    const f64 ext = bb[3 + d] - bb[d];
+    if (ext > 0.0) {
+      const f64 nb = fmin(2097151.0, floor(ext / h + 0.5) + 1.0);
+      f64 xv, shift = 0.5;   // nodes sit at the cell centres; element centroids between them
       if (ien) {
         const int4 nd4 = *reinterpret_cast<const int4*>(ien + (size_t)i * 4);
         xv = 0.25 * (xg[(size_t)nd4.x * 3 + d] + xg[(size_t)nd4.y * 3 + d] + xg[(size_t)nd4.z * 3 + d] + xg[(size_t)nd4.w * 3 + d]);
+        shift = 0.0;
       } else {
         xv = xg[(size_t)i * 3 + d];
       }
-      c = (unsigned long long)fmin(nb - 1.0, floor((xv - bb[d]) / ext[d] * nb));
+      c = (unsigned long long)fmin(nb - 1.0, fmax(0.0, floor((xv - bb[d]) / h + shift)));
     }
     key |= spread21(c) << d;
   }
