@@ -518,6 +518,42 @@ __global__ void __launch_bounds__(256) k_bbox_part(int n, const f64* __restrict_
   }
 }
 
+// part[block] = sum over the block's elements of the element's SHORTEST edge: their mean is the node spacing the Morton cells
+// are sized with (exactly the lattice constant on a structured tet mesh, whatever the shape of the node set; a local average
+// on an unstructured one).  Per-block partials, summed in block order by the consumer: deterministic.
+__global__ void __launch_bounds__(256) k_spacing_part(int E, const int* __restrict__ ien, const f64* __restrict__ xg,
+                                                      f64* __restrict__ part) {
+  __shared__ f64 sm[8];
+  f64 acc = 0.0;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    const int4 nd = *reinterpret_cast<const int4*>(ien + (size_t)e * 4);
+    const int v[4] = {nd.x, nd.y, nd.z, nd.w};
+    f64 x[4][3];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int d = 0; d < 3; d++) x[a][d] = xg[(size_t)v[a] * 3 + d];
+    f64 m2 = 1e300;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = a + 1; b < 4; b++) {
+        const f64 dx = x[a][0] - x[b][0], dy = x[a][1] - x[b][1], dz = x[a][2] - x[b][2];
+        m2 = fmin(m2, dx * dx + dy * dy + dz * dz);
+      }
+    acc += sqrt(m2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    f64 r = 0.0;
+    for (int k = 0; k < 8; k++) r += sm[k];
+    part[blockIdx.x] = r;
+  }
+}
+
 __device__ __forceinline__ unsigned long long spread21(unsigned long long v) {   // 21 bits -> every third bit
   v &= 0x1fffffull;
   v = (v | (v << 32)) & 0x1f00000000ffffull;
@@ -531,7 +567,7 @@ __device__ __forceinline__ unsigned long long spread21(unsigned long long v) {  
 // ien == nullptr: key of node i (n nodes); else key of the centroid of element i (n elements, cell size from n_cells_ref nodes)
 __global__ void k_morton_keys(int n, int nblk, const f64* __restrict__ xg, const f64* __restrict__ part,
                               unsigned long long* __restrict__ keys, int* __restrict__ ids, const int* __restrict__ ien = nullptr,
-                              int n_cells_ref = 0) {
+                              int n_cells_ref = 0, const f64* __restrict__ spart = nullptr, int nsblk = 0, int n_elem = 0) {
   __shared__ f64 bb[6];
   if (threadIdx.x < 6) {
     f64 r = part[threadIdx.x];
@@ -539,12 +575,19 @@ __global__ void k_morton_keys(int n, int nblk, const f64* __restrict__ xg, const
     bb[threadIdx.x] = r;
   }
   __syncthreads();
-  // Cell size s: one node per cell, cells CENTRED on the nodes.  A lattice of n_d nodes per direction spans ext_d = (n_d - 1) s,
-  // so s solves prod_d (ext_d / s + 1) = n over the non-flat directions (bisection; flat directions count as one cell).  With
-  // s = (volume / n)^(1/nd) instead, the cells of a box that is only a few planes thick (the local mesh of a rank) come out
-  // smaller than the node spacing and drift against the lattice: 8-row groups then stage 128 elements instead of 112.
+  // Cell size s: one node per cell, cells CENTRED on the nodes.  With the elements at hand, s = the mean shortest edge
+  // (k_spacing_part): the lattice constant of a structured mesh even when the node set is a staircase-shaped part of it.
+  // Without them: a lattice of n_d nodes per direction spans ext_d = (n_d - 1) s, so s solves prod_d (ext_d / s + 1) = n over the
+  // non-flat directions (bisection; flat directions count as one cell).  s = (volume / n)^(1/nd) -- the first version -- makes
+  // the cells of a box that is only a few planes thick (the local mesh of a rank) smaller than the node spacing: they drift
+  // against the lattice and 8-row groups stage 128 elements instead of 112.
   __shared__ f64 s_cell;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && spart && n_elem > 0) {
+    f64 sum = 0.0;
+    for (int k = 0; k < nsblk; k++) sum += spart[k];
+    s_cell = sum / (f64)n_elem;
+    if (!(s_cell > 0.0)) s_cell = 1.0;
+  } else if (threadIdx.x == 0) {
     const f64 cnt = (f64)(ien ? n_cells_ref : n);
     f64 emax = 0.0;
     for (int d = 0; d < 3; d++) emax = fmax(emax, bb[3 + d] - bb[d]);
@@ -846,7 +889,12 @@ int build_fpatch(const dfb_plan* p, const f64* d_xg, cudaStream_t st) {
     DFB_CHECK(ids.alloc((size_t)E));
     k_bbox_part<<<nblk, 256, 0, st>>>(N, d_xg, part);
     DFB_LAUNCH_CHECK();
-    k_morton_keys<<<ceil_div(E, 256), 256, 0, st>>>(E, nblk, d_xg, part, keys, ids, p->ien, N);
+    DevBuf<f64> spart;
+    const int nsblk = std::min(1024, ceil_div(E, 256));
+    DFB_CHECK(spart.alloc((size_t)nsblk));
+    k_spacing_part<<<nsblk, 256, 0, st>>>(E, p->ien, d_xg, spart);
+    DFB_LAUNCH_CHECK();
+    k_morton_keys<<<ceil_div(E, 256), 256, 0, st>>>(E, nblk, d_xg, part, keys, ids, p->ien, N, spart, nsblk, E);
     DFB_LAUNCH_CHECK();
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_out.p, ids.p, order.p, E, 0, 63, st);
     DFB_CHECK(tmp.alloc(tmp_bytes));
@@ -955,7 +1003,14 @@ int build_pairs(const dfb_plan* p, int R, const f64* d_xg, cudaStream_t st) {
     DFB_CHECK(ids.alloc((size_t)n_act));
     k_bbox_part<<<nblk, 256, 0, st>>>(n_act, d_xg, part);
     DFB_LAUNCH_CHECK();
-    k_morton_keys<<<ceil_div(n_act, 256), 256, 0, st>>>(n_act, nblk, d_xg, part, keys, ids);
+    DevBuf<f64> spart;
+    const int nsblk = std::min(1024, ceil_div(p->E, 256));
+    DFB_CHECK(spart.alloc((size_t)std::max(1, nsblk)));
+    if (p->E > 0) {
+      k_spacing_part<<<nsblk, 256, 0, st>>>(p->E, p->ien, d_xg, spart);
+      DFB_LAUNCH_CHECK();
+    }
+    k_morton_keys<<<ceil_div(n_act, 256), 256, 0, st>>>(n_act, nblk, d_xg, part, keys, ids, nullptr, 0, spart, nsblk, p->E);
     DFB_LAUNCH_CHECK();
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_out.p, ids.p, order.p, n_act, 0, 63, st);
     DFB_CHECK(tmp.alloc(tmp_bytes));
