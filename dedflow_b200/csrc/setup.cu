@@ -631,6 +631,21 @@ __global__ void k_morton_keys(int n, int nblk, const f64* __restrict__ xg, const
   ids[i] = i;
 }
 
+// Rows are grouped EIGHT AT A TIME along the Morton curve, so a group is an aligned 2x2x2 block of nodes only while every block
+// before it on the curve is complete: one block with a node missing (the staircase surface of a bisection part, a domain
+// boundary) shifts every later group across two blocks (130 staged elements per group instead of 113).  Rows of incomplete
+// blocks therefore go to the END of the order (bit 63 of the key, second sort): the complete blocks stay aligned.
+// keys: sorted Morton keys, ids: the rows in that order; out_keys[i] = key with bit 63 set for rows of incomplete blocks.
+__global__ void k_mark_partial_blocks(int n, const unsigned long long* __restrict__ keys, unsigned long long* __restrict__ out_keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = keys[i], blk = k >> 3;
+  const long long p0 = (long long)i - (long long)(k & 7ull);   // where the block starts if it is complete (one row per cell)
+  bool full = p0 >= 0 && p0 + 7 < n;
+  if (full) full = keys[p0] == (blk << 3) && keys[p0 + 7] == ((blk << 3) | 7ull);
+  out_keys[i] = full ? k : (k | (1ull << 63));
+}
+
 __global__ void k_iota_rpos(int N, int n, const int* __restrict__ order, int* __restrict__ rpos) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
@@ -1016,6 +1031,16 @@ int build_pairs(const dfb_plan* p, int R, const f64* d_xg, cudaStream_t st) {
     DFB_CHECK(tmp.alloc(tmp_bytes));
     cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_out.p, ids.p, order.p, n_act, 0, 63, st);
     DFB_LAUNCH_CHECK();
+    if (R == 8) {   // complete 2x2x2 blocks first (aligned groups), the rows of incomplete blocks after them
+      k_mark_partial_blocks<<<ceil_div(n_act, 256), 256, 0, st>>>(n_act, keys_out, keys);
+      DFB_LAUNCH_CHECK();
+      DFB_CUDA(cudaMemcpyAsync(ids, order, sizeof(int) * (size_t)n_act, cudaMemcpyDeviceToDevice, st));
+      size_t tb2 = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tb2, keys.p, keys_out.p, ids.p, order.p, n_act, 0, 64, st);
+      if (tb2 > tmp_bytes) { tmp_bytes = tb2; DFB_CHECK(tmp.alloc(tmp_bytes)); }
+      cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_out.p, ids.p, order.p, n_act, 0, 64, st);
+      DFB_LAUNCH_CHECK();
+    }
     DFB_CUDA(cudaStreamSynchronize(st));   // the scratch buffers above are released at the end of this scope
   } else {
     std::vector<int> h(n_act);
