@@ -653,6 +653,14 @@ __global__ void k_iota_rpos(int N, int n, const int* __restrict__ order, int* __
   else rpos[i] = -1;
 }
 
+// the same for an order with padding entries (-1) between groups: rpos is preset to -1, n_pos positions are walked
+__global__ void k_rpos_padded(int n_pos, const int* __restrict__ order, int* __restrict__ rpos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pos) return;
+  const int row = order[i];
+  if (row >= 0) rpos[row] = i;
+}
+
 __global__ void k_pair_group_count(int n_act, int n_cta, int R, const int* __restrict__ order, const int* __restrict__ row_ptr,
                                    const int* __restrict__ col_ind, int* __restrict__ cnt) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -661,6 +669,7 @@ __global__ void k_pair_group_count(int n_act, int n_cta, int R, const int* __res
   int total = 4 * R;
   for (int pos = g * R; pos < min(n_act, (g + 1) * R); pos++) {
     const int row = order[pos];
+    if (row < 0) continue;   // padding
     const int s = row_ptr[row], len = row_ptr[row + 1] - s;
     total += len - 1 - lower_bound_dev(col_ind + s, len, row);   // entries right of the diagonal
   }
@@ -676,8 +685,8 @@ __global__ void k_pair_meta(int n_act, int n_cta, int R, const int* __restrict__
   int pos = base + 4 * R;
   for (int r = 0; r < R; r++) {
     uint2 md = make_uint2(0xffffffffu, 0u);
-    if (g * R + r < n_act) {
-      const int row = order[g * R + r];
+    const int row = g * R + r < n_act ? order[g * R + r] : -1;
+    if (row >= 0) {   // (-1: padding, or past the end)
       const int s = row_ptr[row], len = row_ptr[row + 1] - s;
       const int kd = lower_bound_dev(col_ind + s, len, row);
       md = make_uint2((u32)row, (u32)kd | 0x100u);
@@ -748,6 +757,7 @@ __global__ void __launch_bounds__(64) k_pair_group_elems(int n_act, int n_cta, i
   bool ovf = false;
   for (int pos = g * R; pos < min(n_act, (g + 1) * R); pos++) {
     const int row = order[pos];
+    if (row < 0) continue;   // padding
     for (int c = v2c_ptr[row]; c < v2c_ptr[row + 1]; c++) {
       const int e = v2c[c] >> 2;
       int lo = 0, hi = n;
@@ -999,7 +1009,8 @@ int build_pairs(const dfb_plan* p, int R, const f64* d_xg, cudaStream_t st) {
   if ((i64)p->E * 16 > 0xffffffffLL) { p->pr_state = -1; return DFB_OK; }
   const int N = p->N, E = p->E, n_act = p->n_rows;
   const u32* slot32 = reinterpret_cast<const u32*>(p->slot);
-  const int n_cta = ceil_div(n_act, R);
+  int n_pos = n_act;             // positions of the row order (more than n_act once groups are padded, see below)
+  int n_cta = ceil_div(n_pos, R);
   DevBuf<int> cnt, row_pair, icnt, gcnt, flags, order, rpos;
   DevBuf<char> tmp;
   DevBuf<u32> contrib32;
@@ -1040,6 +1051,41 @@ int build_pairs(const dfb_plan* p, int R, const f64* d_xg, cudaStream_t st) {
       if (tb2 > tmp_bytes) { tmp_bytes = tb2; DFB_CHECK(tmp.alloc(tmp_bytes)); }
       cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_out.p, ids.p, order.p, n_act, 0, 64, st);
       DFB_LAUNCH_CHECK();
+      // The leftover rows (a few per cent on a lattice-like mesh) get ONE GROUP PER BLOCK, padded to R positions with -1: a group
+      // of leftover rows from several blocks stages up to 156 elements, one more than fits four CTAs of k_pairJ per SM, and the
+      // shared-memory size of the launch is the maximum over all groups.  Done on the host (set-up, a few thousand rows);
+      // skipped when most rows are leftovers (unstructured meshes: the plain Morton order is the better grouping there).
+      std::vector<unsigned long long> hk((size_t)n_act);
+      DFB_CUDA(cudaMemcpyAsync(hk.data(), keys_out.p, sizeof(unsigned long long) * (size_t)n_act, cudaMemcpyDeviceToHost, st));
+      DFB_CUDA(cudaStreamSynchronize(st));
+      const int n_full = (int)(std::lower_bound(hk.begin(), hk.end(), 1ull << 63) - hk.begin());
+      const int n_tail = n_act - n_full;
+      if (n_tail > 0 && (n_full % R) == 0 && (i64)n_tail * 5 <= (i64)n_act) {
+        std::vector<int> hrow((size_t)n_tail), padded;
+        DFB_CUDA(cudaMemcpy(hrow.data(), order.p + n_full, sizeof(int) * (size_t)n_tail, cudaMemcpyDeviceToHost));
+        padded.reserve((size_t)n_tail * 2);
+        unsigned long long cur = ~0ull;
+        int in_group = R;   // forces a new group at the first row
+        for (int i = 0; i < n_tail; i++) {
+          const unsigned long long blk = (hk[(size_t)n_full + i] & ~(1ull << 63)) >> 3;
+          if (blk != cur || in_group == R) {
+            while (in_group < R) { padded.push_back(-1); in_group++; }
+            cur = blk;
+            in_group = 0;
+          }
+          padded.push_back(hrow[(size_t)i]);
+          in_group++;
+        }
+        while (in_group < R) { padded.push_back(-1); in_group++; }
+        n_pos = n_full + (int)padded.size();
+        n_cta = n_pos / R;
+        DevBuf<int> order2;
+        DFB_CHECK(order2.alloc((size_t)n_pos));
+        DFB_CUDA(cudaMemcpy(order2.p, order.p, sizeof(int) * (size_t)n_full, cudaMemcpyDeviceToDevice));
+        DFB_CUDA(cudaMemcpy(order2.p + n_full, padded.data(), sizeof(int) * padded.size(), cudaMemcpyHostToDevice));
+        cudaFree(order.p);
+        order.p = order2.release();
+      }
     }
     DFB_CUDA(cudaStreamSynchronize(st));   // the scratch buffers above are released at the end of this scope
   } else {
@@ -1048,14 +1094,19 @@ int build_pairs(const dfb_plan* p, int R, const f64* d_xg, cudaStream_t st) {
     DFB_CUDA(cudaMemcpyAsync(order, h.data(), sizeof(int) * (size_t)n_act, cudaMemcpyHostToDevice, st));
     DFB_CUDA(cudaStreamSynchronize(st));
   }
-  k_iota_rpos<<<ceil_div(N, 256), 256, 0, st>>>(N, n_act, order, rpos);
+  if (n_pos == n_act) {
+    k_iota_rpos<<<ceil_div(N, 256), 256, 0, st>>>(N, n_act, order, rpos);
+  } else {
+    DFB_CUDA(cudaMemsetAsync(rpos, 0xff, sizeof(int) * (size_t)N, st));
+    k_rpos_padded<<<ceil_div(n_pos, 256), 256, 0, st>>>(n_pos, order, rpos);
+  }
   DFB_LAUNCH_CHECK();
   // ---- items ----
   DFB_CHECK(cnt.alloc((size_t)n_cta + 1));
   DFB_CHECK(flags.alloc(3));   // [0] degenerate element, [1] group too large, [2] max elements per group
   DFB_CUDA(cudaMemsetAsync(flags, 0, 3 * sizeof(int), st));
   DFB_CUDA(cudaMalloc(&p->pr_grp_item, sizeof(int) * ((size_t)n_cta + 1)));
-  k_pair_group_count<<<ceil_div((i64)n_cta + 1, 128), 128, 0, st>>>(n_act, n_cta, R, order, p->row_ptr, p->col_ind, cnt);
+  k_pair_group_count<<<ceil_div((i64)n_cta + 1, 128), 128, 0, st>>>(n_pos, n_cta, R, order, p->row_ptr, p->col_ind, cnt);
   DFB_LAUNCH_CHECK();
   tmp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt.p, p->pr_grp_item, n_cta + 1, st);
@@ -1070,7 +1121,7 @@ int build_pairs(const dfb_plan* p, int R, const f64* d_xg, cudaStream_t st) {
   DFB_CHECK(row_pair.alloc((size_t)N));
   DFB_CHECK(icnt.alloc((size_t)n_items + 1));
   DFB_CUDA(cudaMemsetAsync(icnt, 0, sizeof(int) * ((size_t)n_items + 1), st));
-  k_pair_meta<<<ceil_div(n_cta, 128), 128, 0, st>>>(n_act, n_cta, R, order, p->row_ptr, p->col_ind, p->pr_grp_item, p->pr_meta, row_pair);
+  k_pair_meta<<<ceil_div(n_cta, 128), 128, 0, st>>>(n_pos, n_cta, R, order, p->row_ptr, p->col_ind, p->pr_grp_item, p->pr_meta, row_pair);
   DFB_LAUNCH_CHECK();
   const int cgrid = ceil_div((i64)E * 16, 256);
   k_pair_contrib<false><<<cgrid, 256, 0, st>>>(E, R, p->ien, p->row_ptr, p->col_ind, p->v2c_ptr, p->v2c, slot32, p->pr_grp_item, rpos,
@@ -1095,7 +1146,7 @@ int build_pairs(const dfb_plan* p, int R, const f64* d_xg, cudaStream_t st) {
   DFB_CHECK(gcnt.alloc((size_t)n_cta + 1));
   DFB_CUDA(cudaMemsetAsync(gcnt, 0, sizeof(int) * ((size_t)n_cta + 1), st));
   DFB_CUDA(cudaMalloc(&p->pr_elem_ptr, sizeof(int) * ((size_t)n_cta + 1)));
-  k_pair_group_elems<false><<<ceil_div(n_cta, 64), 64, 0, st>>>(n_act, n_cta, R, order, p->v2c_ptr, p->v2c, gcnt, nullptr, nullptr, flags.p + 1);
+  k_pair_group_elems<false><<<ceil_div(n_cta, 64), 64, 0, st>>>(n_pos, n_cta, R, order, p->v2c_ptr, p->v2c, gcnt, nullptr, nullptr, flags.p + 1);
   DFB_LAUNCH_CHECK();
   tmp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, gcnt.p, p->pr_elem_ptr, n_cta + 1, st);
@@ -1116,7 +1167,7 @@ int build_pairs(const dfb_plan* p, int R, const f64* d_xg, cudaStream_t st) {
     return DFB_OK;
   }
   DFB_CUDA(cudaMalloc(&p->pr_elems, sizeof(int) * (size_t)std::max(1, total_ge)));
-  k_pair_group_elems<true><<<ceil_div(n_cta, 64), 64, 0, st>>>(n_act, n_cta, R, order, p->v2c_ptr, p->v2c, nullptr, p->pr_elem_ptr, p->pr_elems, nullptr);
+  k_pair_group_elems<true><<<ceil_div(n_cta, 64), 64, 0, st>>>(n_pos, n_cta, R, order, p->v2c_ptr, p->v2c, nullptr, p->pr_elem_ptr, p->pr_elems, nullptr);
   DFB_LAUNCH_CHECK();
   DFB_CUDA(cudaMalloc(&p->pr_contrib, sizeof(unsigned short) * (size_t)std::max(1, n_contrib)));
   k_pair_contrib16<<<ceil_div(n_items, 128), 128, 0, st>>>(n_items, R, p->pr_meta, p->pr_item_ptr, contrib32, rpos, p->pr_elem_ptr, p->pr_elems,
