@@ -313,3 +313,33 @@ def test_every_parsed_switch_is_also_read_from_the_environment():
     env_list = src[src.index("static const char* keys[]"):]
     env_list = set(re.findall(r'"(DFB_[A-Z0-9_]+)"', env_list[:env_list.index("};")]))
     assert parsed == env_list, (sorted(parsed - env_list), sorted(env_list - parsed))
+
+
+def test_pc2_restatement_is_a_better_preconditioner_than_block_jacobi(oracle):
+    """oracle/pc2_oracle.py (the checker of the opt-in preconditioner, tests/test_gpu_pc2.py) on the first Newton system of a
+    time step: its right-preconditioned GMRES meets the tolerance in fewer iterations than the reference's block-Jacobi, the
+    returned vector has the residual the history claims, and one application is linear."""
+    import scipy.sparse as sp
+    from oracle import pc2_oracle
+    mesh = boxmesh.make_box(10)
+    N = mesh.num_node
+    ctx = oracle.driver_setup(mesh)
+    wgold, dwgold, dwg = boxmesh.state_initial(mesh)
+    fac = (oracle.K_GAMMA - 1.0) / oracle.K_GAMMA
+    dwg[:3 * N] *= fac
+    dwg[4 * N:] *= fac
+    wga, dwga = oracle.alpha_states(N, wgold, dwgold, dwg)
+    F = oracle.assemble_system(ctx, wga, dwga, want_F=True)
+    blocks = oracle.assemble_system(ctx, wga, dwga, want_J=True)
+    _, it_jacobi, hist_jacobi = oracle.gmres(ctx["pattern"], blocks, F)
+    R = pc2_oracle.Pc2Oracle(oracle, mesh, ctx["pattern"], blocks, agg_cells=4, cheb_degree=10)
+    x, it, hist = R.gmres(F)
+    assert it % 20 == 0 and it <= it_jacobi and hist[-1] <= 1e-4 * hist[0]
+    assert hist[20] < hist_jacobi[20]                       # and it is ahead at the first test already
+    A = sp.bmat([[R.A00, R.A01], [R.A10, R.A11]]).tocsr()
+    res = np.linalg.norm(F[:4 * N] - A @ x[:4 * N])
+    assert abs(res - hist[-1]) <= 1e-8 * hist[0]
+    rng = np.random.default_rng(3)
+    a, b = rng.standard_normal(6 * N), rng.standard_normal(6 * N)
+    lin = R.apply(2.0 * a - 3.0 * b)[:4 * N] - (2.0 * R.apply(a) - 3.0 * R.apply(b))[:4 * N]
+    assert np.abs(lin).max() <= 1e-9 * np.abs(R.apply(a)[:4 * N]).max()
